@@ -1,0 +1,225 @@
+"""ctypes binding of libdvl_b200.so (include/dvl_b200.h).
+
+The CUDA library is the product; there is no other implementation behind these calls.  If the
+shared object is missing or no sm_100 device is present the calls raise -- loudly -- instead of
+computing anything on the host.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from typing import Optional
+
+import numpy as np
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libdvl_b200.so")
+
+DVL_OK = 0
+DVL_F32, DVL_BF16, DVL_F16 = 0, 1, 2
+PRECISION_FP32, PRECISION_BF16 = 0, 1
+FLAG_NORMALIZE_QUERIES, FLAG_NORMALIZE_GALLERY, FLAG_FULL_SORT = 1, 2, 4
+MAX_CLASSES = 16
+
+EXPORTS = (
+    "dvl_abi_version", "dvl_create", "dvl_destroy", "dvl_last_error", "dvl_workspace_bytes",
+    "dvl_launch_count", "dvl_eval_ranking", "dvl_eval_ranking_host", "dvl_rank_and_score", "dvl_similarity",
+)
+
+_STATUS = {-1: "DVL_ERR_INVALID", -2: "DVL_ERR_NO_DEVICE", -3: "DVL_ERR_CUDA", -4: "DVL_ERR_OOM",
+           -5: "DVL_ERR_UNSUPPORTED", -6: "DVL_ERR_OVERFLOW"}
+
+
+class DvlError(RuntimeError):
+    def __init__(self, code: int, message: str):
+        super().__init__(f"{_STATUS.get(code, code)}: {message}")
+        self.code = code
+
+
+_lib = None
+
+
+def lib() -> ctypes.CDLL:
+    """Loads the CUDA library (building is ``__graft_entry__.build()``'s job)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            f"{LIB_PATH} is missing: the sm_100a CUDA extension has not been built "
+            "(run `python -c 'import __graft_entry__ as g; g.build()'`). There is no CPU fallback.")
+    L = ctypes.CDLL(LIB_PATH)
+    c_void_p, c_int, c_i32, c_i64, c_u32 = ctypes.c_void_p, ctypes.c_int, ctypes.c_int32, ctypes.c_int64, ctypes.c_uint32
+    L.dvl_abi_version.restype = c_int
+    L.dvl_create.argtypes = [ctypes.POINTER(c_void_p), c_int]
+    L.dvl_destroy.argtypes = [c_void_p]
+    L.dvl_last_error.argtypes = [c_void_p]
+    L.dvl_last_error.restype = ctypes.c_char_p
+    L.dvl_workspace_bytes.argtypes = [c_void_p]
+    L.dvl_workspace_bytes.restype = ctypes.c_size_t
+    L.dvl_launch_count.argtypes = [c_void_p]
+    L.dvl_launch_count.restype = ctypes.c_uint64
+    L.dvl_eval_ranking.argtypes = [c_void_p, c_void_p, c_int, c_void_p, c_int, c_void_p, c_i64, c_i32, c_i32, c_i32,
+                                   c_i64, c_int, c_u32, c_void_p, c_void_p, c_void_p, c_void_p, c_i64, c_void_p,
+                                   c_void_p]
+    L.dvl_eval_ranking_host.argtypes = [c_void_p, c_void_p, c_int, c_void_p, c_int, c_void_p, c_i64, c_i32, c_i32,
+                                        c_i32, c_i64, c_int, c_u32, c_void_p, c_void_p, c_void_p]
+    L.dvl_rank_and_score.argtypes = [c_void_p, c_void_p, c_i64, c_void_p, c_i64, c_i32, c_i32, c_i64, c_void_p,
+                                     c_void_p, c_void_p, c_void_p, c_i64, c_void_p]
+    L.dvl_similarity.argtypes = [c_void_p, c_void_p, c_int, c_void_p, c_int, c_i64, c_i32, c_i32, c_int, c_u32,
+                                 c_void_p, c_i64, c_void_p]
+    for name in EXPORTS:
+        if name not in ("dvl_last_error", "dvl_workspace_bytes", "dvl_launch_count"):
+            getattr(L, name).restype = c_int
+    _lib = L
+    return L
+
+
+def _dtype_code(t: torch.dtype) -> int:
+    if t == torch.float32:
+        return DVL_F32
+    if t == torch.bfloat16:
+        return DVL_BF16
+    if t == torch.float16:
+        return DVL_F16
+    raise TypeError(f"unsupported embedding dtype {t}")
+
+
+def _np_dtype_code(a: np.ndarray) -> int:
+    if a.dtype == np.float32:
+        return DVL_F32
+    if a.dtype == np.float16:
+        return DVL_F16
+    raise TypeError(f"unsupported host embedding dtype {a.dtype}")
+
+
+class Context:
+    """One dvl_ctx bound to one CUDA device."""
+
+    def __init__(self, device: int = 0):
+        self._h = ctypes.c_void_p()
+        rc = lib().dvl_create(ctypes.byref(self._h), int(device))
+        if rc != DVL_OK:
+            self._h = ctypes.c_void_p()
+            raise DvlError(rc, f"dvl_create(device={device}) failed: an sm_100 (B200) device is required; "
+                               "there is no CPU fallback")
+        self.device = int(device)
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h:
+            lib().dvl_destroy(self._h)
+            self._h = ctypes.c_void_p()
+
+    def __del__(self):  # pragma: no cover
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc: int):
+        if rc != DVL_OK:
+            raise DvlError(rc, lib().dvl_last_error(self._h).decode("utf-8", "replace"))
+
+    @property
+    def launch_count(self) -> int:
+        return int(lib().dvl_launch_count(self._h))
+
+    @property
+    def workspace_bytes(self) -> int:
+        return int(lib().dvl_workspace_bytes(self._h))
+
+    def _stream(self) -> int:
+        return int(torch.cuda.current_stream(self.device).cuda_stream)
+
+    @staticmethod
+    def _ptr(t: Optional[torch.Tensor]):
+        return ctypes.c_void_p(t.data_ptr()) if t is not None else ctypes.c_void_p()
+
+    # ------------------------------------------------------------------------------------
+    def eval_ranking(self, gallery: torch.Tensor, queries: torch.Tensor, labels_u8: torch.Tensor, n_classes: int,
+                     top_n: int, precision: int = PRECISION_FP32, flags: int = 0, want_per_query: bool = False,
+                     ranked_cap: int = 0, want_scores: bool = False):
+        """gallery [N,D], queries [Q,D], labels uint8 [N]: all CUDA, contiguous.  Returns a dict with
+        ``mean`` (4 python floats) and optionally ``per_query`` [Q,4] f64, ``ranked_len`` [Q] i32,
+        ``ranked_idx`` [Q,ranked_cap] i32, ``scores`` [Q,N] f32 (device tensors)."""
+        assert gallery.is_cuda and queries.is_cuda and labels_u8.is_cuda
+        assert gallery.is_contiguous() and queries.is_contiguous() and labels_u8.is_contiguous()
+        assert labels_u8.dtype == torch.uint8
+        n, d = gallery.shape
+        q, d2 = queries.shape
+        if d != d2:
+            raise ValueError(f"embedding depth mismatch: gallery {d}, queries {d2}")
+        if labels_u8.numel() != n:
+            raise ValueError("labels and gallery differ in length")
+        dev = gallery.device
+        mean = (ctypes.c_double * 4)()
+        per_query = torch.empty((q, 4), dtype=torch.float64, device=dev) if want_per_query else None
+        ranked_len = torch.empty((q,), dtype=torch.int32, device=dev) if (ranked_cap > 0 or want_per_query) else None
+        ranked_idx = torch.full((q, ranked_cap), -1, dtype=torch.int32, device=dev) if ranked_cap > 0 else None
+        scores = torch.empty((q, n), dtype=torch.float32, device=dev) if want_scores else None
+        rc = lib().dvl_eval_ranking(self._h, self._ptr(gallery), _dtype_code(gallery.dtype), self._ptr(queries),
+                                    _dtype_code(queries.dtype), self._ptr(labels_u8), n, d, q, int(n_classes),
+                                    int(top_n), int(precision), int(flags), ctypes.cast(mean, ctypes.c_void_p),
+                                    self._ptr(per_query), self._ptr(ranked_len), self._ptr(ranked_idx),
+                                    int(ranked_cap), self._ptr(scores), ctypes.c_void_p(self._stream()))
+        self._check(rc)
+        return dict(mean=[float(x) for x in mean], per_query=per_query, ranked_len=ranked_len,
+                    ranked_idx=ranked_idx, scores=scores)
+
+    def eval_ranking_host(self, gallery: np.ndarray, queries: np.ndarray, labels_u8: np.ndarray, n_classes: int,
+                          top_n: int, precision: int = PRECISION_FP32, flags: int = 0,
+                          per_query_out: Optional[np.ndarray] = None):
+        """Host (ideally pinned) inputs; H2D copies happen inside the call."""
+        n, d = gallery.shape
+        q = queries.shape[0]
+        assert gallery.flags["C_CONTIGUOUS"] and queries.flags["C_CONTIGUOUS"] and labels_u8.dtype == np.uint8
+        mean = (ctypes.c_double * 4)()
+        pq = ctypes.c_void_p(per_query_out.ctypes.data) if per_query_out is not None else ctypes.c_void_p()
+        rc = lib().dvl_eval_ranking_host(self._h, ctypes.c_void_p(gallery.ctypes.data), _np_dtype_code(gallery),
+                                         ctypes.c_void_p(queries.ctypes.data), _np_dtype_code(queries),
+                                         ctypes.c_void_p(labels_u8.ctypes.data), n, d, q, int(n_classes), int(top_n),
+                                         int(precision), int(flags), ctypes.cast(mean, ctypes.c_void_p), pq,
+                                         ctypes.c_void_p(self._stream()))
+        self._check(rc)
+        return [float(x) for x in mean]
+
+    def rank_and_score(self, scores: torch.Tensor, labels_u8: torch.Tensor, n_classes: int, top_n: int,
+                       ranked_cap: int = 0):
+        assert scores.is_cuda and scores.dtype == torch.float32 and scores.stride(1) == 1
+        q, n = scores.shape
+        dev = scores.device
+        mean = (ctypes.c_double * 4)()
+        per_query = torch.empty((q, 4), dtype=torch.float64, device=dev)
+        ranked_len = torch.empty((q,), dtype=torch.int32, device=dev)
+        ranked_idx = torch.full((q, ranked_cap), -1, dtype=torch.int32, device=dev) if ranked_cap > 0 else None
+        rc = lib().dvl_rank_and_score(self._h, self._ptr(scores), int(scores.stride(0)), self._ptr(labels_u8), n, q,
+                                      int(n_classes), int(top_n), ctypes.cast(mean, ctypes.c_void_p),
+                                      self._ptr(per_query), self._ptr(ranked_len), self._ptr(ranked_idx),
+                                      int(ranked_cap), ctypes.c_void_p(self._stream()))
+        self._check(rc)
+        return dict(mean=[float(x) for x in mean], per_query=per_query, ranked_len=ranked_len, ranked_idx=ranked_idx)
+
+    def similarity(self, gallery: torch.Tensor, queries: torch.Tensor, precision: int = PRECISION_FP32,
+                   flags: int = 0) -> torch.Tensor:
+        assert gallery.is_cuda and queries.is_cuda and gallery.is_contiguous() and queries.is_contiguous()
+        n, d = gallery.shape
+        q = queries.shape[0]
+        out = torch.empty((q, n), dtype=torch.float32, device=gallery.device)
+        rc = lib().dvl_similarity(self._h, self._ptr(gallery), _dtype_code(gallery.dtype), self._ptr(queries),
+                                  _dtype_code(queries.dtype), n, d, q, int(precision), int(flags), self._ptr(out), n,
+                                  ctypes.c_void_p(self._stream()))
+        self._check(rc)
+        return out
+
+
+_contexts = {}
+
+
+def context(device: Optional[int] = None) -> Context:
+    """Process-wide context per device."""
+    if device is None:
+        device = torch.cuda.current_device() if torch.cuda.is_available() else 0
+    if device not in _contexts:
+        _contexts[device] = Context(device)
+    return _contexts[device]

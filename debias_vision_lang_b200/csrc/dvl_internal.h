@@ -1,0 +1,133 @@
+// Host-side internals shared by the translation units of libdvl_b200.so.
+#pragma once
+
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/dvl_b200.h"
+
+namespace dvl {
+
+struct Ctx;
+
+// Grow-only device buffer owned by the context.
+struct DevBuf {
+  void* ptr = nullptr;
+  size_t bytes = 0;
+};
+
+struct Ctx {
+  int device = 0;
+  int num_sms = 0;
+  std::string err;
+  uint64_t launches = 0;
+  size_t ws_bytes = 0;
+  // named workspace buffers
+  DevBuf gal_planes, qry_planes, gal_inv_norm, qry_inv_norm;
+  DevBuf keys[2], labs[2], idxs[2];
+  DevBuf tile_hist, class_counts, log_tab, per_query, mean_dev, scores_tmp, seg_len;
+  DevBuf h_gallery, h_queries, h_labels;   // staging for the host-input entry point
+  double* mean_pinned = nullptr;           // 4 doubles, pinned host
+  int64_t log_tab_len = 0;
+  // driver entry point for tensor-map encoding (resolved once, no -lcuda link dependency)
+  void* encode_tiled = nullptr;
+  bool gemm_attr_set = false;
+};
+
+int set_error(Ctx* c, int code, const char* fmt, ...);
+int ensure(Ctx* c, DevBuf& b, size_t bytes);
+
+#define DVL_CUDA(ctx, call)                                                                         \
+  do {                                                                                              \
+    cudaError_t e__ = (call);                                                                       \
+    if (e__ != cudaSuccess)                                                                         \
+      return dvl::set_error((ctx), DVL_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), \
+                            __FILE__, __LINE__);                                                    \
+  } while (0)
+
+#define DVL_TRY(expr)            \
+  do {                           \
+    int rc__ = (expr);           \
+    if (rc__ != DVL_OK) return rc__; \
+  } while (0)
+
+#define DVL_LAUNCH_CHECK(ctx, what)                                                                  \
+  do {                                                                                               \
+    (ctx)->launches++;                                                                               \
+    cudaError_t e__ = cudaGetLastError();                                                            \
+    if (e__ != cudaSuccess)                                                                          \
+      return dvl::set_error((ctx), DVL_ERR_CUDA, "launch of %s failed: %s", what, cudaGetErrorString(e__)); \
+  } while (0)
+
+// ---- prep.cu ---------------------------------------------------------------------------
+// rows [r, d] of `dtype` -> `planes` bf16 planes [planes][r][dp] (dp = padded row pitch, zero
+// filled) and, if inv_norm != nullptr, 1/||row||_2.
+int launch_split_rows(Ctx* c, const void* src, int dtype, int64_t rows, int d, int dp, int planes,
+                      __nv_bfloat16* dst, float* inv_norm, cudaStream_t st);
+int launch_class_counts(Ctx* c, const uint8_t* labels, int64_t n, int n_classes, unsigned long long* counts,
+                        cudaStream_t st);
+// table[i] = ln(i) for i in [0, len) with table[0] = 0
+int ensure_log_table(Ctx* c, int64_t len, cudaStream_t st);
+
+// ---- gemm.cu ---------------------------------------------------------------------------
+struct GemmArgs {
+  const __nv_bfloat16* qry_planes;  // [planes][q][dp]
+  const __nv_bfloat16* gal_planes;  // [planes][n][dp]
+  int planes;                       // 1 (bf16) or 3 (fp32 via bf16x3)
+  int64_t n;
+  int q;
+  int d;       // logical depth
+  int dp;      // row pitch (elements), multiple of 8
+  const float* qry_scale;  // [q] or nullptr (1/||t_q||)
+  const float* gal_scale;  // [n] or nullptr (1/||g_i||)
+  // outputs (any may be null)
+  uint32_t* keys;   // [q][ldk]
+  int64_t ldk;
+  float* scores;    // [q][lds]
+  int64_t lds;
+};
+int launch_sim_gemm(Ctx* c, const GemmArgs& a, cudaStream_t st);
+
+// ---- segsort.cu ------------------------------------------------------------------------
+// Stable ascending LSD radix sort of q independent segments of n 32-bit keys (pitch ldk).
+// Payloads: the gallery label (u8, looked up by position in the first pass) and, optionally,
+// the position itself (i32).  On return *out_buf says which of the two ping-pong buffers
+// holds the result.
+struct SortArgs {
+  uint32_t* keys[2];
+  uint8_t* labs[2];
+  int32_t* idxs[2];   // both null when ranked indices are not requested
+  const uint8_t* gallery_labels;
+  int64_t n;
+  int64_t ldk;
+  int q;
+};
+int launch_segmented_sort(Ctx* c, const SortArgs& a, int* out_buf, cudaStream_t st);
+int launch_scores_to_keys(Ctx* c, const float* scores, int64_t lds, uint32_t* keys, int64_t ldk, int64_t n, int q,
+                          cudaStream_t st);
+
+// ---- metrics.cu ------------------------------------------------------------------------
+struct MetricArgs {
+  const uint32_t* keys;   // sorted keys [q][ldk] (used to find m when top_n < n), may be null if top_n >= n
+  const uint8_t* labs;    // ranked labels [q][ldl]
+  int64_t ldk, ldl;
+  int64_t n_avail;        // ranked rows available per query (n for the full sort)
+  int64_t n_gallery;      // N of the whole gallery (dem_par denominator)
+  int64_t top_n;
+  int q;
+  int n_classes;
+  const unsigned long long* class_counts;  // [n_classes], global
+  const double* log_tab;                   // ln(i)
+  double* per_query;                       // [q][4]
+  int32_t* ranked_len;                     // [q] or null
+};
+int launch_metrics(Ctx* c, const MetricArgs& a, cudaStream_t st);
+int launch_mean(Ctx* c, const double* per_query, int q, double* mean_dev, cudaStream_t st);
+int launch_copy_ranked(Ctx* c, const int32_t* idx_sorted, int64_t ldi, const int32_t* ranked_len, int q,
+                       int32_t* out, int64_t cap, cudaStream_t st);
+
+}  // namespace dvl

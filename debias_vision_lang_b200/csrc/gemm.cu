@@ -1,0 +1,280 @@
+// Similarity stage (measuring_bias.py:114 for all queries at once):
+//   S[q, i] = sum_k T[q, k] * G[i, k]
+// as ONE tcgen05 GEMM instead of Q fp32 mat-vecs.  sm_100a only.
+//
+// Mapping.  UMMA M (TMEM lanes)  = 128 queries   -> an epilogue thread owns ONE query row
+//           UMMA N (TMEM columns) = 256 gallery rows
+//           K-blocks of 64 bf16 (= one 128-byte swizzle row), 4 x tcgen05.mma (K=16) each.
+// Both operands are K-major in memory (row-major [rows, D]), loaded by TMA with the
+// 128-byte swizzle straight into the canonical UMMA layout; no transposes anywhere.
+//
+// Persistent, warp-specialised CTA (one per SM):
+//   warp 0      TMA producer (one lane)      full/empty mbarrier ring, kStages deep
+//   warp 1      TMEM allocator + MMA issuer (one lane), double-buffered fp32 accumulators
+//               (2 x 256 TMEM columns) so the epilogue of tile t overlaps the MMAs of t+1
+//   warps 2..5  epilogue: tcgen05.ld 32 lanes x 32 columns -> fused scale (L2 normalisation)
+//               -> ranking key / fp32 score -> 128-byte row segments to HBM
+//
+// fp32 mode: operands arrive as three exact bf16 planes each; the K loop runs over the six
+// (i, j) plane pairs with i + j <= 4, smallest terms first, all into the same accumulator.
+//
+// Tiles are ordered gallery-block major so that CTAs running at the same time share the
+// gallery block (read from HBM once, then L2 hits) while the small query matrix stays
+// L2-resident.
+#include <stdarg.h>
+
+#include "dvl_common.cuh"
+#include "dvl_internal.h"
+
+namespace dvl {
+
+namespace {
+
+constexpr int BM = 128;            // queries per tile
+constexpr int BN = 256;            // gallery rows per tile
+constexpr int BK = 64;             // bf16 per k-block (128 B)
+constexpr int UMMA_K = 16;
+constexpr int kStages = 4;
+constexpr int kABytes = BM * BK * 2;   // 16 KB
+constexpr int kBBytes = BN * BK * 2;   // 32 KB
+constexpr int kStageBytes = kABytes + kBBytes;
+constexpr int kTmemCols = 512;         // 2 accumulator buffers x 256 columns
+constexpr int kNumThreads = 192;       // 6 warps
+constexpr int kEpiThreads = 128;
+constexpr size_t kSmemBytes = 1024 /*align slack*/ + (size_t)kStages * kStageBytes + 256 /*barriers*/;
+
+// plane pairs (query plane, gallery plane), smallest product magnitude first
+__constant__ int c_term_a[6] = {0, 1, 2, 0, 1, 0};
+__constant__ int c_term_b[6] = {2, 1, 0, 1, 0, 0};
+
+struct KernelParams {
+  int64_t n;
+  int q;
+  int n_qtiles;
+  int64_t n_tiles;
+  int k_blocks;     // ceil(d / 64)
+  int n_terms;      // 1 or 6
+  const float* qry_scale;
+  const float* gal_scale;
+  uint32_t* keys;
+  int64_t ldk;
+  float* scores;
+  int64_t lds;
+};
+
+__global__ void __launch_bounds__(kNumThreads, 1)
+sim_gemm_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_g,
+                const KernelParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  // 128-byte-swizzle atoms need 1024-byte aligned tiles
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bar_base = smem_base + kStages * kStageBytes;
+  // barrier addresses
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (kStages + s); };
+  auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * kStages + a); };
+  auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * kStages + 2 + a); };
+  const uint32_t tmem_slot = bar_base + 8u * (2 * kStages + 4);
+  volatile uint32_t* tmem_slot_ptr =
+      reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(tfull_bar(a), 1);
+      mbar_init(tempty_bar(a), kEpiThreads);
+    }
+    fence_mbar_init();
+    tma_prefetch_desc(&map_q);
+    tma_prefetch_desc(&map_g);
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, kTmemCols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  const int iters_per_tile = p.k_blocks * p.n_terms;
+
+  if (warp == 0) {
+    // ------------------------------ TMA producer ------------------------------
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int64_t t = blockIdx.x; t < p.n_tiles; t += gridDim.x) {
+        const int qt = (int)(t % p.n_qtiles);
+        const int64_t gb = t / p.n_qtiles;
+        for (int it = 0; it < iters_per_tile; ++it) {
+          const int term = it / p.k_blocks;
+          const int kb = it - term * p.k_blocks;
+          const int pa = (p.n_terms == 1) ? 0 : c_term_a[term];
+          const int pb = (p.n_terms == 1) ? 0 : c_term_b[term];
+          mbar_wait(empty_bar(stage), phase ^ 1u);
+          mbar_arrive_expect_tx(full_bar(stage), kStageBytes);
+          const uint32_t sa = smem_base + stage * kStageBytes;
+          tma_load_3d(sa, &map_q, full_bar(stage), kb * BK, qt * BM, pa);
+          tma_load_3d(sa + kABytes, &map_g, full_bar(stage), kb * BK, (int)(gb * BN), pb);
+          if (++stage == kStages) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------ MMA issuer ------------------------------
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(BM, BN);
+      int stage = 0;
+      uint32_t phase = 0;
+      int as = 0;
+      uint32_t aphase = 0;
+      for (int64_t t = blockIdx.x; t < p.n_tiles; t += gridDim.x) {
+        mbar_wait(tempty_bar(as), aphase ^ 1u);   // epilogue has drained this accumulator
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + (uint32_t)(as * BN);
+        for (int it = 0; it < iters_per_tile; ++it) {
+          mbar_wait(full_bar(stage), phase);      // TMA bytes have landed
+          tc_fence_after();
+          const uint32_t sa = smem_base + stage * kStageBytes;
+          const uint32_t sb = sa + kABytes;
+#pragma unroll
+          for (int k = 0; k < BK / UMMA_K; ++k) {
+            const uint64_t da = umma_desc_sw128(sa + k * (UMMA_K * 2));
+            const uint64_t db = umma_desc_sw128(sb + k * (UMMA_K * 2));
+            umma_bf16_ss(tmem_d, da, db, idesc, (it > 0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit(empty_bar(stage));          // smem slot free once these MMAs retire
+          if (++stage == kStages) { stage = 0; phase ^= 1u; }
+        }
+        umma_commit(tfull_bar(as));               // accumulator complete -> epilogue
+        as ^= 1;
+        if (as == 0) aphase ^= 1u;
+      }
+    }
+    __syncwarp();
+  } else {
+    // ------------------------------ epilogue ------------------------------
+    const int quarter = warp & 3;                 // TMEM lanes this warp may touch: 32*quarter..+31
+    const int row_in_tile = quarter * 32 + lane;
+    int as = 0;
+    uint32_t aphase = 0;
+    for (int64_t t = blockIdx.x; t < p.n_tiles; t += gridDim.x) {
+      const int qt = (int)(t % p.n_qtiles);
+      const int64_t gb = t / p.n_qtiles;
+      const int qrow = qt * BM + row_in_tile;
+      const bool row_ok = qrow < p.q;
+      const float qs = (p.qry_scale != nullptr && row_ok) ? __ldg(p.qry_scale + qrow) : 1.0f;
+      mbar_wait(tfull_bar(as), aphase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + (uint32_t)(as * BN) + ((uint32_t)(quarter * 32) << 16);
+#pragma unroll 1
+      for (int chunk = 0; chunk < BN / 32; ++chunk) {
+        uint32_t v[32];
+        tmem_ld_32x32(taddr + (uint32_t)(chunk * 32), v);
+        tmem_ld_wait();
+        const int64_t col0 = gb * BN + chunk * 32;
+        if (p.qry_scale != nullptr || p.gal_scale != nullptr) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            float s = __uint_as_float(v[j]) * qs;
+            if (p.gal_scale != nullptr) s *= (col0 + j < p.n) ? __ldg(p.gal_scale + col0 + j) : 0.f;
+            v[j] = __float_as_uint(s);
+          }
+        }
+        if (row_ok) {
+          if (p.scores != nullptr) {
+            float* dst = p.scores + (int64_t)qrow * p.lds + col0;
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) st_global_v4(dst + j, v[j], v[j + 1], v[j + 2], v[j + 3]);
+          }
+          if (p.keys != nullptr) {
+            uint32_t* dst = p.keys + (int64_t)qrow * p.ldk + col0;
+#pragma unroll
+            for (int j = 0; j < 32; j += 4)
+              st_global_v4(dst + j, score_to_key(__uint_as_float(v[j])), score_to_key(__uint_as_float(v[j + 1])),
+                           score_to_key(__uint_as_float(v[j + 2])), score_to_key(__uint_as_float(v[j + 3])));
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(tempty_bar(as));
+      as ^= 1;
+      if (as == 0) aphase ^= 1u;
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, kTmemCols);
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+int make_map(Ctx* c, CUtensorMap* map, const void* base, int64_t rows, int d, int dp, int planes, int box_rows) {
+  if (c->encode_tiled == nullptr) {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+    if (e != cudaSuccess || fn == nullptr || qres != cudaDriverEntryPointSuccess)
+      return set_error(c, DVL_ERR_CUDA, "cuTensorMapEncodeTiled entry point unavailable: %s", cudaGetErrorString(e));
+    c->encode_tiled = fn;
+  }
+  // logical depth d (not the pitch): columns >= d are zero-filled by TMA
+  cuuint64_t dims[3] = {(cuuint64_t)d, (cuuint64_t)rows, (cuuint64_t)planes};
+  cuuint64_t strides[2] = {(cuuint64_t)dp * 2ull, (cuuint64_t)rows * (cuuint64_t)dp * 2ull};
+  cuuint32_t box[3] = {(cuuint32_t)BK, (cuuint32_t)box_rows, 1u};
+  cuuint32_t estr[3] = {1u, 1u, 1u};
+  CUresult r = ((EncodeTiledFn)c->encode_tiled)(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base),
+                                                dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                                CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                                                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return set_error(c, DVL_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+  return DVL_OK;
+}
+
+}  // namespace
+
+int launch_sim_gemm(Ctx* c, const GemmArgs& a, cudaStream_t st) {
+  if (a.dp % 8 != 0) return set_error(c, DVL_ERR_INVALID, "plane row pitch must be a multiple of 8 elements");
+  if (a.n <= 0 || a.q <= 0 || a.d <= 0) return set_error(c, DVL_ERR_INVALID, "empty similarity problem");
+  if (a.n > 0x7FFFFF00ll) return set_error(c, DVL_ERR_UNSUPPORTED, "gallery shard larger than 2^31 rows");
+  CUtensorMap map_q, map_g;
+  DVL_TRY(make_map(c, &map_q, a.qry_planes, a.q, a.d, a.dp, a.planes, BM));
+  DVL_TRY(make_map(c, &map_g, a.gal_planes, a.n, a.d, a.dp, a.planes, BN));
+  KernelParams p;
+  p.n = a.n;
+  p.q = a.q;
+  p.n_qtiles = (a.q + BM - 1) / BM;
+  p.n_tiles = (int64_t)p.n_qtiles * ((a.n + BN - 1) / BN);
+  p.k_blocks = (a.d + BK - 1) / BK;
+  p.n_terms = (a.planes == 3) ? 6 : 1;
+  p.qry_scale = a.qry_scale;
+  p.gal_scale = a.gal_scale;
+  p.keys = a.keys;
+  p.ldk = a.ldk;
+  p.scores = a.scores;
+  p.lds = a.lds;
+  if (a.keys != nullptr && (a.ldk % 4 != 0 || a.ldk < ((a.n + BN - 1) / BN) * BN))
+    return set_error(c, DVL_ERR_INVALID, "key pitch must cover whole 256-column tiles");
+  if (a.scores != nullptr && (a.lds % 4 != 0 || a.lds < ((a.n + BN - 1) / BN) * BN))
+    return set_error(c, DVL_ERR_INVALID, "score pitch must cover whole 256-column tiles");
+  if (!c->gemm_attr_set) {
+    DVL_CUDA(c, cudaFuncSetAttribute(sim_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
+    c->gemm_attr_set = true;
+  }
+  int64_t grid = p.n_tiles < c->num_sms ? p.n_tiles : c->num_sms;
+  sim_gemm_kernel<<<(unsigned)grid, kNumThreads, kSmemBytes, st>>>(map_q, map_g, p);
+  DVL_LAUNCH_CHECK(c, "sim_gemm_kernel");
+  return DVL_OK;
+}
+
+}  // namespace dvl

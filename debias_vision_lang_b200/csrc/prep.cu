@@ -1,0 +1,155 @@
+// Operand preparation for the similarity stage and the query-independent label statistics.
+//
+//  * split_rows:   embeddings -> bf16 planes.  bf16 mode: one plane (round to nearest even).
+//                  fp32 mode: x == b1 + b2 + b3 exactly, three bf16 planes, so that the six
+//                  product terms a_i*b_j (i+j<=4) accumulated in fp32 on the tensor cores
+//                  reproduce the fp32 similarity of measuring_bias.py:114 to ~2^-24.
+//                  Also emits 1/||row|| for the fused normalisation (measuring_bias.py:79).
+//  * class_counts: Counter(df.label)  (measuring_bias.py:23,56) -- once per call instead of once
+//                  per query and per metric.
+//  * log table:    ln(i), i < len, fp64 -- NDKL needs ln h, ln i and log2(i+1) per ranked row.
+#include "dvl_common.cuh"
+#include "dvl_internal.h"
+
+namespace dvl {
+
+template <typename T>
+__device__ __forceinline__ float load_as_float(const T* p);
+template <>
+__device__ __forceinline__ float load_as_float<float>(const float* p) { return __ldg(p); }
+template <>
+__device__ __forceinline__ float load_as_float<__nv_bfloat16>(const __nv_bfloat16* p) {
+  return __bfloat162float(*p);
+}
+template <>
+__device__ __forceinline__ float load_as_float<__half>(const __half* p) { return __half2float(*p); }
+
+// One warp per row; lane handles 4 consecutive elements per step (coalesced 512 B / warp for fp32).
+template <typename T, int PLANES>
+__global__ void __launch_bounds__(256) split_rows_kernel(const T* __restrict__ src, int64_t rows, int d, int dp,
+                                                         __nv_bfloat16* __restrict__ dst,
+                                                         float* __restrict__ inv_norm) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warps_total = (int64_t)gridDim.x * (blockDim.x >> 5);
+  const int64_t plane_stride = rows * (int64_t)dp;
+  for (int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); row < rows; row += warps_total) {
+    const T* s = src + row * (int64_t)d;
+    __nv_bfloat16* o = dst + row * (int64_t)dp;
+    float ss = 0.f;
+    for (int c0 = lane * 4; c0 < dp; c0 += 128) {
+      float x[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) x[j] = (c0 + j < d) ? load_as_float<T>(s + c0 + j) : 0.f;
+      __align__(8) __nv_bfloat16 b[PLANES][4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        ss = fmaf(x[j], x[j], ss);
+        float r = x[j];
+#pragma unroll
+        for (int p = 0; p < PLANES; ++p) {
+          b[p][j] = __float2bfloat16_rn(r);
+          r = r - __bfloat162float(b[p][j]);   // exact: the residual of a round-to-8-bits fits fp32
+        }
+      }
+#pragma unroll
+      for (int p = 0; p < PLANES; ++p)
+        *reinterpret_cast<uint2*>(o + p * plane_stride + c0) = *reinterpret_cast<const uint2*>(b[p]);
+    }
+    if (inv_norm != nullptr) {
+#pragma unroll
+      for (int off = 16; off > 0; off >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, off);
+      if (lane == 0) inv_norm[row] = 1.0f / sqrtf(ss);
+    }
+  }
+}
+
+template <typename T>
+static int launch_split_t(Ctx* c, const T* src, int64_t rows, int d, int dp, int planes, __nv_bfloat16* dst,
+                          float* inv_norm, cudaStream_t st) {
+  const int warps_per_block = 8;
+  int64_t blocks = (rows + warps_per_block - 1) / warps_per_block;
+  int64_t cap = (int64_t)c->num_sms * 16;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  if (planes == 1)
+    split_rows_kernel<T, 1><<<(unsigned)blocks, 256, 0, st>>>(src, rows, d, dp, dst, inv_norm);
+  else
+    split_rows_kernel<T, 3><<<(unsigned)blocks, 256, 0, st>>>(src, rows, d, dp, dst, inv_norm);
+  DVL_LAUNCH_CHECK(c, "split_rows_kernel");
+  return DVL_OK;
+}
+
+int launch_split_rows(Ctx* c, const void* src, int dtype, int64_t rows, int d, int dp, int planes,
+                      __nv_bfloat16* dst, float* inv_norm, cudaStream_t st) {
+  if (planes != 1 && planes != 3) return set_error(c, DVL_ERR_INVALID, "planes must be 1 or 3");
+  if (dp % 4 != 0) return set_error(c, DVL_ERR_INVALID, "row pitch must be a multiple of 4");
+  switch (dtype) {
+    case DVL_F32: return launch_split_t<float>(c, (const float*)src, rows, d, dp, planes, dst, inv_norm, st);
+    case DVL_BF16:
+      return launch_split_t<__nv_bfloat16>(c, (const __nv_bfloat16*)src, rows, d, dp, planes, dst, inv_norm, st);
+    case DVL_F16: return launch_split_t<__half>(c, (const __half*)src, rows, d, dp, planes, dst, inv_norm, st);
+    default: return set_error(c, DVL_ERR_INVALID, "unknown dtype %d", dtype);
+  }
+}
+
+// ----------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) class_counts_kernel(const uint8_t* __restrict__ labels, int64_t n,
+                                                           int n_classes, unsigned long long* __restrict__ counts,
+                                                           unsigned int* __restrict__ bad) {
+  __shared__ unsigned int sh[kMaxClasses];
+  if (threadIdx.x < kMaxClasses) sh[threadIdx.x] = 0;
+  __syncthreads();
+  unsigned int local[kMaxClasses];
+#pragma unroll
+  for (int k = 0; k < kMaxClasses; ++k) local[k] = 0;
+  unsigned int oob = 0;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int l = labels[i];
+    oob |= (l >= n_classes);
+#pragma unroll
+    for (int k = 0; k < kMaxClasses; ++k) local[k] += (l == k);
+  }
+#pragma unroll
+  for (int k = 0; k < kMaxClasses; ++k) {
+    unsigned int v = local[k];
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+    if ((threadIdx.x & 31) == 0 && v) atomicAdd(&sh[k], v);
+  }
+  if (oob) atomicOr(bad, 1u);
+  __syncthreads();
+  if (threadIdx.x < n_classes && sh[threadIdx.x]) atomicAdd(&counts[threadIdx.x], (unsigned long long)sh[threadIdx.x]);
+}
+
+int launch_class_counts(Ctx* c, const uint8_t* labels, int64_t n, int n_classes, unsigned long long* counts,
+                        cudaStream_t st) {
+  // counts has kMaxClasses + 1 slots; the last one is the out-of-range flag
+  DVL_CUDA(c, cudaMemsetAsync(counts, 0, sizeof(unsigned long long) * (kMaxClasses + 1), st));
+  int64_t blocks = (n + 256 * 16 - 1) / (256 * 16);
+  if (blocks > (int64_t)c->num_sms * 8) blocks = (int64_t)c->num_sms * 8;
+  if (blocks < 1) blocks = 1;
+  class_counts_kernel<<<(unsigned)blocks, 256, 0, st>>>(labels, n, n_classes, counts,
+                                                        reinterpret_cast<unsigned int*>(counts + kMaxClasses));
+  DVL_LAUNCH_CHECK(c, "class_counts_kernel");
+  return DVL_OK;
+}
+
+// ----------------------------------------------------------------------------------------
+__global__ void log_table_kernel(double* __restrict__ tab, int64_t len) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < len; i += (int64_t)gridDim.x * blockDim.x)
+    tab[i] = (i == 0) ? 0.0 : log((double)i);
+}
+
+int ensure_log_table(Ctx* c, int64_t len, cudaStream_t st) {
+  if (len <= c->log_tab_len) return DVL_OK;
+  int64_t want = len + len / 8 + 1024;
+  DVL_TRY(ensure(c, c->log_tab, (size_t)want * sizeof(double)));
+  int64_t blocks = (want + 255) / 256;
+  if (blocks > (int64_t)c->num_sms * 8) blocks = (int64_t)c->num_sms * 8;
+  log_table_kernel<<<(unsigned)blocks, 256, 0, st>>>((double*)c->log_tab.ptr, want);
+  DVL_LAUNCH_CHECK(c, "log_table_kernel");
+  c->log_tab_len = want;
+  return DVL_OK;
+}
+
+}  // namespace dvl

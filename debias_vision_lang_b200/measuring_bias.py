@@ -1,0 +1,275 @@
+"""Host-side mirror of the reference's ``debias_clip/measuring_bias.py`` interface for the
+bias-measurement hot path.  Same function names, argument meaning, return shapes and error
+behaviour; the arithmetic is done by hand-written sm_100a CUDA behind the C ABI
+(``include/dvl_b200.h``).  No CPU fallback: without the CUDA library and a B200 these raise.
+
+Mapping to the reference (``/root/reference/debias_clip/measuring_bias.py``):
+
+===============================  ==========================  ===================================
+here                             reference                   what changed
+===============================  ==========================  ===================================
+``normalized_discounted_KL``     ``:17-44``                  ranking + NDKL on the GPU (1 query)
+``compute_skew_metrics``         ``:47-72``                  ranking + MaxSkew on the GPU
+``get_prompt_embeddings``        ``:75-82``                  unchanged semantics (torch ops)
+``get_labels_img_embeddings``    ``:85-99``                  no per-batch ``.cpu()`` round trip
+``eval_ranking``                 ``:102-119``                ONE fused pass for all queries
+``gen_prompts``                  ``:122-133``                same 319 prompts, built in
+``measure_bias``                 ``:139-156``                both evaluations from one pass;
+                                                             ``img_preproc``/``tokenizer`` optional
+===============================  ==========================  ===================================
+"""
+from __future__ import annotations
+
+import math
+from typing import Callable, Dict, List, Optional, Tuple, Union
+
+import numpy as np
+import torch
+
+from . import _capi
+
+__all__ = [
+    "normalized_discounted_KL", "compute_skew_metrics", "get_prompt_embeddings", "get_labels_img_embeddings",
+    "eval_ranking", "gen_prompts", "measure_bias", "evaluate", "DEFAULT_OPTS", "PROMPT_TEMPLATES", "PROMPT_CONCEPTS",
+]
+
+# data/prompt_templates.csv of the reference (11 non-blank templates x 29 concepts), kept in the
+# order gen_prompts (measuring_bias.py:122-133) walks them; checked against the reference's own
+# output in tests/golden/prompts.json.
+PROMPT_TEMPLATES = (
+    "This is the face of a {} person", "This is a photo of a {} person", "This person is {}", "A {} person",
+    "A {} individual", "This individual is {}", "Photo of a {}", "{}", "This is a {}", "This is the photo of a {}",
+    "A {}",
+)
+PROMPT_CONCEPTS = (
+    "good", "kind", "successful", "noncriminal", "nonviolent", "moral", "rich", "honest", "smart", "evil", "unkind",
+    "unsuccessful", "criminal", "violent", "immoral", "poor", "dishonest", "dumb", "clever", "stupid", "hardworking",
+    "lazy", "nasty", "trustworthy", "untrustworthy", "caring", "dangerous", "heroic", "villainous",
+)
+
+# ``opts`` is the reference's unused extension point (measuring_bias.py:136,139); keys understood here:
+#   precision          "fp32" (default; bf16x3 split, matches the reference's fp32 mat-vec) | "bf16"
+#   normalize_gallery  False (default, as eval_ranking) | True (cosine similarity)
+#   topn               overrides measure_bias's top-n (reference: whole gallery, 1.0)
+#   dataset            a ready dataset object instead of FairFace(mode="val", ...)
+#   batch_size / num_workers   DataLoader settings (reference: 256 / 6)
+DEFAULT_OPTS: dict = dict()
+
+_PRECISIONS = {"fp32": _capi.PRECISION_FP32, "bf16": _capi.PRECISION_BF16}
+
+
+def gen_prompts() -> List[str]:
+    """The 319 prompts of the reference's prompt array (measuring_bias.py:122-133)."""
+    return [t.format(c) for t in PROMPT_TEMPLATES for c in PROMPT_CONCEPTS]
+
+
+# ---------------------------------------------------------------------------------------------
+# label handling (Counter(df.label) / datasets.py:30-46)
+# ---------------------------------------------------------------------------------------------
+def _encode_labels(labels_list, need_contiguous: bool) -> Tuple[np.ndarray, int]:
+    """labels -> uint8 codes 0..C-1 over the distinct values present (what Counter sees).
+    NDKL in the reference indexes its count array with the raw label (measuring_bias.py:33-34),
+    so labels outside 0..C-1 raise IndexError there; we raise the same."""
+    lab = np.asarray(labels_list)
+    if lab.ndim != 1:
+        lab = lab.reshape(-1)
+    values, codes = np.unique(lab, return_inverse=True)
+    n_classes = len(values)
+    if n_classes > _capi.MAX_CLASSES:
+        raise ValueError(f"{n_classes} distinct labels; at most {_capi.MAX_CLASSES} attribute classes are supported")
+    if need_contiguous:
+        as_int = values.astype(np.int64)
+        if not np.array_equal(as_int, np.arange(n_classes)):
+            raise IndexError(f"labels must be the contiguous ints 0..{n_classes - 1} for ndkl "
+                             "(the reference indexes top_n_label_counts[label])")
+    return codes.astype(np.uint8), n_classes
+
+
+def _resolve_topn(topn: Union[int, float], n: int) -> int:
+    # Float -> proportion of the dataset, Int -> top n            (measuring_bias.py:107-110)
+    if isinstance(topn, float):
+        topn = math.ceil(n * topn)
+    topn = int(topn)
+    if topn < 1:
+        raise ZeroDivisionError("top_n must be >= 1 (the reference divides by top_n)")
+    return topn
+
+
+def _device_of(t: torch.Tensor) -> torch.device:
+    if t.is_cuda:
+        return t.device
+    if not torch.cuda.is_available():
+        raise RuntimeError("the bias-measurement path runs on a B200 only: no CUDA device is visible and "
+                           "there is no CPU fallback")
+    return torch.device("cuda", torch.cuda.current_device())
+
+
+def _as_device_matrix(x, dev: torch.device) -> torch.Tensor:
+    t = x if isinstance(x, torch.Tensor) else torch.as_tensor(np.asarray(x))
+    if t.dtype not in (torch.float32, torch.float16, torch.bfloat16):
+        t = t.float()
+    return t.detach().to(dev).contiguous()
+
+
+_last = {"key": None, "value": None}
+
+
+def evaluate(labels_list, image_embeddings, prompts_embeddings, topn: Union[int, float] = 1.0,
+             opts: Optional[dict] = None, need_contiguous: bool = True, per_query: bool = False,
+             ranked_cap: int = 0) -> Dict[str, object]:
+    """One fused pass over the hot path for all queries: similarity, ranking, label histograms,
+    MaxSkew and NDKL.  Returns ``{"maxskew": {...}, "ndkl": {...}}`` (+ per-query tensors when asked)."""
+    opts = dict(opts or {})
+    if len(image_embeddings) != len(labels_list):
+        raise ValueError("All arrays must be of the same length")     # what pd.DataFrame raises at :115
+    if len(prompts_embeddings) == 0:
+        raise ZeroDivisionError("division by zero")                   # sum(v)/len(v) at :119 never reached
+    n = len(image_embeddings)
+    top_n = _resolve_topn(topn, n)
+    img = image_embeddings if isinstance(image_embeddings, torch.Tensor) else torch.as_tensor(np.asarray(image_embeddings))
+    dev = _device_of(img)
+    g = _as_device_matrix(img, dev)
+    t = _as_device_matrix(prompts_embeddings, dev)
+    if t.dim() == 1:
+        t = t[None, :]
+    codes, n_classes = _encode_labels(labels_list, need_contiguous)
+    lab = torch.from_numpy(codes).to(dev)
+    precision = _PRECISIONS[opts.get("precision", "fp32")]
+    flags = 0
+    if opts.get("normalize_gallery", False):
+        flags |= _capi.FLAG_NORMALIZE_GALLERY
+    if opts.get("normalize_queries", False):
+        flags |= _capi.FLAG_NORMALIZE_QUERIES
+    if opts.get("full_sort", False):
+        flags |= _capi.FLAG_FULL_SORT
+    with torch.cuda.device(dev):
+        res = _capi.context(dev.index).eval_ranking(g, t, lab, n_classes, top_n, precision, flags,
+                                                    want_per_query=per_query, ranked_cap=ranked_cap)
+    m = res["mean"]
+    out = {"maxskew": {"eq_opp": m[0], "dem_par": m[1]}, "ndkl": {"eq_opp": m[2], "dem_par": m[3]}}
+    if per_query:
+        out["per_query"] = res["per_query"]
+        out["ranked_len"] = res["ranked_len"]
+    if ranked_cap:
+        out["ranked_idx"] = res["ranked_idx"]
+        out["ranked_len"] = res["ranked_len"]
+    return out
+
+
+def eval_ranking(labels_list: np.ndarray, image_embeddings: torch.Tensor, prompts_embeddings: torch.Tensor,
+                 evaluation: str = "maxskew", topn: Union[int, float] = 1.0, opts: Optional[dict] = None):
+    """Drop-in for ``eval_ranking`` (measuring_bias.py:102-119): mean over the queries of the
+    requested metric for both desired distributions -> ``{"eq_opp": float, "dem_par": float}``.
+
+    The reference calls this twice (once per evaluation, :153) and recomputes similarities and
+    rankings each time; here both evaluations come out of one pass, and a second call on the
+    same tensors reuses it."""
+    assert evaluation in ("maxskew", "ndkl")
+    key = None
+    if isinstance(image_embeddings, torch.Tensor) and isinstance(prompts_embeddings, torch.Tensor):
+        lab_arr = np.asarray(labels_list)
+        key = (image_embeddings.data_ptr(), image_embeddings._version, tuple(image_embeddings.shape),
+               prompts_embeddings.data_ptr(), prompts_embeddings._version, tuple(prompts_embeddings.shape),
+               lab_arr.__array_interface__["data"][0], hash(lab_arr.tobytes()) if lab_arr.size < (1 << 22) else None,
+               repr(topn), repr(sorted((opts or {}).items())))
+    if key is not None and _last["key"] == key:
+        both = _last["value"]
+    else:
+        both = evaluate(labels_list, image_embeddings, prompts_embeddings, topn, opts,
+                        need_contiguous=(evaluation == "ndkl"))
+        if key is not None and evaluation == "maxskew":
+            # only reusable by an ndkl call if the labels would have passed its check as well
+            try:
+                _encode_labels(labels_list, True)
+                _last["key"], _last["value"] = key, both
+            except IndexError:
+                _last["key"] = None
+        elif key is not None:
+            _last["key"], _last["value"] = key, both
+    return dict(both[evaluation])
+
+
+def _single_query(df, top_n: int, need_contiguous: bool) -> List[float]:
+    scores = np.ascontiguousarray(np.asarray(df["score"], dtype=np.float32))
+    codes, n_classes = _encode_labels(np.asarray(df["label"]), need_contiguous)
+    if int(top_n) < 1:
+        raise ZeroDivisionError("division by zero")
+    if not torch.cuda.is_available():
+        raise RuntimeError("no CUDA device: the bias-measurement path has no CPU fallback")
+    dev = torch.device("cuda", torch.cuda.current_device())
+    s = torch.from_numpy(scores).to(dev)[None, :]
+    lab = torch.from_numpy(codes).to(dev)
+    return _capi.context(dev.index).rank_and_score(s, lab, n_classes, int(top_n))["mean"]
+
+
+def normalized_discounted_KL(df, top_n: int) -> dict:
+    """Drop-in for measuring_bias.py:17-44 on a DataFrame with ``score`` and ``label`` columns."""
+    m = _single_query(df, top_n, True)
+    return {"ndkl_eq_opp": m[2], "ndkl_dem_par": m[3]}
+
+
+def compute_skew_metrics(df, top_n: int) -> dict:
+    """Drop-in for measuring_bias.py:47-72 on a DataFrame with ``score`` and ``label`` columns."""
+    m = _single_query(df, top_n, False)
+    return {"maxskew_eq_opp": m[0], "maxskew_dem_par": m[1]}
+
+
+# ---------------------------------------------------------------------------------------------
+# embedding hand-off (the producers of the path's inputs)
+# ---------------------------------------------------------------------------------------------
+def get_prompt_embeddings(model, tokenizer, device: torch.device, prompts: List[str]) -> torch.Tensor:
+    """measuring_bias.py:75-82: encode, L2-normalise in the model's dtype, then fp32."""
+    with torch.no_grad():
+        prompts_tokenized = tokenizer(prompts).to(device)
+        prompt_embeddings = model.encode_text(prompts_tokenized)
+        prompt_embeddings = prompt_embeddings / prompt_embeddings.norm(dim=-1, keepdim=True)
+    return prompt_embeddings.to(device).float()
+
+
+def get_labels_img_embeddings(images_dl, model, device: torch.device, progress: bool = False
+                              ) -> Tuple[np.ndarray, torch.Tensor]:
+    """measuring_bias.py:85-99 without the per-batch ``.cpu()`` / final ``.to(device)`` round
+    trip: embeddings stay on the device they were produced on."""
+    image_embeddings = []
+    image_labels = []
+    it = images_dl
+    if progress:
+        try:
+            from tqdm import tqdm
+            it = tqdm(images_dl, desc="Embedding images")
+        except ImportError:  # pragma: no cover
+            pass
+    for batch in it:
+        with torch.no_grad():
+            image_embeddings.append(model.encode_image(batch["img"].to(device)))
+        lab = batch["iat_label"]
+        image_labels.append(lab.detach().cpu().numpy() if isinstance(lab, torch.Tensor) else np.asarray(lab))
+    labels = np.concatenate([np.atleast_1d(x) for x in image_labels]) if image_labels else np.zeros(0, dtype=np.int64)
+    return labels, torch.cat(image_embeddings, dim=0).to(device)
+
+
+def measure_bias(cliplike, img_preproc: Optional[Callable] = None, tokenizer: Optional[Callable] = None,
+                 attribute: str = "gender", opts: dict = DEFAULT_OPTS):
+    """Drop-in for ``debias_clip.measure_bias`` (measuring_bias.py:139-156).  Also accepts the README
+    form ``measure_bias(model, attribute=...)`` (README.md:145)."""
+    from torch.utils.data import DataLoader
+    from .datasets import FairFace
+
+    opts = dict(opts or {})
+    ds = opts.get("dataset")
+    if ds is None:
+        ds = FairFace(mode="val", iat_type=attribute, transforms=img_preproc)
+    dl = DataLoader(ds, batch_size=opts.get("batch_size", 256), num_workers=opts.get("num_workers", 6))
+    if tokenizer is None:
+        try:
+            import clip as _clip
+            tokenizer = _clip.tokenize
+        except ImportError as e:
+            raise TypeError("measure_bias needs a tokenizer (openai `clip` is not installed)") from e
+
+    prompts: List[str] = gen_prompts()
+    device = torch.device("cuda")          # hard-coded in the reference too (:148)
+    labels_list, image_embeddings = get_labels_img_embeddings(dl, cliplike, device, progress=opts.get("progress", False))
+    prompts_embeddings = get_prompt_embeddings(cliplike, tokenizer, device, prompts)
+    both = evaluate(labels_list, image_embeddings, prompts_embeddings, opts.get("topn", 1.0), opts)
+    return {"maxskew": dict(both["maxskew"]), "ndkl": dict(both["ndkl"])}

@@ -1,0 +1,155 @@
+/*
+ * dvl_b200.h -- C ABI of the B200-native bias-measurement hot path.
+ *
+ * The reference (oxai/debias-vision-lang) has no FFI of its own: its hot path is plain
+ * Python (debias_clip/measuring_bias.py).  This header is the boundary a drop-in
+ * replacement binds instead: each entry point names the reference lines it replaces.
+ * Plain C types only (no torch, no C++), every buffer is owned by the caller, the
+ * library owns only the workspace inside its context.  All functions return DVL_OK (0)
+ * or a negative dvl_status; nothing throws across the boundary; the text of the last
+ * failure is kept per context (dvl_last_error).  A context is bound to one device and
+ * is not thread-safe; use one per device/thread.  There is no CPU fallback: without an
+ * sm_100 device every compute entry point fails with DVL_ERR_NO_DEVICE.
+ *
+ * Hot path:
+ *   a1  query L2-normalisation            measuring_bias.py:79,81
+ *   a2  image x query similarity          measuring_bias.py:114
+ *   a3  ranking, nlargest(keep="all")     measuring_bias.py:29,57 (pandas selectn.py:106-190)
+ *   a4  global label histogram            measuring_bias.py:23,56
+ *   a5  MaxSkew@k                         measuring_bias.py:47-72
+ *   a6  NDKL                              measuring_bias.py:17-44
+ *   a7  mean over queries                 measuring_bias.py:117,119
+ */
+#ifndef DVL_B200_H_
+#define DVL_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DVL_B200_ABI_VERSION 1
+
+#if defined(__GNUC__)
+#define DVL_API __attribute__((visibility("default")))
+#else
+#define DVL_API
+#endif
+
+typedef struct dvl_ctx dvl_ctx;
+
+typedef enum dvl_status {
+  DVL_OK = 0,
+  DVL_ERR_INVALID = -1,      /* bad argument (the reference raises AssertionError / IndexError) */
+  DVL_ERR_NO_DEVICE = -2,    /* no CUDA device, or not compute capability 10.x */
+  DVL_ERR_CUDA = -3,         /* a CUDA runtime / driver call failed; see dvl_last_error */
+  DVL_ERR_OOM = -4,          /* workspace allocation failed */
+  DVL_ERR_UNSUPPORTED = -5,  /* shape outside what the kernels take (e.g. D > 8192) */
+  DVL_ERR_OVERFLOW = -6      /* a caller-provided output buffer is too small */
+} dvl_status;
+
+/* element type of an embedding matrix handed in by the caller */
+typedef enum dvl_dtype { DVL_F32 = 0, DVL_BF16 = 1, DVL_F16 = 2 } dvl_dtype;
+
+/* arithmetic of the similarity stage (a2).
+ * FP32: every operand is split exactly into three bf16 planes and the six largest product
+ *       terms are accumulated in fp32 on the tensor cores (error ~2^-24 of |g||t|; exact on
+ *       data whose dot products are exactly representable, whatever the summation order).
+ * BF16: operands rounded once to bf16, fp32 accumulation (2e-2 tolerance of BASELINE.json). */
+typedef enum dvl_precision { DVL_PRECISION_FP32 = 0, DVL_PRECISION_BF16 = 1 } dvl_precision;
+
+/* flags */
+#define DVL_FLAG_NORMALIZE_QUERIES 0x1u /* a1: divide each query row by its L2 norm (fused into the
+                                           similarity epilogue).  Off when the caller already did
+                                           measuring_bias.py:79. */
+#define DVL_FLAG_NORMALIZE_GALLERY 0x2u /* NOT what eval_ranking does: cosine mode */
+#define DVL_FLAG_FULL_SORT         0x4u /* force the materialise-and-sort ranking route even when
+                                           top_n << N (the route top_n >= N always takes) */
+
+/* per-query result layout: 4 doubles per query */
+#define DVL_MAXSKEW_EQ_OPP 0
+#define DVL_MAXSKEW_DEM_PAR 1
+#define DVL_NDKL_EQ_OPP 2
+#define DVL_NDKL_DEM_PAR 3
+
+#define DVL_MAX_CLASSES 16
+
+/* ---- life cycle ------------------------------------------------------------------- */
+DVL_API int dvl_abi_version(void);
+/* Binds a context to CUDA device `device` (must be sm_100).  */
+DVL_API int dvl_create(dvl_ctx** out, int device);
+DVL_API int dvl_destroy(dvl_ctx* ctx);
+/* Text of the last failure on this context ("" if none); valid until the next call. */
+DVL_API const char* dvl_last_error(const dvl_ctx* ctx);
+/* Bytes of device workspace currently held by the context. */
+DVL_API size_t dvl_workspace_bytes(const dvl_ctx* ctx);
+/* Number of kernels this context launched since creation (bench.py's gpu_launches). */
+DVL_API uint64_t dvl_launch_count(const dvl_ctx* ctx);
+
+/* ---- the hot path, device-resident inputs ----------------------------------------------
+ * Replaces BOTH calls `eval_ranking(labels, image_embeddings, prompts_embeddings, ev, topn)`
+ * for ev in ("maxskew", "ndkl") (measuring_bias.py:153-154 -> :102-119) with one pass:
+ * similarity -> rank (score desc, lowest index first, boundary ties kept) -> label
+ * histograms -> MaxSkew + NDKL -> mean over queries.
+ *
+ *   gallery   device [n, d] row-major, gallery_dtype    (raw image embeddings, NOT normalised)
+ *   queries   device [q, d] row-major, query_dtype      (unit rows unless NORMALIZE_QUERIES)
+ *   labels    device [n] uint8, values 0..n_classes-1, every class present (datasets.py:43)
+ *   top_n     already resolved to an int (float topn -> ceil(n*topn), measuring_bias.py:109-110)
+ *   out_mean4 HOST   double[4]: mean over queries, order DVL_MAXSKEW_EQ_OPP.. (written before return;
+ *             the call synchronises `stream`)
+ *   out_per_query     device double [q][4] or NULL
+ *   out_ranked_len    device int32 [q] or NULL: m_q = number of ranked rows (>= min(top_n,n))
+ *   out_ranked_idx    device int32 [q][ranked_cap] or NULL: gallery indices in ranked order,
+ *                     first min(m_q, ranked_cap) entries of each row valid
+ *   out_scores        device float [q][n] or NULL: the fp32 similarities (full-sort route only)
+ *   stream    cudaStream_t (as void*) everything is enqueued on; NULL = default stream
+ */
+DVL_API int dvl_eval_ranking(dvl_ctx* ctx,
+                     const void* gallery, int gallery_dtype,
+                     const void* queries, int query_dtype,
+                     const uint8_t* labels,
+                     int64_t n, int32_t d, int32_t q, int32_t n_classes, int64_t top_n,
+                     int precision, uint32_t flags,
+                     double* out_mean4,
+                     double* out_per_query,
+                     int32_t* out_ranked_len, int32_t* out_ranked_idx, int64_t ranked_cap,
+                     float* out_scores,
+                     void* stream);
+
+/* Same computation with HOST inputs: copies gallery, queries and labels to the device
+ * (cudaMemcpyAsync on `stream`; pinned buffers make it asynchronous), runs the path and
+ * returns the four means.  This is the call bench.py times for its end-to-end number. */
+DVL_API int dvl_eval_ranking_host(dvl_ctx* ctx,
+                          const void* gallery_host, int gallery_dtype,
+                          const void* queries_host, int query_dtype,
+                          const uint8_t* labels_host,
+                          int64_t n, int32_t d, int32_t q, int32_t n_classes, int64_t top_n,
+                          int precision, uint32_t flags,
+                          double* out_mean4, double* out_per_query_host,
+                          void* stream);
+
+/* ---- stage entry points (same kernels, exposed for stage-isolated parity tests) -------- */
+
+/* a3-a7 on an explicit score matrix: device float [q][ld_scores] (first n columns used).
+ * Replaces compute_skew_metrics + normalized_discounted_KL (measuring_bias.py:47-72, :17-44)
+ * applied to each row's DataFrame{"score","label"}. */
+DVL_API int dvl_rank_and_score(dvl_ctx* ctx, const float* scores, int64_t ld_scores,
+                       const uint8_t* labels, int64_t n, int32_t q, int32_t n_classes, int64_t top_n,
+                       double* out_mean4, double* out_per_query,
+                       int32_t* out_ranked_len, int32_t* out_ranked_idx, int64_t ranked_cap,
+                       void* stream);
+
+/* a2 only: device float out [q][ld_out] = queries . gallery^T with the precision/flags above
+ * (measuring_bias.py:114 for all queries at once). */
+DVL_API int dvl_similarity(dvl_ctx* ctx,
+                   const void* gallery, int gallery_dtype, const void* queries, int query_dtype,
+                   int64_t n, int32_t d, int32_t q, int precision, uint32_t flags,
+                   float* out, int64_t ld_out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DVL_B200_H_ */
