@@ -1,0 +1,367 @@
+#!/usr/bin/env python
+"""Benchmark of the bias-measurement hot path (BASELINE.json metric: gallery-query pairs/s
+scored + ranked + reduced to MaxSkew/NDKL).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload cfg2|cfg1|cfg3|cfg5|cfg4shard]
+    python bench.py --impl reference ...      # the reference's CPU path (row-by-row port) on host cores
+
+One JSON line on stdout (rank 0).  A step = one pass of the whole hot path over one synthetic
+batch: similarity -> ranking -> label histograms -> MaxSkew + NDKL -> mean over queries.
+`value` = pairs (N*Q, counted once) per second with inputs resident in HBM; `e2e` = the same
+through dvl_eval_ranking_host with pinned HOST buffers (H2D of gallery/queries/labels and D2H of
+the result inside the timed region).  Under torchrun (N > 1) every rank holds the gallery and
+ranks its own slice of the queries (top_n = N workloads shard by query: no data-path collective;
+see DESIGN.md section 6), timing is max-over-ranks of CUDA-event time.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+METRIC = "gallery-query pairs/s scored+ranked (MaxSkew/NDKL)"
+UNIT = "pairs/s"
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            p = json.load(f)
+        return dict(hbm_gbs=p["hbm_gbs"], bf16_tflops=p["bf16_tflops"],
+                    bf16_tflops_sustained=p.get("bf16_tflops_sustained", p["bf16_tflops"]), source="measured")
+    return dict(hbm_gbs=6650.0, bf16_tflops=1590.0, bf16_tflops_sustained=1400.0, source="fallback")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
+    FIELDS = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+              "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "200",
+                 "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["nvidia-smi unavailable"])
+        time.sleep(0.25)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, smax, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.lines:
+            parts = [p.strip() for p in line.split(",")]
+            if len(parts) < 9:
+                continue
+            try:
+                sm.append(float(parts[1]))
+                smax.append(float(parts[2]))
+            except ValueError:
+                continue
+            for name, val in zip(names, parts[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["no samples"])
+        return dict(sm_mhz=float(np.median(sm)), sm_max_mhz=float(max(smax)), reasons=sorted(reasons),
+                    samples=len(sm))
+
+
+def make_workload(name: str, device: str, rank: int = 0):
+    from debias_vision_lang_b200 import synthetic
+    if name == "cfg4shard":       # one GPU's shard of BASELINE config 4 (1.25 M x 768, 10 k queries, bf16)
+        w = synthetic.clip_like(1_250_000, 768, 10_000, 2, seed=1238 + rank, device=device)
+        w.name, w.topn = "cfg4shard", 1000
+        return w, "bf16"
+    w = synthetic.baseline_workload(name, device=device)
+    return w, synthetic.BASELINE_CONFIGS[name]["precision"]
+
+
+def workload_description(name, w, precision, world):
+    n, d = w.gallery.shape
+    q = w.queries.shape[0]
+    return {
+        "workload": f"{name}: {n}x{d} gallery x {q} queries, C={w.n_classes}, top_n="
+                    f"{'N (measure_bias default)' if w.topn == 1.0 else w.topn}, {precision} similarity"
+                    + (f"; {world} GPUs, each ranks its own {q} queries over the full gallery" if world > 1 else ""),
+        "n_gallery": n, "depth": d, "n_queries_per_gpu": q, "n_classes": w.n_classes,
+        "top_n": n if w.topn == 1.0 else w.topn, "precision": precision,
+        "l2_policy": f"inputs larger than L2 ({n * d * 4 / 1e6:.0f} MB fp32 gallery + {q * n * 4 / 1e6:.0f} MB of keys per pass vs 126 MB L2); no explicit flush",
+        "parallelism": "1 GPU" if world == 1 else f"query-sharded x{world} (no data-path collective)",
+    }
+
+
+# ------------------------------------------------------------------------------------------
+# reference arm / cpu baseline: the row-by-row port of the reference on the host cores
+# ------------------------------------------------------------------------------------------
+def cpu_reference_sample(w, n_queries: int):
+    """Times the reference-style port (pandas DataFrame + nlargest + per-row Python loop, both
+    evaluations) on `n_queries` queries of the workload; returns (pairs/s, seconds, description)."""
+    from oracle import port
+    g = w.gallery.detach().cpu().float()
+    t = w.queries[:n_queries].detach().cpu().float()
+    t0 = time.perf_counter()
+    res = port.measure(w.labels, g, t, w.topn)
+    dt = time.perf_counter() - t0
+    pairs = g.shape[0] * t.shape[0]
+    return pairs / dt, dt, res
+
+
+def cpu_vectorised_sample(w, n_queries: int):
+    from oracle import spec
+    g = w.gallery.detach().cpu().float()
+    t = w.queries[:n_queries].detach().cpu().float()
+    t0 = time.perf_counter()
+    spec.measure(w.labels, g, t, w.topn)
+    dt = time.perf_counter() - t0
+    return g.shape[0] * t.shape[0] / dt, dt
+
+
+def sample_queries_for(name: str) -> int:
+    # ~10-30 s of CPU work with the row-by-row port (BASELINE.md section 3 per-query costs)
+    return {"cfg1": 40, "cfg2": 3, "cfg3": 24, "cfg5": 24, "cfg4shard": 16}.get(name, 4)
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    w, precision = make_workload(args.workload, "cpu")
+    # size the per-step sample so that the K + W steps together take ~150 s of CPU time
+    t_all = time.perf_counter()
+    _, t_one, _ = cpu_reference_sample(w, 1)
+    nq = int(150.0 / ((args.steps + args.warmup) * max(t_one, 1e-3)))
+    nq = max(1, min(nq, w.queries.shape[0], 4 * sample_queries_for(args.workload)))
+    vals = []
+    for _ in range(args.warmup):
+        cpu_reference_sample(w, nq)
+    for _ in range(args.steps):
+        v, dt, _ = cpu_reference_sample(w, nq)
+        vals.append((v, dt))
+    total = time.perf_counter() - t_all
+    value = float(np.mean([v for v, _ in vals]))
+    ms = float(np.mean([dt for _, dt in vals]) * 1e3)
+    cores = torch.get_num_threads()
+    sample = (f"{nq} of {w.queries.shape[0]} queries x full gallery, both evaluations, row-by-row port "
+              f"(pandas nlargest + per-row loop; torch matvec on {cores} threads, the rest single-threaded)")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_description(args.workload, w, precision, 1),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
+                         "host_cpus": os.cpu_count()},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0, "wall_s": total,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch.distributed as dist
+    from debias_vision_lang_b200 import _capi
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a B200: there is no CPU fallback for the product path "
+                           "(use --impl reference for the CPU baseline)")
+    torch.cuda.set_device(local_rank)
+    dev = f"cuda:{local_rank}"
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device(dev))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    peaks = load_peaks()
+    w, precision = make_workload(args.workload, dev, rank)
+    if world > 1 and args.workload != "cfg4shard":
+        # query sharding: same gallery on every rank, a different slice of a world-times larger query set
+        from debias_vision_lang_b200 import synthetic
+        cfg = synthetic.BASELINE_CONFIGS[args.workload]
+        wq = synthetic.clip_like(1024, cfg["d"], cfg["q"], cfg["c"], seed=4321 + rank, device=dev)
+        w.queries = wq.queries
+    n, d = w.gallery.shape
+    q = w.queries.shape[0]
+    top_n = n if w.topn == 1.0 else int(w.topn)
+    prec = _capi.PRECISION_FP32 if precision == "fp32" else _capi.PRECISION_BF16
+    lab = torch.from_numpy(w.labels.astype(np.uint8)).to(dev)
+    ctx = _capi.context(local_rank)
+
+    def step():
+        return ctx.eval_ranking(w.gallery, w.queries, lab, w.n_classes, top_n, prec)["mean"]
+
+    for _ in range(max(args.warmup, 3)):
+        result = step()
+    barrier()
+    ctx.get_profile()
+    ctx.set_profiling(True)
+    launches0 = ctx.launch_count
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record()
+    for _ in range(args.steps):
+        result = step()
+    ev1.record()
+    barrier()
+    clocks = sampler.stop()
+    elapsed_ms = ev0.elapsed_time(ev1)
+    profile = ctx.get_profile()
+    ctx.set_profiling(False)
+    launches = ctx.launch_count - launches0
+    t = torch.tensor([elapsed_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    elapsed_ms = float(t.item())
+    pairs_per_step = n * q * world
+    value = pairs_per_step * args.steps / (elapsed_ms * 1e-3)
+
+    # ---- end to end through the C ABI with pinned host buffers ----
+    g_host = w.gallery.detach().cpu().pin_memory()
+    t_host = w.queries.detach().cpu().pin_memory()
+    l_host = torch.from_numpy(w.labels.astype(np.uint8)).pin_memory()
+    g_np, t_np, l_np = g_host.numpy(), t_host.numpy(), l_host.numpy()
+    for _ in range(2):
+        e2e_result = ctx.eval_ranking_host(g_np, t_np, l_np, w.n_classes, top_n, prec)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        e2e_result = ctx.eval_ranking_host(g_np, t_np, l_np, w.n_classes, top_n, prec)
+    e1.record()
+    barrier()
+    e2e_ms = e0.elapsed_time(e1)
+    t = torch.tensor([e2e_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_ms = float(t.item())
+    e2e_value = pairs_per_step * args.steps / (e2e_ms * 1e-3)
+    assert max(abs(a - b) for a, b in zip(e2e_result, result)) == 0.0, "host and device entry points disagree"
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel family, from the per-stage events of the timed region ----
+    stage_ms = {k: v[0] / args.steps for k, v in profile.items()}
+    stage_launches = {k: v[1] // args.steps for k, v in profile.items()}
+    dominant = max(stage_ms, key=lambda k: stage_ms[k])
+    pairs_rank = n * q
+    if dominant == "gemm":
+        terms = 6 if precision == "fp32" else 1
+        flops = 2.0 * pairs_rank * d                       # algorithmic: 2*D flop per pair
+        achieved = flops / (stage_ms["gemm"] * 1e-3) / 1e12
+        roof = {"bound": "tensor", "kernel": "sim_gemm_kernel", "achieved": achieved,
+                "peak": peaks["bf16_tflops"], "unit": "TFLOP/s", "frac": achieved / peaks["bf16_tflops"],
+                "traffic": None, "peak_source": peaks["source"] + " bf16 burst",
+                "issued_tflops": achieved * terms,
+                "note": f"algorithmic 2*D flop/pair; fp32 mode issues {terms}x that in bf16 products"}
+    else:
+        # the radix sort: per launch of tile_scatter_kernel a pair costs key read+write (8 B) and label
+        # read+write (2 B); see DESIGN.md section 4
+        launches_k = max(1, stage_launches.get("sort_scatter", 4))
+        ms_per_launch = stage_ms["sort_scatter"] / launches_k
+        bytes_per_launch = pairs_rank * 10.0
+        achieved = bytes_per_launch / (ms_per_launch * 1e-3) / 1e9
+        sort_ms = stage_ms["sort_hist"] + stage_ms["sort_scan"] + stage_ms["sort_scatter"]
+        roof = {"bound": "hbm", "kernel": "tile_scatter_kernel", "achieved": achieved, "peak": peaks["hbm_gbs"],
+                "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"], "traffic": None,
+                "peak_source": peaks["source"] + " copy bandwidth",
+                "launches_per_step": launches_k, "ms_per_launch": ms_per_launch,
+                "algorithmic_bytes_per_launch": bytes_per_launch,
+                "ranking_stage": {"algorithmic_bytes": pairs_rank * 8.0, "ms": sort_ms,
+                                  "achieved_gbs": pairs_rank * 8.0 / (sort_ms * 1e-3) / 1e9,
+                                  "frac": pairs_rank * 8.0 / (sort_ms * 1e-3) / 1e9 / peaks["hbm_gbs"]}}
+
+    # ---- CPU baseline beside it (rank 0, N = 1 only): bounded sample of the same workload ----
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        nq = sample_queries_for(args.workload)
+        v, dt, _ = cpu_reference_sample(w, nq)
+        vv, vdt = cpu_vectorised_sample(w, min(q, max(nq, 8)))
+        cpu = {"value": v, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+               "sample": f"{nq} of {q} queries x full gallery, both evaluations, row-by-row port of the reference "
+                         f"({dt:.1f} s; matvec multi-threaded, pandas/python part one thread)",
+               "host_cpus": os.cpu_count(),
+               "vectorised_oracle": {"value": vv, "unit": UNIT, "seconds": vdt,
+                                     "sample": f"{min(q, max(nq, 8))} queries, numpy float64 oracle/spec.py"}}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32" if precision == "fp32" else "bf16",
+        "data": "synthetic (seeded CLIP-like embeddings and labels; no FairFace/CLIP weights offline)",
+        "config": workload_description(args.workload, w, precision, world),
+        "roofline": roof,
+        "stage_ms": stage_ms, "stage_launches": stage_launches,
+        "cpu_baseline": cpu,
+        "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_ms / args.steps,
+                "h2d_bytes_per_step": int(g_np.nbytes + t_np.nbytes + l_np.nbytes) * world,
+                "d2h_bytes_per_step": 32 * world,
+                "api": "dvl_eval_ranking_host (C ABI, pinned host buffers)"},
+        "gpu_launches": int(launches),
+        "clocks": clocks,
+        "result": {"maxskew_eq_opp": result[0], "maxskew_dem_par": result[1], "ndkl_eq_opp": result[2],
+                   "ndkl_dem_par": result[3]},
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="cfg2", choices=["cfg1", "cfg2", "cfg3", "cfg5", "cfg4shard"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

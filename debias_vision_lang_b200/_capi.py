@@ -21,10 +21,12 @@ DVL_F32, DVL_BF16, DVL_F16 = 0, 1, 2
 PRECISION_FP32, PRECISION_BF16 = 0, 1
 FLAG_NORMALIZE_QUERIES, FLAG_NORMALIZE_GALLERY, FLAG_FULL_SORT = 1, 2, 4
 MAX_CLASSES = 16
+STAGES = ("prep", "gemm", "sort_hist", "sort_scan", "sort_scatter", "metrics", "select", "copy")
+NUM_STAGES = len(STAGES)
 
 EXPORTS = (
     "dvl_abi_version", "dvl_create", "dvl_destroy", "dvl_last_error", "dvl_workspace_bytes",
-    "dvl_launch_count", "dvl_eval_ranking", "dvl_eval_ranking_host", "dvl_rank_and_score", "dvl_similarity",
+    "dvl_launch_count", "dvl_set_profiling", "dvl_get_profile", "dvl_eval_ranking", "dvl_eval_ranking_host", "dvl_rank_and_score", "dvl_similarity",
 )
 
 _STATUS = {-1: "DVL_ERR_INVALID", -2: "DVL_ERR_NO_DEVICE", -3: "DVL_ERR_CUDA", -4: "DVL_ERR_OOM",
@@ -60,6 +62,8 @@ def lib() -> ctypes.CDLL:
     L.dvl_workspace_bytes.restype = ctypes.c_size_t
     L.dvl_launch_count.argtypes = [c_void_p]
     L.dvl_launch_count.restype = ctypes.c_uint64
+    L.dvl_set_profiling.argtypes = [c_void_p, c_int]
+    L.dvl_get_profile.argtypes = [c_void_p, c_void_p, c_void_p]
     L.dvl_eval_ranking.argtypes = [c_void_p, c_void_p, c_int, c_void_p, c_int, c_void_p, c_i64, c_i32, c_i32, c_i32,
                                    c_i64, c_int, c_u32, c_void_p, c_void_p, c_void_p, c_void_p, c_i64, c_void_p,
                                    c_void_p]
@@ -128,6 +132,16 @@ class Context:
     @property
     def workspace_bytes(self) -> int:
         return int(lib().dvl_workspace_bytes(self._h))
+
+    def set_profiling(self, enabled: bool):
+        self._check(lib().dvl_set_profiling(self._h, 1 if enabled else 0))
+
+    def get_profile(self):
+        """{stage name: (milliseconds, kernel launches)} accumulated since the previous call."""
+        ms = (ctypes.c_double * NUM_STAGES)()
+        ln = (ctypes.c_uint64 * NUM_STAGES)()
+        self._check(lib().dvl_get_profile(self._h, ctypes.cast(ms, ctypes.c_void_p), ctypes.cast(ln, ctypes.c_void_p)))
+        return {STAGES[i]: (float(ms[i]), int(ln[i])) for i in range(NUM_STAGES)}
 
     def _stream(self) -> int:
         return int(torch.cuda.current_stream(self.device).cuda_stream)

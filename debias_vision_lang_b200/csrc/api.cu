@@ -48,6 +48,30 @@ int ensure(Ctx* c, DevBuf& b, size_t bytes) {
   return DVL_OK;
 }
 
+StageScope::StageScope(Ctx* ctx, int stage_id, cudaStream_t stream) : c(ctx), stage(stage_id), st(stream) {
+  launches0 = c->launches;
+  if (!c->profiling) return;
+  auto get = [&]() {
+    cudaEvent_t e = nullptr;
+    if (!c->prof_free.empty()) {
+      e = c->prof_free.back();
+      c->prof_free.pop_back();
+    } else if (cudaEventCreate(&e) != cudaSuccess) {
+      e = nullptr;
+    }
+    return e;
+  };
+  e0 = get();
+  e1 = get();
+  if (e0 != nullptr) cudaEventRecord(e0, st);
+}
+
+StageScope::~StageScope() {
+  if (!c->profiling || e0 == nullptr || e1 == nullptr) return;
+  cudaEventRecord(e1, st);
+  c->prof_recs.push_back({stage, e0, e1, c->launches - launches0});
+}
+
 namespace {
 
 inline int64_t round_up(int64_t v, int64_t m) { return (v + m - 1) / m * m; }
@@ -93,8 +117,12 @@ int run_similarity(Ctx* c, const void* gallery, int gdt, const void* queries, in
     DVL_TRY(ensure(c, c->qry_inv_norm, (size_t)q * 4));
     qnorm = (float*)c->qry_inv_norm.ptr;
   }
-  DVL_TRY(launch_split_rows(c, gallery, gdt, n, d, dp, planes, (__nv_bfloat16*)c->gal_planes.ptr, gnorm, st));
-  DVL_TRY(launch_split_rows(c, queries, qdt, q, d, dp, planes, (__nv_bfloat16*)c->qry_planes.ptr, qnorm, st));
+  {
+    StageScope scope(c, DVL_STAGE_PREP, st);
+    DVL_TRY(launch_split_rows(c, gallery, gdt, n, d, dp, planes, (__nv_bfloat16*)c->gal_planes.ptr, gnorm, st));
+    DVL_TRY(launch_split_rows(c, queries, qdt, q, d, dp, planes, (__nv_bfloat16*)c->qry_planes.ptr, qnorm, st));
+  }
+  StageScope scope(c, DVL_STAGE_GEMM, st);
   GemmArgs g;
   g.qry_planes = (const __nv_bfloat16*)c->qry_planes.ptr;
   g.gal_planes = (const __nv_bfloat16*)c->gal_planes.ptr;
@@ -130,8 +158,11 @@ int run_sort_and_score(Ctx* c, const uint8_t* labels, int64_t n, int q, int n_cl
   DVL_TRY(ensure(c, c->per_query, (size_t)q * 4 * sizeof(double)));
   DVL_TRY(ensure(c, c->seg_len, (size_t)q * sizeof(int32_t)));
   DVL_TRY(ensure(c, c->mean_dev, 8 * sizeof(double)));
-  DVL_TRY(ensure_log_table(c, (n > top_n ? n : top_n) + 2, st));
-  DVL_TRY(launch_class_counts(c, labels, n, n_classes, (unsigned long long*)c->class_counts.ptr, st));
+  {
+    StageScope scope(c, DVL_STAGE_PREP, st);
+    DVL_TRY(ensure_log_table(c, (n > top_n ? n : top_n) + 2, st));
+    DVL_TRY(launch_class_counts(c, labels, n, n_classes, (unsigned long long*)c->class_counts.ptr, st));
+  }
 
   SortArgs s;
   s.keys[0] = (uint32_t*)c->keys[0].ptr;
@@ -162,9 +193,15 @@ int run_sort_and_score(Ctx* c, const uint8_t* labels, int64_t n, int q, int n_cl
   m.log_tab = (const double*)c->log_tab.ptr;
   m.per_query = out_per_query != nullptr ? out_per_query : (double*)c->per_query.ptr;
   m.ranked_len = ranked_len;
-  DVL_TRY(launch_metrics(c, m, st));
-  DVL_TRY(launch_mean(c, m.per_query, q, (double*)c->mean_dev.ptr, st));
-  if (want_idx) DVL_TRY(launch_copy_ranked(c, s.idxs[buf], ldk, ranked_len, q, out_ranked_idx, ranked_cap, st));
+  {
+    StageScope scope(c, DVL_STAGE_METRICS, st);
+    DVL_TRY(launch_metrics(c, m, st));
+    DVL_TRY(launch_mean(c, m.per_query, q, (double*)c->mean_dev.ptr, st));
+  }
+  if (want_idx) {
+    StageScope scope(c, DVL_STAGE_COPY, st);
+    DVL_TRY(launch_copy_ranked(c, s.idxs[buf], ldk, ranked_len, q, out_ranked_idx, ranked_cap, st));
+  }
   DVL_CUDA(c, cudaMemcpyAsync(c->mean_pinned, c->mean_dev.ptr, 4 * sizeof(double), cudaMemcpyDeviceToHost, st));
   // the out-of-range label flag travels with the class counts
   unsigned long long bad_flag = 0;
@@ -236,6 +273,11 @@ DVL_API int dvl_destroy(dvl_ctx* c) {
   for (dvl::DevBuf* b : bufs)
     if (b->ptr != nullptr) cudaFree(b->ptr);
   if (c->mean_pinned != nullptr) cudaFreeHost(c->mean_pinned);
+  for (auto& r : c->prof_recs) {
+    cudaEventDestroy(r.e0);
+    cudaEventDestroy(r.e1);
+  }
+  for (cudaEvent_t e : c->prof_free) cudaEventDestroy(e);
   delete c;
   return DVL_OK;
 }
@@ -243,6 +285,34 @@ DVL_API int dvl_destroy(dvl_ctx* c) {
 DVL_API const char* dvl_last_error(const dvl_ctx* c) { return c == nullptr ? "null context" : c->err.c_str(); }
 DVL_API size_t dvl_workspace_bytes(const dvl_ctx* c) { return c == nullptr ? 0 : c->ws_bytes; }
 DVL_API uint64_t dvl_launch_count(const dvl_ctx* c) { return c == nullptr ? 0 : c->launches; }
+
+DVL_API int dvl_set_profiling(dvl_ctx* c, int enabled) {
+  if (c == nullptr) return DVL_ERR_INVALID;
+  c->profiling = enabled != 0;
+  return DVL_OK;
+}
+
+DVL_API int dvl_get_profile(dvl_ctx* c, double* stage_ms, uint64_t* stage_launches) {
+  if (c == nullptr) return DVL_ERR_INVALID;
+  dvl::DeviceGuard guard(c->device);
+  for (auto& r : c->prof_recs) {
+    float ms = 0.f;
+    if (cudaEventSynchronize(r.e1) == cudaSuccess && cudaEventElapsedTime(&ms, r.e0, r.e1) == cudaSuccess) {
+      c->stage_ms[r.stage] += ms;
+      c->stage_launches[r.stage] += r.launches;
+    }
+    c->prof_free.push_back(r.e0);
+    c->prof_free.push_back(r.e1);
+  }
+  c->prof_recs.clear();
+  for (int i = 0; i < DVL_NUM_STAGES; ++i) {
+    if (stage_ms != nullptr) stage_ms[i] = c->stage_ms[i];
+    if (stage_launches != nullptr) stage_launches[i] = c->stage_launches[i];
+    c->stage_ms[i] = 0.0;
+    c->stage_launches[i] = 0;
+  }
+  return DVL_OK;
+}
 
 DVL_API int dvl_similarity(dvl_ctx* c, const void* gallery, int gdt, const void* queries, int qdt, int64_t n, int32_t d,
                    int32_t q, int precision, uint32_t flags, float* out, int64_t ld_out, void* stream) {
@@ -313,9 +383,12 @@ DVL_API int dvl_eval_ranking_host(dvl_ctx* c, const void* gallery_host, int gdt,
   DVL_TRY(dvl::ensure(c, c->h_gallery, gbytes));
   DVL_TRY(dvl::ensure(c, c->h_queries, qbytes));
   DVL_TRY(dvl::ensure(c, c->h_labels, (size_t)n));
-  DVL_CUDA(c, cudaMemcpyAsync(c->h_gallery.ptr, gallery_host, gbytes, cudaMemcpyHostToDevice, st));
-  DVL_CUDA(c, cudaMemcpyAsync(c->h_queries.ptr, queries_host, qbytes, cudaMemcpyHostToDevice, st));
-  DVL_CUDA(c, cudaMemcpyAsync(c->h_labels.ptr, labels_host, (size_t)n, cudaMemcpyHostToDevice, st));
+  {
+    dvl::StageScope scope(c, DVL_STAGE_COPY, st);
+    DVL_CUDA(c, cudaMemcpyAsync(c->h_gallery.ptr, gallery_host, gbytes, cudaMemcpyHostToDevice, st));
+    DVL_CUDA(c, cudaMemcpyAsync(c->h_queries.ptr, queries_host, qbytes, cudaMemcpyHostToDevice, st));
+    DVL_CUDA(c, cudaMemcpyAsync(c->h_labels.ptr, labels_host, (size_t)n, cudaMemcpyHostToDevice, st));
+  }
   DVL_TRY(dvl::ensure(c, c->per_query, (size_t)q * 4 * sizeof(double)));
   int rc = dvl_eval_ranking(c, c->h_gallery.ptr, gdt, c->h_queries.ptr, qdt, (const uint8_t*)c->h_labels.ptr, n, d, q,
                             n_classes, top_n, precision, flags, out_mean4, (double*)c->per_query.ptr, nullptr,

@@ -36,6 +36,24 @@ struct Ctx {
   // driver entry point for tensor-map encoding (resolved once, no -lcuda link dependency)
   void* encode_tiled = nullptr;
   bool gemm_attr_set = false;
+  // per-stage CUDA-event timing (dvl_set_profiling / dvl_get_profile)
+  bool profiling = false;
+  struct ProfRec { int stage; cudaEvent_t e0, e1; uint64_t launches; };
+  std::vector<ProfRec> prof_recs;
+  std::vector<cudaEvent_t> prof_free;
+  double stage_ms[DVL_NUM_STAGES] = {0};
+  uint64_t stage_launches[DVL_NUM_STAGES] = {0};
+};
+
+// Brackets the kernels of one stage with events on the launching stream when profiling is on.
+struct StageScope {
+  Ctx* c;
+  int stage;
+  cudaStream_t st;
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  uint64_t launches0;
+  StageScope(Ctx* ctx, int stage_id, cudaStream_t stream);
+  ~StageScope();
 };
 
 int set_error(Ctx* c, int code, const char* fmt, ...);

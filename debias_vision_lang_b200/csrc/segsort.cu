@@ -183,10 +183,17 @@ int launch_segmented_sort(Ctx* c, const SortArgs& a, int* out_buf, cudaStream_t 
       const int64_t off = (int64_t)q0 * a.ldk;
       uint32_t* th_q = th + (int64_t)q0 * tiles * kRadix;
       dim3 grid((unsigned)tiles, (unsigned)qn);
-      tile_hist_kernel<<<grid, kSortThreads, 0, st>>>(a.keys[cur] + off, a.ldk, a.n, shift, tiles, th_q);
-      DVL_LAUNCH_CHECK(c, "tile_hist_kernel");
-      seg_scan_kernel<<<(unsigned)qn, kRadix, 0, st>>>(th_q, tiles);
-      DVL_LAUNCH_CHECK(c, "seg_scan_kernel");
+      {
+        StageScope scope(c, DVL_STAGE_SORT_HIST, st);
+        tile_hist_kernel<<<grid, kSortThreads, 0, st>>>(a.keys[cur] + off, a.ldk, a.n, shift, tiles, th_q);
+        DVL_LAUNCH_CHECK(c, "tile_hist_kernel");
+      }
+      {
+        StageScope scope(c, DVL_STAGE_SORT_SCAN, st);
+        seg_scan_kernel<<<(unsigned)qn, kRadix, 0, st>>>(th_q, tiles);
+        DVL_LAUNCH_CHECK(c, "seg_scan_kernel");
+      }
+      StageScope scope(c, DVL_STAGE_SORT_SCATTER, st);
       const uint32_t* ki = a.keys[cur] + off;
       const uint8_t* li = a.labs[cur] + off;
       const int32_t* ii = has_idx ? a.idxs[cur] + off : nullptr;

@@ -1,0 +1,135 @@
+"""Dataset interface of the reference (``debias_clip/datasets.py``) as the hot path sees it:
+items are dict-likes with ``"img"`` and ``"iat_label"`` (datasets.py:125-131), attribute
+strings map to contiguous int labels 0..C-1 (datasets.py:17-19,50-51, gen_labels :30-46).
+
+This side of the boundary is I/O, not the accelerated path.  What is here: the label
+encodings, ``gen_labels`` with the reference's checks, a ``FairFace`` that reads an already
+present FairFace directory with the reference's ordering rules but runs on pandas >= 2
+(the reference's ``equal_split`` crashes there) and never downloads (no network),
+and ``EmbeddingGallery`` -- the device-resident (embeddings, labels) pair the path consumes.
+"""
+from __future__ import annotations
+
+import os
+from typing import Callable, Optional, Union
+
+import numpy as np
+import torch
+from torch.utils.data import Dataset
+
+from . import Dotdict, FAIRFACE_DATA_PATH
+
+
+class IATDataset(Dataset):
+    GENDER_ENCODING = {"Female": 1, "Male": 0}
+    AGE_ENCODING = {"0-2": 0, "3-9": 1, "10-19": 2, "20-29": 3, "30-39": 4,
+                    "40-49": 5, "50-59": 6, "60-69": 7, "more than 70": 8}
+
+    def __init__(self):
+        self.image_embeddings: Optional[torch.Tensor] = None
+        self.iat_labels: Optional[np.ndarray] = None
+        self._img_fnames = None
+        self._transforms = None
+        self.use_cache = None
+        self.iat_type = None
+        self.n_iat_classes = None
+
+    def gen_labels(self, iat_type: str, label_encoding: Optional[dict] = None):
+        """attribute name -> (int labels, number of classes); every class must occur
+        (datasets.py:43) -- the metrics index their count arrays with the label."""
+        if iat_type in ("gender_science", "test_weat", "gender"):
+            column, encoding = "gender", IATDataset.GENDER_ENCODING
+        elif iat_type == "race":
+            column, encoding = "race", self.RACE_ENCODING
+        elif iat_type == "age":
+            column, encoding = "age", IATDataset.AGE_ENCODING
+        else:
+            raise NotImplementedError
+        if label_encoding is not None:
+            encoding = label_encoding
+        labels_list = self.labels[column]
+        assert set(labels_list.unique()) == set(encoding.keys()), "There is a missing label, invalid for WEAT"
+        return np.array([encoding[x] for x in labels_list], dtype=int), len(encoding)
+
+
+class FairFace(IATDataset):
+    RACE_ENCODING = {"White": 0, "Southeast Asian": 1, "Middle Eastern": 2,
+                     "Black": 3, "Indian": 4, "Latino_Hispanic": 5, "East Asian": 6}
+
+    def __init__(self, iat_type: str = None, lazy: bool = True, mode: str = "train",
+                 _n_samples: Union[float, int] = None, transforms: Callable = None, equal_split: bool = True,
+                 data_path: Optional[str] = None):
+        super().__init__()
+        import pandas as pd
+        self.DATA_PATH = str(data_path or FAIRFACE_DATA_PATH)
+        self.download_data()
+        self.mode = mode
+        self._transforms = (lambda x: x) if transforms is None else transforms
+        self.labels = pd.read_csv(os.path.join(self.DATA_PATH, "labels", mode, f"{mode}_labels.csv"))
+        # lexicographic file order defines the gallery index order, hence the tie-break
+        self.labels = self.labels.sort_values("file")
+        if _n_samples is not None:
+            if isinstance(_n_samples, float):
+                _n_samples = int(len(self.labels) * _n_samples)
+            self.labels = self.labels[:_n_samples]
+        if equal_split:
+            # datasets.py:66-78: same number of Male and Female rows, all Male rows first
+            male = self.labels.loc[self.labels["gender"] == "Male"]
+            female = self.labels.loc[self.labels["gender"] == "Female"]
+            k = min(len(male), len(female))
+            self.labels = pd.concat([male.sample(n=k, random_state=1), female.sample(n=k, random_state=1)],
+                                    ignore_index=True)
+        self._img_fnames = [os.path.join(self.DATA_PATH, "imgs", "train_val", x) for x in self.labels["file"]]
+        self._fname_to_inx = {fname: inx for inx, fname in enumerate(self._img_fnames)}
+        self.images_list = None
+        if not lazy:
+            self.images_list = [self[i] for i in range(len(self.labels))]
+        self.iat_type = iat_type
+        self.iat_labels, self.n_iat_classes = self.gen_labels(iat_type=iat_type)
+
+    def download_data(self):
+        """The reference downloads from Google Drive (datasets.py:89-117); this build has no network,
+        so the data must already be in place."""
+        need = [os.path.join(self.DATA_PATH, "labels"), os.path.join(self.DATA_PATH, "imgs")]
+        missing = [p for p in need if not os.path.isdir(p)]
+        if missing:
+            raise FileNotFoundError(
+                f"FairFace data not found under {self.DATA_PATH} (missing {missing}); place labels/<mode>/"
+                "<mode>_labels.csv and imgs/train_val/ there -- downloading is not supported offline")
+
+    def _load_fairface_sample(self, sample_labels) -> dict:
+        from PIL import Image
+        res = Dotdict(dict(sample_labels))
+        res.img = self._transforms(Image.open(os.path.join(self.DATA_PATH, "imgs", "train_val", res.file)))
+        return res
+
+    def __getitem__(self, index: int):
+        if self.images_list is not None:
+            return self.images_list[index]
+        sample = self._load_fairface_sample(self.labels.iloc[index])
+        sample.iat_label = self.iat_labels[index]
+        return sample
+
+    def __len__(self):
+        return len(self.labels)
+
+
+class EmbeddingGallery(IATDataset):
+    """A gallery that already is embeddings: items are ``{"img": embedding, "iat_label": label}`` so
+    it can flow through ``get_labels_img_embeddings`` with an identity ``encode_image``; the pair
+    (``image_embeddings``, ``iat_labels``) fills the two attributes the reference reserves but never
+    implements (datasets.py:22-23)."""
+
+    def __init__(self, image_embeddings: torch.Tensor, iat_labels: np.ndarray, iat_type: str = "gender"):
+        super().__init__()
+        assert len(image_embeddings) == len(iat_labels)
+        self.image_embeddings = image_embeddings
+        self.iat_labels = np.asarray(iat_labels)
+        self.iat_type = iat_type
+        self.n_iat_classes = int(len(np.unique(self.iat_labels)))
+
+    def __getitem__(self, index: int):
+        return {"img": self.image_embeddings[index], "iat_label": int(self.iat_labels[index])}
+
+    def __len__(self):
+        return len(self.iat_labels)

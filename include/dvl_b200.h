@@ -76,6 +76,17 @@ typedef enum dvl_precision { DVL_PRECISION_FP32 = 0, DVL_PRECISION_BF16 = 1 } dv
 
 #define DVL_MAX_CLASSES 16
 
+/* stages reported by dvl_get_profile */
+#define DVL_STAGE_PREP 0         /* operand split / conversion, label histogram, ln table */
+#define DVL_STAGE_GEMM 1         /* tcgen05 similarity GEMM (+ fused epilogue) */
+#define DVL_STAGE_SORT_HIST 2    /* radix sort: tile digit histograms */
+#define DVL_STAGE_SORT_SCAN 3    /* radix sort: per-segment scans */
+#define DVL_STAGE_SORT_SCATTER 4 /* radix sort: stable scatter */
+#define DVL_STAGE_METRICS 5      /* MaxSkew/NDKL + mean over queries */
+#define DVL_STAGE_SELECT 6       /* streaming top-k: candidate selection / merge */
+#define DVL_STAGE_COPY 7         /* host<->device and layout copies issued by the library */
+#define DVL_NUM_STAGES 8
+
 /* ---- life cycle ------------------------------------------------------------------- */
 DVL_API int dvl_abi_version(void);
 /* Binds a context to CUDA device `device` (must be sm_100).  */
@@ -87,6 +98,12 @@ DVL_API const char* dvl_last_error(const dvl_ctx* ctx);
 DVL_API size_t dvl_workspace_bytes(const dvl_ctx* ctx);
 /* Number of kernels this context launched since creation (bench.py's gpu_launches). */
 DVL_API uint64_t dvl_launch_count(const dvl_ctx* ctx);
+
+/* Per-stage device timing with CUDA events recorded on the caller's stream around each stage's
+ * kernels.  dvl_get_profile synchronises, writes the milliseconds and kernel-launch counts
+ * accumulated per stage since the previous call (arrays of DVL_NUM_STAGES) and resets them. */
+DVL_API int dvl_set_profiling(dvl_ctx* ctx, int enabled);
+DVL_API int dvl_get_profile(dvl_ctx* ctx, double* stage_ms, uint64_t* stage_launches);
 
 /* ---- the hot path, device-resident inputs ----------------------------------------------
  * Replaces BOTH calls `eval_ranking(labels, image_embeddings, prompts_embeddings, ev, topn)`

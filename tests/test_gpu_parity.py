@@ -1,0 +1,261 @@
+"""Parity tests proper: the CUDA path, called through the C ABI, against the oracle and the
+golden vectors the reference produced.  Run on the B200 box with `-m gpu`.
+
+Bars (BASELINE.json north_star): rankings bit-exact (lowest-index tie-break, boundary ties
+kept); similarities within 1e-5 (fp32 mode) / 2e-2 (bf16 mode) norm-wise relative
+(|ds| <= tol*|g||t|: a purely relative bound is meaningless near s = 0);
+MaxSkew and NDKL within 1e-6 absolute (in practice ~1e-15)."""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import build_ranking_workload, load_golden, u32_to_f32
+from debias_vision_lang_b200 import _capi, measuring_bias, synthetic
+import debias_vision_lang_b200 as dvl
+from oracle import spec
+
+pytestmark = pytest.mark.gpu
+
+METRIC_TOL = 1e-6      # the bar
+TIGHT = 1e-12          # what float64 on both sides actually gives on identical rankings
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    assert torch.cuda.is_available()
+    return _capi.context(0)
+
+
+def _flat(d):
+    return [d["maxskew"]["eq_opp"], d["maxskew"]["dem_par"], d["ndkl"]["eq_opp"], d["ndkl"]["dem_par"]]
+
+
+def test_stage_golden_vectors_rank_and_metrics(ctx, stage_cases):
+    """Every (scores, labels, top_n) case the reference was run on: ranked order bit-exact,
+    four metrics to 1e-12 -- ties, signed zeros, NaN, +-inf, denormals, top_n > n included."""
+    for case in stage_cases:
+        s = u32_to_f32(case["scores_u32"])
+        lab = np.asarray(case["labels"])
+        codes = np.searchsorted(np.unique(lab), lab).astype(np.uint8)
+        c = len(np.unique(lab))
+        cap = max(1, len(case["order"]))
+        res = ctx.rank_and_score(torch.from_numpy(s.copy()).cuda()[None, :], torch.from_numpy(codes).cuda(), c,
+                                 case["top_n"], ranked_cap=cap)
+        m = int(res["ranked_len"][0])
+        assert m == len(case["order"]), case["name"]
+        assert res["ranked_idx"][0, :m].cpu().tolist() == case["order"], case["name"]
+        got = res["per_query"][0].cpu().tolist()
+        # the reference's ndkl needs labels 0..C-1; golden ndkl values exist only for such cases
+        want = [case["maxskew_eq_opp"], case["maxskew_dem_par"], case["ndkl_eq_opp"], case["ndkl_dem_par"]]
+        for g, w_ in zip(got, want):
+            if math.isnan(w_):
+                continue
+            assert abs(g - w_) <= TIGHT * max(1.0, abs(w_)), (case["name"], got, want)
+
+
+def test_ranking_golden_vectors_end_to_end(ranking_cases):
+    """eval_ranking-level vectors of the reference on exactly-summable (dyadic) embeddings, through the
+    public drop-in API, fp32 mode: similarity + ranking + metrics + mean."""
+    for case in ranking_cases:
+        w, topn = build_ranking_workload(case)
+        g, t = w.gallery.cuda(), w.queries.cuda()
+        for ev in ("maxskew", "ndkl"):
+            got = dvl.eval_ranking(w.labels, g, t, ev, topn)
+            for k in ("eq_opp", "dem_par"):
+                assert abs(got[k] - case["expected"][ev][k]) <= TIGHT, (case, ev, k, got)
+
+
+@pytest.mark.parametrize("n,d,q", [(256, 64, 128), (1000, 128, 130), (5000, 512, 319), (3001, 768, 257),
+                                   (777, 200, 33), (70000, 1024, 64)])
+def test_similarity_tolerances(ctx, n, d, q):
+    torch.manual_seed(n + d + q)
+    g = torch.randn(n, d, device="cuda") * (1.0 + 9.0 * torch.rand(n, 1, device="cuda"))
+    t = torch.randn(q, d, device="cuda")
+    t = t / t.norm(dim=-1, keepdim=True)
+    exact = t.double() @ g.double().T
+    scale = g.double().norm(dim=-1)[None, :] * t.double().norm(dim=-1)[:, None]
+    s32 = ctx.similarity(g, t, _capi.PRECISION_FP32)
+    assert ((s32.double() - exact).abs() / scale).max().item() <= 1e-5
+    # in practice the bf16x3 split is as accurate as an fp32 dot product
+    assert ((s32.double() - exact).abs() / scale).max().item() <= 2e-6
+    sbf = ctx.similarity(g, t, _capi.PRECISION_BF16)
+    assert ((sbf.double() - exact).abs() / scale).max().item() <= 2e-2
+    # and bf16 mode equals the product of the bf16-rounded operands up to fp32 accumulation
+    model = t.bfloat16().double() @ g.bfloat16().double().T
+    assert ((sbf.double() - model).abs() / scale).max().item() <= 2e-6
+
+
+def test_similarity_exact_on_dyadic_grid(ctx):
+    w = synthetic.dyadic_grid(5000, 512, 70, 2, seed=12)
+    g, t = w.gallery.cuda(), w.queries.cuda()
+    exact = (t.double() @ g.double().T)
+    for prec in (_capi.PRECISION_FP32, _capi.PRECISION_BF16):     # |k| <= 127 fits bf16 exactly
+        s = ctx.similarity(g, t, prec)
+        assert torch.equal(s.double(), exact)
+
+
+def test_fused_normalisation_flags(ctx):
+    torch.manual_seed(5)
+    g = torch.randn(3000, 256, device="cuda") * 7
+    t = torch.randn(40, 256, device="cuda") * 3
+    s = ctx.similarity(g, t, _capi.PRECISION_FP32, _capi.FLAG_NORMALIZE_QUERIES)
+    want = (t / t.norm(dim=-1, keepdim=True)).double() @ g.double().T
+    assert ((s.double() - want).abs() / g.double().norm(dim=-1)[None, :]).max().item() <= 1e-5
+    s = ctx.similarity(g, t, _capi.PRECISION_FP32, _capi.FLAG_NORMALIZE_QUERIES | _capi.FLAG_NORMALIZE_GALLERY)
+    want = (t / t.norm(dim=-1, keepdim=True)).double() @ (g / g.norm(dim=-1, keepdim=True)).double().T
+    assert (s.double() - want).abs().max().item() <= 1e-5
+
+
+@pytest.mark.parametrize("n,q,c,topn", [(10954, 16, 2, 1000), (10954, 8, 2, 10954), (30011, 6, 7, 30011),
+                                        (30011, 6, 9, 500), (4096, 5, 3, 1), (513, 3, 2, 600)])
+def test_stage_isolation_random_scores(ctx, n, q, c, topn):
+    """The CUDA similarities (random, un-tied data) fed back through the oracle's ranking+metrics must
+    give the identical ranked index lists and metrics."""
+    w = synthetic.clip_like(n, 128, q, c, seed=n + q)
+    g, t = w.gallery.cuda(), w.queries.cuda()
+    lab = torch.from_numpy(w.labels.astype(np.uint8)).cuda()
+    res = ctx.eval_ranking(g, t, lab, c, topn, _capi.PRECISION_FP32, want_per_query=True,
+                           ranked_cap=min(n, topn) + 64, want_scores=True)
+    scores = res["scores"].cpu().numpy()
+    want, orders = spec.eval_scores_matrix(scores, w.labels, topn)
+    lens = res["ranked_len"].cpu().numpy()
+    idx = res["ranked_idx"].cpu().numpy()
+    for i in range(q):
+        assert lens[i] == len(orders[i])
+        assert np.array_equal(idx[i, :lens[i]], orders[i])
+    assert np.abs(res["per_query"].cpu().numpy() - want).max() <= TIGHT
+    assert np.abs(np.asarray(res["mean"]) - want.mean(axis=0)).max() <= TIGHT
+
+
+def test_metrics_match_oracle_on_clip_like_data():
+    """End to end against the oracle's own fp32 similarities (CPU BLAS order): metrics within the 1e-6
+    bar even though individual near-tied ranks may legitimately differ."""
+    w = synthetic.clip_like(20000, 512, 48, 7, seed=9)
+    for topn in (1000, 1.0):
+        want = spec.measure(w.labels, w.gallery, w.queries, topn)
+        got = dvl.evaluate(w.labels, w.gallery.cuda(), w.queries.cuda(), topn)
+        assert max(abs(a - b) for a, b in zip(_flat(got), _flat(want))) <= METRIC_TOL
+
+
+def test_bf16_mode_matches_oracle_on_bf16_rounded_inputs():
+    w = synthetic.clip_like(12000, 256, 32, 2, seed=10)
+    g16 = w.gallery.bfloat16().float()
+    t16 = w.queries.bfloat16().float()
+    want = spec.measure(w.labels, g16, t16, 500)
+    got = dvl.evaluate(w.labels, w.gallery.cuda(), w.queries.cuda(), 500, {"precision": "bf16"})
+    assert max(abs(a - b) for a, b in zip(_flat(got), _flat(want))) <= METRIC_TOL
+    # bf16 gallery handed in directly gives the same numbers
+    got2 = dvl.evaluate(w.labels, w.gallery.cuda().bfloat16(), w.queries.cuda(), 500, {"precision": "bf16"})
+    assert _flat(got2) == _flat(got)
+
+
+def test_gv1_regression_vector():
+    gv = load_golden("gv1.json")
+    torch.manual_seed(gv["seed"])
+    img = torch.randn(gv["n"], gv["d"])
+    txt = torch.randn(gv["q"], gv["d"])
+    txt /= txt.norm(dim=-1, keepdim=True)
+    labels = np.random.RandomState(gv["seed"]).randint(0, gv["c"], size=gv["n"])
+    g, t = img.cuda(), txt.cuda()
+    for key, want in gv["expected"].items():
+        ev, topn = key.split("@")
+        topn = float(topn) if "." in topn else int(topn)
+        got = dvl.eval_ranking(labels, g, t, ev, topn)
+        for k in want:
+            assert abs(got[k] - want[k]) <= METRIC_TOL, (key, k, got[k], want[k])
+
+
+def test_dataframe_entry_points_match_golden(stage_cases):
+    import pandas as pd
+    for case in stage_cases[:40]:
+        lab = np.asarray(case["labels"])
+        if not np.array_equal(np.unique(lab), np.arange(len(np.unique(lab)))):
+            continue
+        df = pd.DataFrame({"score": u32_to_f32(case["scores_u32"]), "label": lab})
+        ms = dvl.compute_skew_metrics(df, case["top_n"])
+        nd = dvl.normalized_discounted_KL(df, case["top_n"])
+        assert abs(ms["maxskew_eq_opp"] - case["maxskew_eq_opp"]) <= TIGHT
+        assert abs(ms["maxskew_dem_par"] - case["maxskew_dem_par"]) <= TIGHT
+        if not math.isnan(case["ndkl_eq_opp"]):
+            assert abs(nd["ndkl_eq_opp"] - case["ndkl_eq_opp"]) <= TIGHT
+            assert abs(nd["ndkl_dem_par"] - case["ndkl_dem_par"]) <= TIGHT
+
+
+def test_edge_cases_and_errors(ctx):
+    w = synthetic.dyadic_grid(300, 64, 3, 2, seed=1)
+    g, t = w.gallery.cuda(), w.queries.cuda()
+    # a label >= n_classes is rejected, not mis-counted
+    bad = torch.full((300,), 5, dtype=torch.uint8, device="cuda")
+    with pytest.raises(_capi.DvlError):
+        ctx.eval_ranking(g, t, bad, 2, 10)
+    with pytest.raises(_capi.DvlError):
+        ctx.eval_ranking(g, t, torch.zeros(300, dtype=torch.uint8, device="cuda"), 1, 0)
+    with pytest.raises(ValueError):
+        dvl.eval_ranking(w.labels[:-1], g, t, "maxskew", 10)
+    # a single gallery row, a single query, depth not a multiple of 64 or 8
+    for (n, d, q) in [(1, 64, 1), (2, 20, 1), (259, 100, 2), (257, 52, 129)]:
+        ww = synthetic.dyadic_grid(n, d, q, min(2, n), seed=n)
+        want = spec.measure(ww.labels, ww.gallery, ww.queries, 1.0)
+        got = dvl.evaluate(ww.labels, ww.gallery.cuda(), ww.queries.cuda(), 1.0)
+        assert max(abs(a - b) for a, b in zip(_flat(got), _flat(want))) <= TIGHT, (n, d, q)
+    # fp16 embeddings (CLIP on CUDA is fp16; the reference does .float() on them)
+    w16 = synthetic.clip_like(5000, 128, 8, 2, seed=3)
+    g16 = w16.gallery.half()
+    want = spec.measure(w16.labels, g16.float(), w16.queries, 100)
+    got = dvl.evaluate(w16.labels, g16.cuda(), w16.queries.cuda(), 100)
+    assert max(abs(a - b) for a, b in zip(_flat(got), _flat(want))) <= METRIC_TOL
+
+
+def test_measure_bias_drop_in_with_stub_encoders():
+    """measure_bias end to end through the reference's signature with stub encoders: the dataset hands out
+    embeddings as "images", the model's encoders are identities / a fixed table."""
+    from debias_vision_lang_b200.datasets import EmbeddingGallery
+    w = synthetic.clip_like(3000, 64, 319, 2, seed=21)
+    raw_text = w.queries * 3.0          # un-normalised text features: get_prompt_embeddings normalises
+
+    class Stub(torch.nn.Module):
+        def encode_image(self, x):
+            return x
+
+        def encode_text(self, tok):
+            return raw_text.cuda()[tok]
+
+    tok = lambda prompts: torch.arange(len(prompts))
+    got = dvl.measure_bias(Stub(), None, tok, attribute="gender",
+                           opts={"dataset": EmbeddingGallery(w.gallery, w.labels), "num_workers": 0})
+    t_norm = raw_text / raw_text.norm(dim=-1, keepdim=True)
+    want = spec.measure(w.labels, w.gallery, t_norm, 1.0)
+    assert set(got) == {"maxskew", "ndkl"} and set(got["ndkl"]) == {"eq_opp", "dem_par"}
+    assert max(abs(a - b) for a, b in zip(_flat(got), _flat(want))) <= METRIC_TOL
+
+
+def test_full_size_properties_cfg2(ctx):
+    """BASELINE config 2 at full size (108,501 x 512 x 319, C=7, k=N): size-independent properties.
+    dem_par MaxSkew@N is exactly 0 and eq_opp MaxSkew@N = ln(C*max_c n_c/N); every
+    ranked list is a permutation; scores along each ranked list are non-increasing; the run is
+    bit-reproducible."""
+    w = synthetic.baseline_workload("cfg2", device="cuda")
+    n, q = w.gallery.shape[0], 32
+    lab = torch.from_numpy(w.labels.astype(np.uint8)).cuda()
+    t = w.queries[:q].contiguous()
+    res = ctx.eval_ranking(w.gallery, t, lab, 7, n, _capi.PRECISION_FP32, want_per_query=True, ranked_cap=n,
+                           want_scores=True)
+    pq = res["per_query"].cpu().numpy()
+    counts = np.bincount(w.labels, minlength=7)
+    assert np.all(pq[:, 1] == 0.0)
+    assert np.abs(pq[:, 0] - math.log(7 * counts.max() / n)).max() <= 1e-12
+    assert torch.all(res["ranked_len"] == n)
+    idx = res["ranked_idx"].long()
+    assert torch.equal(torch.sort(idx, dim=1).values, torch.arange(n, device="cuda")[None, :].expand(q, n))
+    ranked_scores = torch.gather(res["scores"], 1, idx)
+    assert torch.all(ranked_scores[:, 1:] <= ranked_scores[:, :-1])
+    # ties broken by lowest index
+    tie = ranked_scores[:, 1:] == ranked_scores[:, :-1]
+    assert torch.all(idx[:, 1:][tie] > idx[:, :-1][tie])
+    res2 = ctx.eval_ranking(w.gallery, t, lab, 7, n, _capi.PRECISION_FP32, want_per_query=True)
+    assert torch.equal(res2["per_query"], res["per_query"])
+    # NDKL of 4 sampled queries against the oracle on the CUDA path's own scores
+    want, _ = spec.eval_scores_matrix(res["scores"][:4].cpu().numpy(), w.labels, n)
+    assert np.abs(pq[:4] - want).max() <= TIGHT

@@ -98,3 +98,22 @@ def test_spec_against_live_reference_random():
                     abs(b["eq_opp"] - nd["ndkl_eq_opp"]), abs(b["dem_par"] - nd["ndkl_dem_par"]))
         assert c_eff >= 1
     assert worst <= 1e-12, worst
+
+
+def test_row_by_row_port_matches_golden(stage_cases, ranking_cases):
+    import pandas as pd
+    from oracle import port
+    for case in stage_cases[::3]:
+        lab = np.asarray(case["labels"])
+        df = pd.DataFrame({"score": u32_to_f32(case["scores_u32"]), "label": lab})
+        ms = port.maxskew_one_query(df, case["top_n"])
+        assert abs(ms["eq_opp"] - case["maxskew_eq_opp"]) <= TOL and abs(ms["dem_par"] - case["maxskew_dem_par"]) <= TOL
+        nd = port.ndkl_one_query(df, case["top_n"])
+        if not math.isnan(case["ndkl_eq_opp"]):
+            assert abs(nd["eq_opp"] - case["ndkl_eq_opp"]) <= TOL and abs(nd["dem_par"] - case["ndkl_dem_par"]) <= TOL
+    case = ranking_cases[0]
+    w, topn = build_ranking_workload(case)
+    got = port.measure(w.labels, w.gallery, w.queries, topn)
+    for ev in ("maxskew", "ndkl"):
+        for k in ("eq_opp", "dem_par"):
+            assert abs(got[ev][k] - case["expected"][ev][k]) <= 1e-12
