@@ -160,7 +160,7 @@ int run_sort_and_score(Ctx* c, const uint8_t* labels, int64_t n, int q, int n_cl
   DVL_TRY(ensure(c, c->mean_dev, 8 * sizeof(double)));
   {
     StageScope scope(c, DVL_STAGE_PREP, st);
-    DVL_TRY(ensure_log_table(c, (n > top_n ? n : top_n) + 2, st));
+    DVL_TRY(ensure_metric_tables(c, (n > top_n ? n : top_n) + 2, st));
     DVL_TRY(launch_class_counts(c, labels, n, n_classes, (unsigned long long*)c->class_counts.ptr, st));
   }
 
@@ -190,7 +190,7 @@ int run_sort_and_score(Ctx* c, const uint8_t* labels, int64_t n, int q, int n_cl
   m.q = q;
   m.n_classes = n_classes;
   m.class_counts = (const unsigned long long*)c->class_counts.ptr;
-  m.log_tab = (const double*)c->log_tab.ptr;
+  m.avail = nullptr;
   m.per_query = out_per_query != nullptr ? out_per_query : (double*)c->per_query.ptr;
   m.ranked_len = ranked_len;
   {
@@ -268,7 +268,8 @@ DVL_API int dvl_destroy(dvl_ctx* c) {
   cudaDeviceSynchronize();
   dvl::DevBuf* bufs[] = {&c->gal_planes, &c->qry_planes, &c->gal_inv_norm, &c->qry_inv_norm, &c->keys[0], &c->keys[1],
                          &c->labs[0], &c->labs[1], &c->idxs[0], &c->idxs[1], &c->tile_hist, &c->class_counts,
-                         &c->log_tab, &c->per_query, &c->mean_dev, &c->scores_tmp, &c->seg_len, &c->h_gallery,
+                         &c->log_tab, &c->per_query, &c->mean_dev, &c->scores_tmp, &c->seg_len, &c->sub_cnt, &c->partial,
+                         &c->h_gallery,
                          &c->h_queries, &c->h_labels};
   for (dvl::DevBuf* b : bufs)
     if (b->ptr != nullptr) cudaFree(b->ptr);

@@ -29,7 +29,7 @@ struct Ctx {
   // named workspace buffers
   DevBuf gal_planes, qry_planes, gal_inv_norm, qry_inv_norm;
   DevBuf keys[2], labs[2], idxs[2];
-  DevBuf tile_hist, class_counts, log_tab, per_query, mean_dev, scores_tmp, seg_len;
+  DevBuf tile_hist, class_counts, log_tab, per_query, mean_dev, scores_tmp, seg_len, sub_cnt, partial;
   DevBuf h_gallery, h_queries, h_labels;   // staging for the host-input entry point
   double* mean_pinned = nullptr;           // 4 doubles, pinned host
   int64_t log_tab_len = 0;
@@ -88,8 +88,6 @@ int launch_split_rows(Ctx* c, const void* src, int dtype, int64_t rows, int d, i
                       __nv_bfloat16* dst, float* inv_norm, cudaStream_t st);
 int launch_class_counts(Ctx* c, const uint8_t* labels, int64_t n, int n_classes, unsigned long long* counts,
                         cudaStream_t st);
-// table[i] = ln(i) for i in [0, len) with table[0] = 0
-int ensure_log_table(Ctx* c, int64_t len, cudaStream_t st);
 
 // ---- gemm.cu ---------------------------------------------------------------------------
 struct GemmArgs {
@@ -139,10 +137,12 @@ struct MetricArgs {
   int q;
   int n_classes;
   const unsigned long long* class_counts;  // [n_classes], global
-  const double* log_tab;                   // ln(i)
+  const int32_t* avail;                    // [q] or null: rows available per query (streaming top-k route)
   double* per_query;                       // [q][4]
-  int32_t* ranked_len;                     // [q] or null
+  int32_t* ranked_len;                     // [q], always written
 };
+// fp64 tables XL, WI, PW, PWL of metrics.cu for indices < len
+int ensure_metric_tables(Ctx* c, int64_t len, cudaStream_t st);
 int launch_metrics(Ctx* c, const MetricArgs& a, cudaStream_t st);
 int launch_mean(Ctx* c, const double* per_query, int q, double* mean_dev, cudaStream_t st);
 int launch_copy_ranked(Ctx* c, const int32_t* idx_sorted, int64_t ldi, const int32_t* ranked_len, int q,

@@ -3,13 +3,27 @@
 // both desired distributions (eq_opp, dem_par), all arithmetic in float64 like the
 // reference's numpy/math, then the mean over queries (measuring_bias.py:119).
 //
-// One CTA per query.  Each warp owns a contiguous slice of the ranked prefix and walks it
-// 32 ranks at a time: per class c one ballot + popc gives every lane its prefix count
-// h_c(i); with S1 = sum_c h_c ln h_c and S2 = sum_c h_c ln d_c
-//     KL(h(i)/i || d) = (S1 - S2)/i - ln i
-// so a rank costs C table look-ups (ln from an fp64 table) and no transcendental.
-// m (the number of ranked rows, > top_n when boundary ties were kept; selectn.py:176-182)
-// is found by binary search in the sorted keys.
+// NDKL without transcendental or division work per ranked row, and with work per row that does
+// not grow with the number of classes.  With h_c(i) the prefix class counts, w_i = 1/log2(i+1):
+//     KL(h(i)/i || d) = (1/i) [sum_c h_c ln h_c - sum_c h_c ln d_c] - ln i
+// Both sums only change, at rank j, in the term of row j's own class c = l_j, whose count becomes
+// t_j (the row is the t_j-th of its class).  Summing by parts over i >= j:
+//     sum_i w_i KL_i = sum_j T_j (DXL[t_j] - ln d_{l_j})  -  PWL[m]
+//         T_j    = PWI[m] - PWI[j-1],   PWI[i] = sum_{r<=i} w_r / r
+//         DXL[t] = t ln t - (t-1) ln(t-1)
+//         PWL[m] = sum_{i<=m} w_i ln i,  PW[m] = sum_{i<=m} w_i   (eq_opp: ln d = -ln C gives + ln C * PW[m])
+// and Z(top_n) = PW[top_n] (measuring_bias.py:39).  DXL, PWI, PW, PWL are fp64 tables built once
+// per context, so a ranked row costs one ballot+popc per class (its own-class prefix count),
+// two table look-ups and three fp64 FMAs.
+//
+// Kernels (all HBM/L2-bound byte work, one byte per ranked row):
+//   ranked_len   m_q: binary search for the end of the top_n-th key's tie run (keep="all",
+//                selectn.py:176-182) and for the first NaN key (dropped rows, selectn.py:133-134)
+//   sub_counts   class counts of every 1024-row sub-slice (one warp each, SIMD byte compares)
+//   sub_scan     exclusive prefix over the sub-slices of a query
+//   ndkl_partial one warp per sub-slice: 32 rounds of warp-ballot own-class prefix counts
+//   finalize     fixed-order sum of the partials, MaxSkew from the total counts, 4 doubles/query
+//   mean         fixed-tree mean over the queries
 #include "dvl_common.cuh"
 #include "dvl_internal.h"
 
@@ -17,185 +31,290 @@ namespace dvl {
 
 namespace {
 
-constexpr int kMetricThreads = 256;
-constexpr int kMetricWarps = kMetricThreads / 32;
+constexpr int kSub = 1024;            // ranked rows per warp-sized sub-slice
+constexpr int kWarpsPerCta = 4;
 constexpr double kLn2 = 0.693147180559945309417232121458176568;
 
-// Z(top_n) = sum_{i=1..top_n} 1/log2(i+1)   (measuring_bias.py:39), deterministic tree
-__global__ void __launch_bounds__(1024) ndkl_norm_kernel(const double* __restrict__ ln_tab, int64_t top_n,
-                                                         double* __restrict__ z_out) {
-  __shared__ double sh[32];
-  double acc = 0.0;
-  for (int64_t i = 1 + threadIdx.x; i <= top_n; i += blockDim.x) acc += kLn2 / ln_tab[i + 1];
-#pragma unroll
-  for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
-  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = acc;
+// ---- tables ------------------------------------------------------------------------------
+// single CTA so that the prefix sums have one fixed summation order
+__global__ void __launch_bounds__(1024) metric_tables_kernel(double* __restrict__ dxl, double* __restrict__ pwi,
+                                                             double* __restrict__ pw, double* __restrict__ pwl,
+                                                             int64_t len) {
+  __shared__ double sh[3][1024];
+  const int t = threadIdx.x;
+  const int64_t per = (len + 1023) / 1024;
+  const int64_t lo = (int64_t)t * per;
+  const int64_t hi = (lo + per < len) ? lo + per : len;
+  double sw = 0.0, swl = 0.0, swi = 0.0;
+  for (int64_t i = lo; i < hi; ++i) {
+    if (i == 0) continue;
+    const double w = kLn2 / log((double)(i + 1));
+    sw += w;
+    swl += w * log((double)i);
+    swi += w / (double)i;
+  }
+  sh[0][t] = sw;
+  sh[1][t] = swl;
+  sh[2][t] = swi;
   __syncthreads();
-  if (threadIdx.x < 32) {
-    double v = sh[threadIdx.x];
-#pragma unroll
-    for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
-    if (threadIdx.x == 0) *z_out = v;
+  if (t < 3) {
+    double a = 0.0;
+    for (int k = 0; k < 1024; ++k) {
+      const double x = sh[t][k];
+      sh[t][k] = a;
+      a += x;
+    }
+  }
+  __syncthreads();
+  sw = sh[0][t];
+  swl = sh[1][t];
+  swi = sh[2][t];
+  for (int64_t i = lo; i < hi; ++i) {
+    if (i == 0) {
+      dxl[0] = 0.0; pwi[0] = 0.0; pw[0] = 0.0; pwl[0] = 0.0;
+      continue;
+    }
+    const double di = (double)i;
+    const double ln_i = log(di);
+    const double w = kLn2 / log((double)(i + 1));
+    sw += w;
+    swl += w * ln_i;
+    swi += w / di;
+    // i ln i - (i-1) ln(i-1) = ln i + (i-1) ln(1 + 1/(i-1)), without the cancellation
+    dxl[i] = (i == 1) ? 0.0 : ln_i + (di - 1.0) * log1p(1.0 / (di - 1.0));
+    pwi[i] = swi;
+    pw[i] = sw;
+    pwl[i] = swl;
   }
 }
 
-struct MetricParams {
-  const uint32_t* keys;
-  const uint8_t* labs;
-  int64_t ldk, ldl;
-  int64_t n_avail, n_gallery, top_n;
-  int n_classes;
-  const unsigned long long* class_counts;
-  const double* ln_tab;
-  const double* z;
-  double* per_query;
-  int32_t* ranked_len;
-};
-
-__global__ void __launch_bounds__(kMetricThreads) metrics_kernel(const MetricParams p) {
-  __shared__ unsigned int wcnt[kMetricWarps][kMaxClasses];
-  __shared__ double wacc[kMetricWarps][2];
-  __shared__ long long sh_m;
-  const int q = blockIdx.x;
-  const int warp = threadIdx.x >> 5;
-  const int lane = threadIdx.x & 31;
-  const int C = p.n_classes;
-  const uint8_t* lab = p.labs + (int64_t)q * p.ldl;
-
-  if (threadIdx.x == 0) {
-    long long m = p.n_avail;
-    if (p.keys != nullptr) {
-      const uint32_t* k = p.keys + (int64_t)q * p.ldk;
-      // rows with a NaN score are dropped (selectn.py:133-134): they carry the largest key
-      long long lo = 0, hi = p.n_avail;
+// ---- m_q ---------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) ranked_len_kernel(const uint32_t* __restrict__ keys, int64_t ldk,
+                                                         const int32_t* __restrict__ avail, int64_t n_avail,
+                                                         int64_t top_n, int q, int32_t* __restrict__ ranked_len) {
+  const int qi = blockIdx.x * blockDim.x + threadIdx.x;
+  if (qi >= q) return;
+  long long m;
+  if (avail != nullptr) {
+    m = avail[qi];                       // streaming top-k route: the list already ends at the tie run
+  } else if (keys != nullptr) {
+    const uint32_t* k = keys + (int64_t)qi * ldk;
+    long long lo = 0, hi = n_avail;      // first NaN key
+    while (lo < hi) {
+      const long long mid = (lo + hi) >> 1;
+      if (k[mid] < kNanKey) lo = mid + 1; else hi = mid;
+    }
+    const long long n_valid = lo;
+    m = n_valid;
+    if (top_n < n_valid) {
+      const uint32_t kth = k[top_n - 1];
+      lo = top_n; hi = n_valid;          // first position whose key is > kth
       while (lo < hi) {
         const long long mid = (lo + hi) >> 1;
-        if (k[mid] < kNanKey) lo = mid + 1; else hi = mid;
+        if (k[mid] <= kth) lo = mid + 1; else hi = mid;
       }
-      const long long n_valid = lo;
-      m = n_valid;
-      if (p.top_n < n_valid) {
-        const uint32_t kth = k[p.top_n - 1];
-        lo = p.top_n; hi = n_valid;            // first position whose key is > kth
-        while (lo < hi) {
-          const long long mid = (lo + hi) >> 1;
-          if (k[mid] <= kth) lo = mid + 1; else hi = mid;
-        }
-        m = lo;
-      }
-    } else if (p.top_n < m) {
-      m = p.top_n;
+      m = lo;
     }
-    sh_m = m;
+  } else {
+    m = top_n < n_avail ? top_n : n_avail;
   }
-  __syncthreads();
-  const long long m = sh_m;
-  // contiguous slice per warp, a multiple of 32 ranks
-  long long slice = (m + kMetricWarps - 1) / kMetricWarps;
-  slice = (slice + 31) & ~31ll;
-  const long long begin = (long long)warp * slice;
-  long long end = begin + slice;
+  ranked_len[qi] = (int32_t)m;
+}
+
+// ---- class counts of each sub-slice ---------------------------------------------------------
+template <int C>
+__global__ void __launch_bounds__(32 * kWarpsPerCta)
+sub_counts_kernel(const uint8_t* __restrict__ labs, int64_t ldl, const int32_t* __restrict__ ranked_len,
+                  int subs, int stride, uint32_t* __restrict__ sub_cnt) {
+  const int q = blockIdx.y;
+  const int sub = blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (sub >= subs) return;
+  const long long m = ranked_len[q];
+  const long long begin = (long long)sub * kSub;
+  long long end = begin + kSub;
   if (end > m) end = m;
-
-  // phase 1: class counts of the slice
-  unsigned int cnt[kMaxClasses];
+  // the row pitch is a multiple of 256 and kSub of 4: 4-byte label loads are aligned
+  const uint8_t* lab = labs + (int64_t)q * ldl;
+  uint32_t cnt[C];
 #pragma unroll
-  for (int c = 0; c < kMaxClasses; ++c) cnt[c] = 0;
-  for (long long r0 = begin; r0 < end; r0 += 32) {
-    const long long r = r0 + lane;
-    const int l = (r < end) ? (int)lab[r] : 255;
+  for (int c = 0; c < C; ++c) cnt[c] = 0;
+  for (long long r0 = begin + 4 * lane; r0 < end; r0 += 128) {
+    uint32_t four = __ldg(reinterpret_cast<const uint32_t*>(lab + r0));
+    const int valid = (end - r0 >= 4) ? 4 : (int)(end - r0);
+    if (valid < 4) four |= 0xFFFFFFFFu << (8 * valid);      // labels past the end match no class
 #pragma unroll
-    for (int c = 0; c < kMaxClasses; ++c)
-      if (c < C) cnt[c] += __popc(__ballot_sync(0xffffffffu, l == c));
+    for (int c = 0; c < C; ++c) cnt[c] += __popc(__vcmpeq4(four, 0x01010101u * c)) >> 3;
+  }
+#pragma unroll
+  for (int c = 0; c < C; ++c) {
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) cnt[c] += __shfl_xor_sync(0xffffffffu, cnt[c], off);
   }
   if (lane == 0) {
+    uint32_t* out = sub_cnt + ((int64_t)q * stride + sub) * kMaxClasses;
 #pragma unroll
-    for (int c = 0; c < kMaxClasses; ++c) wcnt[warp][c] = cnt[c];
+    for (int c = 0; c < kMaxClasses; ++c) out[c] = 0;
+#pragma unroll
+    for (int c = 0; c < C; ++c) out[c] = cnt[c];
+  }
+}
+
+// exclusive prefix over sub-slices, one thread per (query, class); totals in slot `subs`
+__global__ void __launch_bounds__(128) sub_scan_kernel(uint32_t* __restrict__ sub_cnt, int q, int subs) {
+  const int gid = blockIdx.x * blockDim.x + threadIdx.x;
+  if (gid >= q * kMaxClasses) return;
+  const int qi = gid / kMaxClasses, c = gid % kMaxClasses;
+  uint32_t* base = sub_cnt + (int64_t)qi * (subs + 1) * kMaxClasses + c;
+  uint32_t run = 0;
+  for (int s = 0; s < subs; ++s) {
+    const uint32_t v = base[(int64_t)s * kMaxClasses];
+    base[(int64_t)s * kMaxClasses] = run;
+    run += v;
+  }
+  base[(int64_t)subs * kMaxClasses] = run;
+}
+
+struct PartialParams {
+  const uint8_t* labs;
+  int64_t ldl;
+  const int32_t* ranked_len;
+  int subs;
+  int64_t n_gallery;
+  const uint32_t* sub_pref;               // [q][subs+1][16] exclusive prefixes (+ totals)
+  const unsigned long long* class_counts; // global n_c
+  const double* dxl;
+  const double* pwi;
+  double* partial;                        // [q][subs][2]
+};
+
+template <int C>
+__global__ void __launch_bounds__(32 * kWarpsPerCta) ndkl_partial_kernel(const PartialParams p) {
+  __shared__ double ln_d[kMaxClasses];
+  if (threadIdx.x < kMaxClasses) {
+    double v = 0.0;
+    if (threadIdx.x < C) {
+      const unsigned long long nc = p.class_counts[threadIdx.x];
+      // dem_par: max(count, 1) / N   (measuring_bias.py:27)
+      v = log((double)(nc > 0 ? nc : 1ull) / (double)p.n_gallery);
+    }
+    ln_d[threadIdx.x] = v;
   }
   __syncthreads();
-
-  // per-class constants: ln d_c for dem_par (max(count,1)/N, measuring_bias.py:27)
-  double ln_d[kMaxClasses];
-  unsigned int base[kMaxClasses];
-  int c_present = 0;
+  const int q = blockIdx.y;
+  const int sub = blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (sub >= p.subs) return;
+  const long long m = p.ranked_len[q];
+  const long long begin = (long long)sub * kSub;
+  long long end = begin + kSub;
+  if (end > m) end = m;
+  double acc_eq = 0.0, acc_d = 0.0;
+  if (begin < end) {
+    const uint8_t* lab = p.labs + (int64_t)q * p.ldl;
+    const uint32_t* pref = p.sub_pref + ((int64_t)q * (p.subs + 1) + sub) * kMaxClasses;
+    uint32_t base[C];
 #pragma unroll
-  for (int c = 0; c < kMaxClasses; ++c) {
-    ln_d[c] = 0.0;
-    base[c] = 0;
-    if (c < C) {
-      const unsigned long long nc = p.class_counts[c];
-      c_present += (nc > 0);
-      ln_d[c] = log((double)(nc > 0 ? nc : 1ull) / (double)p.n_gallery);
-      for (int w = 0; w < warp; ++w) base[c] += wcnt[w][c];
-    }
-  }
-  const double ln_c = log((double)c_present);
-
-  // phase 2: discounted KL of every prefix in the slice
-  const unsigned int le_mask = (lane == 31) ? 0xffffffffu : ((2u << lane) - 1u);
-  double acc_eq = 0.0, acc_dp = 0.0;
-  for (long long r0 = begin; r0 < end; r0 += 32) {
-    const long long r = r0 + lane;
-    const bool ok = r < end;
-    const int l = ok ? (int)lab[r] : 255;
-    double s1 = 0.0, s2 = 0.0;
+    for (int c = 0; c < C; ++c) base[c] = pref[c];
+    const double pwi_m = __ldg(p.pwi + m);
+    const uint32_t le_mask = (lane == 31) ? 0xffffffffu : ((2u << lane) - 1u);
+#pragma unroll 2
+    for (long long r0 = begin; r0 < end; r0 += 32) {
+      const long long r = r0 + lane;                 // 0-based rank; row j = r + 1
+      const bool ok = r < end;
+      const int l = ok ? (int)__ldg(lab + r) : 255;
+      uint32_t t = 0;                                // this row is the t-th of its class
 #pragma unroll
-    for (int c = 0; c < kMaxClasses; ++c) {
-      if (c < C) {
-        const unsigned int mask = __ballot_sync(0xffffffffu, l == c);
-        const unsigned int h = base[c] + __popc(mask & le_mask);
+      for (int c = 0; c < C; ++c) {
+        const uint32_t mask = __ballot_sync(0xffffffffu, l == c);
+        if (l == c) t = base[c] + __popc(mask & le_mask);
         base[c] += __popc(mask);
-        const double hd = (double)h;
-        s1 = fma(hd, p.ln_tab[h], s1);
-        s2 = fma(hd, ln_d[c], s2);
+      }
+      if (ok) {
+        const double tj = pwi_m - __ldg(p.pwi + r);  // PWI[m] - PWI[j-1]
+        acc_eq = fma(tj, __ldg(p.dxl + t), acc_eq);
+        acc_d = fma(tj, ln_d[l], acc_d);
       }
     }
-    if (ok) {
-      const long long i = r + 1;
-      const double inv_i = 1.0 / (double)i;
-      const double ln_i = p.ln_tab[i];
-      const double w = kLn2 / p.ln_tab[i + 1];        // 1 / log2(i + 1)
-      acc_eq = fma(fma(s1, inv_i, ln_c - ln_i), w, acc_eq);
-      acc_dp = fma(fma(s1 - s2, inv_i, -ln_i), w, acc_dp);
-    }
-  }
 #pragma unroll
-  for (int off = 16; off > 0; off >>= 1) {
-    acc_eq += __shfl_xor_sync(0xffffffffu, acc_eq, off);
-    acc_dp += __shfl_xor_sync(0xffffffffu, acc_dp, off);
+    for (int off = 16; off > 0; off >>= 1) {
+      acc_eq += __shfl_xor_sync(0xffffffffu, acc_eq, off);
+      acc_d += __shfl_xor_sync(0xffffffffu, acc_d, off);
+    }
   }
   if (lane == 0) {
-    wacc[warp][0] = acc_eq;
-    wacc[warp][1] = acc_dp;
+    double* out = p.partial + ((int64_t)q * p.subs + sub) * 2;
+    out[0] = acc_eq;
+    out[1] = acc_eq - acc_d;
   }
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    double ndkl_eq = 0.0, ndkl_dp = 0.0;
-    for (int w = 0; w < kMetricWarps; ++w) {
-      ndkl_eq += wacc[w][0];
-      ndkl_dp += wacc[w][1];
-    }
-    const double z = *p.z;
-    // MaxSkew over the m ranked rows (measuring_bias.py:58-70)
-    double ms_eq = 0.0, ms_dp = 0.0;
-    for (int c = 0; c < C; ++c) {
-      const unsigned long long nc = p.class_counts[c];
-      if (nc == 0) continue;                   // Counter(df.label) has no such key
-      unsigned int h = 0;
-      for (int w = 0; w < kMetricWarps; ++w) h += wcnt[w][c];
-      double pp = (double)h / (double)p.top_n;
-      if (pp == 0.0) pp = 1.0 / (double)p.top_n;
-      const double lp = log(pp);
-      ms_eq = fmax(ms_eq, lp - log(1.0 / (double)c_present));
-      ms_dp = fmax(ms_dp, lp - log((double)nc / (double)p.n_gallery));
-    }
-    double* out = p.per_query + (int64_t)q * 4;
-    out[DVL_MAXSKEW_EQ_OPP] = ms_eq;
-    out[DVL_MAXSKEW_DEM_PAR] = ms_dp;
-    out[DVL_NDKL_EQ_OPP] = ndkl_eq / z;
-    out[DVL_NDKL_DEM_PAR] = ndkl_dp / z;
-    if (p.ranked_len != nullptr) p.ranked_len[q] = (int32_t)m;
+}
+
+template <int C>
+void launch_counts_and_partials(const PartialParams& p, dim3 grid, int stride, uint32_t* sub_cnt_q, bool counts,
+                                cudaStream_t st) {
+  if (counts)
+    sub_counts_kernel<C><<<grid, 32 * kWarpsPerCta, 0, st>>>(p.labs, p.ldl, p.ranked_len, p.subs, stride, sub_cnt_q);
+  else
+    ndkl_partial_kernel<C><<<grid, 32 * kWarpsPerCta, 0, st>>>(p);
+}
+
+void dispatch_classes(int n_classes, const PartialParams& p, dim3 grid, int stride, uint32_t* sub_cnt_q, bool counts,
+                      cudaStream_t st) {
+  switch (n_classes) {
+#define DVL_CASE(C) case C: launch_counts_and_partials<C>(p, grid, stride, sub_cnt_q, counts, st); break;
+    DVL_CASE(1) DVL_CASE(2) DVL_CASE(3) DVL_CASE(4) DVL_CASE(5) DVL_CASE(6) DVL_CASE(7) DVL_CASE(8)
+    DVL_CASE(9) DVL_CASE(10) DVL_CASE(11) DVL_CASE(12) DVL_CASE(13) DVL_CASE(14) DVL_CASE(15) DVL_CASE(16)
+#undef DVL_CASE
+    default: break;
   }
+}
+
+struct FinalParams {
+  const int32_t* ranked_len;
+  int q;
+  int n_classes;
+  int subs;
+  int64_t n_gallery, top_n;
+  const uint32_t* sub_pref;
+  const unsigned long long* class_counts;
+  const double* partial;
+  const double* pw;
+  const double* pwl;
+  double* per_query;
+};
+
+__global__ void __launch_bounds__(128) finalize_kernel(const FinalParams p) {
+  const int qi = blockIdx.x * blockDim.x + threadIdx.x;
+  if (qi >= p.q) return;
+  const long long m = p.ranked_len[qi];
+  double s_eq = 0.0, s_dp = 0.0;
+  const double* part = p.partial + (int64_t)qi * p.subs * 2;
+  for (int s = 0; s < p.subs; ++s) {
+    s_eq += part[2 * s];
+    s_dp += part[2 * s + 1];
+  }
+  int c_present = 0;
+  for (int c = 0; c < p.n_classes; ++c) c_present += (p.class_counts[c] > 0);
+  const double z = p.pw[p.top_n];
+  const double ndkl_eq = (s_eq + log((double)c_present) * p.pw[m] - p.pwl[m]) / z;
+  const double ndkl_dp = (s_dp - p.pwl[m]) / z;   // s_dp = sum_j T_j (DXL[t_j] - ln d_{l_j})
+  // MaxSkew over the m ranked rows (measuring_bias.py:58-70)
+  const uint32_t* tot = p.sub_pref + ((int64_t)qi * (p.subs + 1) + p.subs) * kMaxClasses;
+  double ms_eq = 0.0, ms_dp = 0.0;
+  for (int c = 0; c < p.n_classes; ++c) {
+    const unsigned long long nc = p.class_counts[c];
+    if (nc == 0) continue;                       // Counter(df.label) has no such key
+    double pp = (double)tot[c] / (double)p.top_n;
+    if (pp == 0.0) pp = 1.0 / (double)p.top_n;   // "no log of 0" (:64-65)
+    const double lp = log(pp);
+    ms_eq = fmax(ms_eq, lp - log(1.0 / (double)c_present));
+    ms_dp = fmax(ms_dp, lp - log((double)nc / (double)p.n_gallery));
+  }
+  double* out = p.per_query + (int64_t)qi * 4;
+  out[DVL_MAXSKEW_EQ_OPP] = ms_eq;
+  out[DVL_MAXSKEW_DEM_PAR] = ms_dp;
+  out[DVL_NDKL_EQ_OPP] = (m > 0) ? ndkl_eq : 0.0;
+  out[DVL_NDKL_DEM_PAR] = (m > 0) ? ndkl_dp : 0.0;
 }
 
 // mean over queries, fixed reduction tree (measuring_bias.py:119)
@@ -236,31 +355,77 @@ __global__ void __launch_bounds__(256) copy_ranked_kernel(const int32_t* __restr
 
 }  // namespace
 
+int ensure_metric_tables(Ctx* c, int64_t len, cudaStream_t st) {
+  if (len <= c->log_tab_len) return DVL_OK;
+  const int64_t want = len + len / 8 + 1024;
+  DVL_TRY(ensure(c, c->log_tab, (size_t)want * 4 * sizeof(double)));
+  double* base = (double*)c->log_tab.ptr;
+  metric_tables_kernel<<<1, 1024, 0, st>>>(base, base + want, base + 2 * want, base + 3 * want, want);
+  DVL_LAUNCH_CHECK(c, "metric_tables_kernel");
+  c->log_tab_len = want;
+  return DVL_OK;
+}
+
 int launch_metrics(Ctx* c, const MetricArgs& a, cudaStream_t st) {
   if (a.n_classes < 1 || a.n_classes > kMaxClasses) return set_error(c, DVL_ERR_INVALID, "n_classes out of range");
   if (a.top_n < 1) return set_error(c, DVL_ERR_INVALID, "top_n must be >= 1");
   const int64_t tab_need = (a.n_avail > a.top_n ? a.n_avail : a.top_n) + 2;
-  if (tab_need > c->log_tab_len) return set_error(c, DVL_ERR_INVALID, "log table too short");
-  DVL_TRY(ensure(c, c->mean_dev, 8 * sizeof(double)));
-  double* z = (double*)c->mean_dev.ptr + 4;
-  ndkl_norm_kernel<<<1, 1024, 0, st>>>(a.log_tab, a.top_n, z);
-  DVL_LAUNCH_CHECK(c, "ndkl_norm_kernel");
-  MetricParams p;
-  p.keys = a.keys;
-  p.labs = a.labs;
-  p.ldk = a.ldk;
-  p.ldl = a.ldl;
-  p.n_avail = a.n_avail;
-  p.n_gallery = a.n_gallery;
-  p.top_n = a.top_n;
-  p.n_classes = a.n_classes;
-  p.class_counts = a.class_counts;
-  p.ln_tab = a.log_tab;
-  p.z = z;
-  p.per_query = a.per_query;
-  p.ranked_len = a.ranked_len;
-  metrics_kernel<<<(unsigned)a.q, kMetricThreads, 0, st>>>(p);
-  DVL_LAUNCH_CHECK(c, "metrics_kernel");
+  if (tab_need > c->log_tab_len) return set_error(c, DVL_ERR_INVALID, "metric tables too short");
+  const int64_t tab = c->log_tab_len;
+  const double* dxl = (const double*)c->log_tab.ptr;
+  const double* pwi = dxl + tab;
+  const double* pw = dxl + 2 * tab;
+  const double* pwl = dxl + 3 * tab;
+  // boundary ties may extend the ranked prefix to every available row
+  const int subs = a.n_avail > kSub ? (int)((a.n_avail + kSub - 1) / kSub) : 1;
+  DVL_TRY(ensure(c, c->sub_cnt, (size_t)a.q * (subs + 1) * kMaxClasses * sizeof(uint32_t)));
+  DVL_TRY(ensure(c, c->partial, (size_t)a.q * subs * 2 * sizeof(double)));
+  uint32_t* sub_cnt = (uint32_t*)c->sub_cnt.ptr;
+  double* partial = (double*)c->partial.ptr;
+
+  ranked_len_kernel<<<(a.q + 127) / 128, 128, 0, st>>>(a.keys, a.ldk, a.avail, a.n_avail, a.top_n, a.q, a.ranked_len);
+  DVL_LAUNCH_CHECK(c, "ranked_len_kernel");
+  const unsigned bx = (unsigned)((subs + kWarpsPerCta - 1) / kWarpsPerCta);
+  for (int phase = 0; phase < 2; ++phase) {
+    for (int q0 = 0; q0 < a.q; q0 += 65535) {
+      const int qn = (a.q - q0) < 65535 ? (a.q - q0) : 65535;
+      dim3 grid(bx, (unsigned)qn);
+      PartialParams p;
+      p.labs = a.labs + (int64_t)q0 * a.ldl;
+      p.ldl = a.ldl;
+      p.ranked_len = a.ranked_len + q0;
+      p.subs = subs;
+      p.n_gallery = a.n_gallery;
+      p.sub_pref = sub_cnt + (int64_t)q0 * (subs + 1) * kMaxClasses;
+      p.class_counts = a.class_counts;
+      p.dxl = dxl;
+      p.pwi = pwi;
+      p.partial = partial + (int64_t)q0 * subs * 2;
+      // counts are written with a (subs + 1) stride so that the scan can append the totals
+      dispatch_classes(a.n_classes, p, grid, subs + 1, sub_cnt + (int64_t)q0 * (subs + 1) * kMaxClasses, phase == 0,
+                       st);
+      DVL_LAUNCH_CHECK(c, phase == 0 ? "sub_counts_kernel" : "ndkl_partial_kernel");
+    }
+    if (phase == 0) {
+      sub_scan_kernel<<<(a.q * kMaxClasses + 127) / 128, 128, 0, st>>>(sub_cnt, a.q, subs);
+      DVL_LAUNCH_CHECK(c, "sub_scan_kernel");
+    }
+  }
+  FinalParams f;
+  f.ranked_len = a.ranked_len;
+  f.q = a.q;
+  f.n_classes = a.n_classes;
+  f.subs = subs;
+  f.n_gallery = a.n_gallery;
+  f.top_n = a.top_n;
+  f.sub_pref = sub_cnt;
+  f.class_counts = a.class_counts;
+  f.partial = partial;
+  f.pw = pw;
+  f.pwl = pwl;
+  f.per_query = a.per_query;
+  finalize_kernel<<<(a.q + 127) / 128, 128, 0, st>>>(f);
+  DVL_LAUNCH_CHECK(c, "finalize_kernel");
   return DVL_OK;
 }
 

@@ -7,7 +7,6 @@
 //                  Also emits 1/||row|| for the fused normalisation (measuring_bias.py:79).
 //  * class_counts: Counter(df.label)  (measuring_bias.py:23,56) -- once per call instead of once
 //                  per query and per metric.
-//  * log table:    ln(i), i < len, fp64 -- NDKL needs ln h, ln i and log2(i+1) per ranked row.
 #include "dvl_common.cuh"
 #include "dvl_internal.h"
 
@@ -131,24 +130,6 @@ int launch_class_counts(Ctx* c, const uint8_t* labels, int64_t n, int n_classes,
   class_counts_kernel<<<(unsigned)blocks, 256, 0, st>>>(labels, n, n_classes, counts,
                                                         reinterpret_cast<unsigned int*>(counts + kMaxClasses));
   DVL_LAUNCH_CHECK(c, "class_counts_kernel");
-  return DVL_OK;
-}
-
-// ----------------------------------------------------------------------------------------
-__global__ void log_table_kernel(double* __restrict__ tab, int64_t len) {
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < len; i += (int64_t)gridDim.x * blockDim.x)
-    tab[i] = (i == 0) ? 0.0 : log((double)i);
-}
-
-int ensure_log_table(Ctx* c, int64_t len, cudaStream_t st) {
-  if (len <= c->log_tab_len) return DVL_OK;
-  int64_t want = len + len / 8 + 1024;
-  DVL_TRY(ensure(c, c->log_tab, (size_t)want * sizeof(double)));
-  int64_t blocks = (want + 255) / 256;
-  if (blocks > (int64_t)c->num_sms * 8) blocks = (int64_t)c->num_sms * 8;
-  log_table_kernel<<<(unsigned)blocks, 256, 0, st>>>((double*)c->log_tab.ptr, want);
-  DVL_LAUNCH_CHECK(c, "log_table_kernel");
-  c->log_tab_len = want;
   return DVL_OK;
 }
 

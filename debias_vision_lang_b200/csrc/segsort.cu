@@ -91,7 +91,7 @@ __global__ void __launch_bounds__(kRadix) seg_scan_kernel(uint32_t* __restrict__
 
 // pass step 3: stable scatter of one tile
 template <bool kFirst, bool kHasIdx>
-__global__ void __launch_bounds__(kSortThreads)
+__global__ void __launch_bounds__(kSortThreads, 4)
 tile_scatter_kernel(const uint32_t* __restrict__ keys_in, const uint8_t* __restrict__ labs_in,
                     const int32_t* __restrict__ idx_in, const uint8_t* __restrict__ gallery_labels,
                     uint32_t* __restrict__ keys_out, uint8_t* __restrict__ labs_out, int32_t* __restrict__ idx_out,
