@@ -19,7 +19,7 @@ LIB_PATH = os.path.join(_HERE, "libdvl_b200.so")
 DVL_OK = 0
 DVL_F32, DVL_BF16, DVL_F16 = 0, 1, 2
 PRECISION_FP32, PRECISION_BF16 = 0, 1
-FLAG_NORMALIZE_QUERIES, FLAG_NORMALIZE_GALLERY, FLAG_FULL_SORT = 1, 2, 4
+FLAG_NORMALIZE_QUERIES, FLAG_NORMALIZE_GALLERY, FLAG_FULL_SORT, FLAG_STREAM_TOPK = 1, 2, 4, 8
 MAX_CLASSES = 16
 STAGES = ("prep", "gemm", "sort_hist", "sort_scan", "sort_scatter", "metrics", "select", "copy")
 NUM_STAGES = len(STAGES)
@@ -27,6 +27,7 @@ NUM_STAGES = len(STAGES)
 EXPORTS = (
     "dvl_abi_version", "dvl_create", "dvl_destroy", "dvl_last_error", "dvl_workspace_bytes",
     "dvl_launch_count", "dvl_set_profiling", "dvl_get_profile", "dvl_eval_ranking", "dvl_eval_ranking_host", "dvl_rank_and_score", "dvl_similarity",
+    "dvl_shard_topk", "dvl_shard_trim", "dvl_shard_pack", "dvl_merge_topk", "dvl_mean",
 )
 
 _STATUS = {-1: "DVL_ERR_INVALID", -2: "DVL_ERR_NO_DEVICE", -3: "DVL_ERR_CUDA", -4: "DVL_ERR_OOM",
@@ -73,6 +74,13 @@ def lib() -> ctypes.CDLL:
                                      c_void_p, c_void_p, c_void_p, c_i64, c_void_p]
     L.dvl_similarity.argtypes = [c_void_p, c_void_p, c_int, c_void_p, c_int, c_i64, c_i32, c_i32, c_int, c_u32,
                                  c_void_p, c_i64, c_void_p]
+    L.dvl_shard_topk.argtypes = [c_void_p, c_void_p, c_int, c_void_p, c_int, c_void_p, c_i64, c_i64, c_i32, c_i32, c_i32,
+                                 c_i64, c_int, c_u32, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]
+    L.dvl_shard_trim.argtypes = [c_void_p, c_void_p, c_i32, c_void_p, c_void_p]
+    L.dvl_shard_pack.argtypes = [c_void_p, c_void_p, c_i32, c_i64, c_void_p, c_void_p]
+    L.dvl_merge_topk.argtypes = [c_void_p, c_void_p, c_i32, c_i32, c_i64, c_i32, c_i32, c_i64, c_void_p, c_i32, c_i64,
+                                 c_void_p, c_void_p, c_void_p, c_i64, c_void_p, c_void_p]
+    L.dvl_mean.argtypes = [c_void_p, c_void_p, c_i32, c_void_p, c_void_p]
     for name in EXPORTS:
         if name not in ("dvl_last_error", "dvl_workspace_bytes", "dvl_launch_count"):
             getattr(L, name).restype = c_int
@@ -225,6 +233,63 @@ class Context:
                                   ctypes.c_void_p(self._stream()))
         self._check(rc)
         return out
+
+
+    # ---- gallery-sharded stages (see sharded.py) -------------------------------------------
+    def shard_topk(self, gallery: torch.Tensor, queries: torch.Tensor, labels_u8: torch.Tensor, index_base: int,
+                   n_classes: int, top_n: int, precision: int = PRECISION_FP32, flags: int = 0):
+        assert gallery.is_cuda and gallery.is_contiguous() and queries.is_contiguous() and labels_u8.dtype == torch.uint8
+        n_local, d = gallery.shape
+        q = queries.shape[0]
+        dev = gallery.device
+        tau = torch.empty((q,), dtype=torch.float32, device=dev)
+        oflags = torch.empty((q,), dtype=torch.int32, device=dev)
+        counts = torch.empty((MAX_CLASSES + 1,), dtype=torch.int64, device=dev)
+        cap = ctypes.c_int32(0)
+        rc = lib().dvl_shard_topk(self._h, self._ptr(gallery), _dtype_code(gallery.dtype), self._ptr(queries),
+                                  _dtype_code(queries.dtype), self._ptr(labels_u8), n_local, int(index_base), d, q,
+                                  int(n_classes), int(top_n), int(precision), int(flags), self._ptr(tau),
+                                  self._ptr(oflags), self._ptr(counts), ctypes.cast(ctypes.byref(cap), ctypes.c_void_p),
+                                  ctypes.c_void_p(self._stream()))
+        self._check(rc)
+        return tau, oflags, counts, int(cap.value)
+
+    def shard_trim(self, tau_bound: torch.Tensor) -> torch.Tensor:
+        q = tau_bound.numel()
+        cnt = torch.empty((q,), dtype=torch.int32, device=tau_bound.device)
+        self._check(lib().dvl_shard_trim(self._h, self._ptr(tau_bound), q, self._ptr(cnt),
+                                         ctypes.c_void_p(self._stream())))
+        return cnt
+
+    def shard_pack(self, cnt: torch.Tensor, length: int) -> torch.Tensor:
+        q = cnt.numel()
+        out = torch.empty((q, length), dtype=torch.int64, device=cnt.device)    # u64 entries, stored as i64
+        self._check(lib().dvl_shard_pack(self._h, self._ptr(cnt), q, int(length), self._ptr(out),
+                                         ctypes.c_void_p(self._stream())))
+        return out
+
+    def merge_topk(self, gathered: torch.Tensor, q0: int, qn: int, n_global: int, class_counts: torch.Tensor,
+                   n_classes: int, top_n: int, ranked_cap: int = 0):
+        world, q_total, length = gathered.shape
+        assert gathered.is_contiguous() and gathered.dtype == torch.int64 and class_counts.dtype == torch.int64
+        dev = gathered.device
+        per_query = torch.empty((qn, 4), dtype=torch.float64, device=dev)
+        ranked_len = torch.empty((qn,), dtype=torch.int32, device=dev)
+        ranked_idx = torch.full((qn, ranked_cap), -1, dtype=torch.int32, device=dev) if ranked_cap > 0 else None
+        oflags = torch.empty((qn,), dtype=torch.int32, device=dev)
+        rc = lib().dvl_merge_topk(self._h, self._ptr(gathered), world, q_total, length, int(q0), int(qn), int(n_global),
+                                  self._ptr(class_counts), int(n_classes), int(top_n), self._ptr(per_query),
+                                  self._ptr(ranked_len), self._ptr(ranked_idx), int(ranked_cap), self._ptr(oflags),
+                                  ctypes.c_void_p(self._stream()))
+        self._check(rc)
+        return dict(per_query=per_query, ranked_len=ranked_len, ranked_idx=ranked_idx, flags=oflags)
+
+    def mean(self, per_query: torch.Tensor):
+        assert per_query.is_cuda and per_query.dtype == torch.float64 and per_query.is_contiguous()
+        mean = (ctypes.c_double * 4)()
+        self._check(lib().dvl_mean(self._h, self._ptr(per_query), per_query.shape[0], ctypes.cast(mean, ctypes.c_void_p),
+                                   ctypes.c_void_p(self._stream())))
+        return [float(x) for x in mean]
 
 
 _contexts = {}

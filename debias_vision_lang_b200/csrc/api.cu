@@ -99,10 +99,18 @@ int check_common(Ctx* c, int64_t n, int32_t d, int32_t q, int32_t n_classes, int
   return DVL_OK;
 }
 
-// similarity into ranking keys and/or fp32 scores (both pitched to whole 256-column tiles)
-int run_similarity(Ctx* c, const void* gallery, int gdt, const void* queries, int qdt, int64_t n, int d, int q,
-                   int precision, uint32_t flags, uint32_t* keys, int64_t ldk, float* scores, int64_t lds,
-                   cudaStream_t st) {
+struct Operands {
+  const __nv_bfloat16* qry_planes;
+  const __nv_bfloat16* gal_planes;
+  int planes;
+  int dp;
+  const float* qry_scale;
+  const float* gal_scale;
+};
+
+// a1 + operand preparation: bf16 planes of gallery and queries, inverse norms for the fused scale
+int prepare_operands(Ctx* c, const void* gallery, int gdt, const void* queries, int qdt, int64_t n, int d, int q,
+                     int precision, uint32_t flags, Operands* op, cudaStream_t st) {
   const int planes = (precision == DVL_PRECISION_FP32) ? 3 : 1;
   const int dp = (int)round_up(d, 8);
   DVL_TRY(ensure(c, c->gal_planes, (size_t)planes * n * dp * 2));
@@ -117,22 +125,46 @@ int run_similarity(Ctx* c, const void* gallery, int gdt, const void* queries, in
     DVL_TRY(ensure(c, c->qry_inv_norm, (size_t)q * 4));
     qnorm = (float*)c->qry_inv_norm.ptr;
   }
-  {
-    StageScope scope(c, DVL_STAGE_PREP, st);
-    DVL_TRY(launch_split_rows(c, gallery, gdt, n, d, dp, planes, (__nv_bfloat16*)c->gal_planes.ptr, gnorm, st));
-    DVL_TRY(launch_split_rows(c, queries, qdt, q, d, dp, planes, (__nv_bfloat16*)c->qry_planes.ptr, qnorm, st));
-  }
-  StageScope scope(c, DVL_STAGE_GEMM, st);
+  StageScope scope(c, DVL_STAGE_PREP, st);
+  DVL_TRY(launch_split_rows(c, gallery, gdt, n, d, dp, planes, (__nv_bfloat16*)c->gal_planes.ptr, gnorm, st));
+  DVL_TRY(launch_split_rows(c, queries, qdt, q, d, dp, planes, (__nv_bfloat16*)c->qry_planes.ptr, qnorm, st));
+  op->qry_planes = (const __nv_bfloat16*)c->qry_planes.ptr;
+  op->gal_planes = (const __nv_bfloat16*)c->gal_planes.ptr;
+  op->planes = planes;
+  op->dp = dp;
+  op->qry_scale = qnorm;
+  op->gal_scale = gnorm;
+  return DVL_OK;
+}
+
+GemmArgs gemm_args(const Operands& op, int64_t n, int d, int q) {
   GemmArgs g;
-  g.qry_planes = (const __nv_bfloat16*)c->qry_planes.ptr;
-  g.gal_planes = (const __nv_bfloat16*)c->gal_planes.ptr;
-  g.planes = planes;
+  g.qry_planes = op.qry_planes;
+  g.gal_planes = op.gal_planes;
+  g.planes = op.planes;
   g.n = n;
   g.q = q;
   g.d = d;
-  g.dp = dp;
-  g.qry_scale = qnorm;
-  g.gal_scale = gnorm;
+  g.dp = op.dp;
+  g.qry_scale = op.qry_scale;
+  g.gal_scale = op.gal_scale;
+  g.keys = nullptr;
+  g.ldk = 0;
+  g.scores = nullptr;
+  g.lds = 0;
+  g.row0 = 0;
+  g.row1 = n;
+  return g;
+}
+
+// similarity into ranking keys and/or fp32 scores (both pitched to whole 256-column tiles)
+int run_similarity(Ctx* c, const void* gallery, int gdt, const void* queries, int qdt, int64_t n, int d, int q,
+                   int precision, uint32_t flags, uint32_t* keys, int64_t ldk, float* scores, int64_t lds,
+                   cudaStream_t st) {
+  Operands op;
+  DVL_TRY(prepare_operands(c, gallery, gdt, queries, qdt, n, d, q, precision, flags, &op, st));
+  StageScope scope(c, DVL_STAGE_GEMM, st);
+  GemmArgs g = gemm_args(op, n, d, q);
   g.keys = keys;
   g.ldk = ldk;
   g.scores = scores;
@@ -140,11 +172,21 @@ int run_similarity(Ctx* c, const void* gallery, int gdt, const void* queries, in
   return launch_sim_gemm(c, g, st);
 }
 
-// keys [q][ldk] in c->keys[0] -> sort -> metrics -> mean.  Shared by eval_ranking (full-sort
-// route) and rank_and_score.
-int run_sort_and_score(Ctx* c, const uint8_t* labels, int64_t n, int q, int n_classes, int64_t top_n, int64_t ldk,
-                       double* out_mean4, double* out_per_query, int32_t* out_ranked_len, int32_t* out_ranked_idx,
-                       int64_t ranked_cap, cudaStream_t st) {
+// query-independent statistics: Counter(df.label) and the fp64 tables
+int run_label_stats(Ctx* c, const uint8_t* labels, int64_t n, int n_classes, int64_t table_len, cudaStream_t st) {
+  DVL_TRY(ensure(c, c->class_counts, sizeof(unsigned long long) * (kMaxClasses + 1)));
+  StageScope scope(c, DVL_STAGE_PREP, st);
+  DVL_TRY(ensure_metric_tables(c, table_len, st));
+  if (labels != nullptr)
+    DVL_TRY(launch_class_counts(c, labels, n, n_classes, (unsigned long long*)c->class_counts.ptr, st));
+  return DVL_OK;
+}
+
+// Full-sort route.  keys [q][ldk] already in c->keys[0] -> stable segmented sort -> metrics.
+// Writes per_query [q][4] and ranked_len [q] (device); ranked indices on request.
+int rank_full(Ctx* c, const uint8_t* labels, int64_t n, int64_t n_gallery, int q, int n_classes, int64_t top_n,
+              int64_t ldk, double* per_query, int32_t* ranked_len, int32_t* out_ranked_idx, int64_t ranked_cap,
+              cudaStream_t st) {
   const bool want_idx = out_ranked_idx != nullptr;
   if (want_idx && ranked_cap < 1) return set_error(c, DVL_ERR_INVALID, "ranked_cap must be >= 1");
   DVL_TRY(ensure(c, c->keys[1], (size_t)q * ldk * 4));
@@ -154,16 +196,6 @@ int run_sort_and_score(Ctx* c, const uint8_t* labels, int64_t n, int q, int n_cl
     DVL_TRY(ensure(c, c->idxs[0], (size_t)q * ldk * 4));
     DVL_TRY(ensure(c, c->idxs[1], (size_t)q * ldk * 4));
   }
-  DVL_TRY(ensure(c, c->class_counts, sizeof(unsigned long long) * (kMaxClasses + 1)));
-  DVL_TRY(ensure(c, c->per_query, (size_t)q * 4 * sizeof(double)));
-  DVL_TRY(ensure(c, c->seg_len, (size_t)q * sizeof(int32_t)));
-  DVL_TRY(ensure(c, c->mean_dev, 8 * sizeof(double)));
-  {
-    StageScope scope(c, DVL_STAGE_PREP, st);
-    DVL_TRY(ensure_metric_tables(c, (n > top_n ? n : top_n) + 2, st));
-    DVL_TRY(launch_class_counts(c, labels, n, n_classes, (unsigned long long*)c->class_counts.ptr, st));
-  }
-
   SortArgs s;
   s.keys[0] = (uint32_t*)c->keys[0].ptr;
   s.keys[1] = (uint32_t*)c->keys[1].ptr;
@@ -177,41 +209,152 @@ int run_sort_and_score(Ctx* c, const uint8_t* labels, int64_t n, int q, int n_cl
   s.q = q;
   int buf = 0;
   DVL_TRY(launch_segmented_sort(c, s, &buf, st));
-
-  int32_t* ranked_len = out_ranked_len != nullptr ? out_ranked_len : (int32_t*)c->seg_len.ptr;
   MetricArgs m;
   m.keys = s.keys[buf];
   m.labs = s.labs[buf];
   m.ldk = ldk;
   m.ldl = ldk;
   m.n_avail = n;
-  m.n_gallery = n;
+  m.n_gallery = n_gallery;
   m.top_n = top_n;
   m.q = q;
   m.n_classes = n_classes;
   m.class_counts = (const unsigned long long*)c->class_counts.ptr;
   m.avail = nullptr;
-  m.per_query = out_per_query != nullptr ? out_per_query : (double*)c->per_query.ptr;
+  m.per_query = per_query;
   m.ranked_len = ranked_len;
   {
     StageScope scope(c, DVL_STAGE_METRICS, st);
     DVL_TRY(launch_metrics(c, m, st));
-    DVL_TRY(launch_mean(c, m.per_query, q, (double*)c->mean_dev.ptr, st));
   }
   if (want_idx) {
     StageScope scope(c, DVL_STAGE_COPY, st);
     DVL_TRY(launch_copy_ranked(c, s.idxs[buf], ldk, ranked_len, q, out_ranked_idx, ranked_cap, st));
   }
+  return DVL_OK;
+}
+
+// mean over queries -> host, plus the label sanity flag; synchronises the stream
+int finish(Ctx* c, const double* per_query, int q, int n_classes, double* out_mean4, bool check_labels,
+           cudaStream_t st) {
+  DVL_TRY(ensure(c, c->mean_dev, 8 * sizeof(double)));
+  {
+    StageScope scope(c, DVL_STAGE_METRICS, st);
+    DVL_TRY(launch_mean(c, per_query, q, (double*)c->mean_dev.ptr, st));
+  }
   DVL_CUDA(c, cudaMemcpyAsync(c->mean_pinned, c->mean_dev.ptr, 4 * sizeof(double), cudaMemcpyDeviceToHost, st));
-  // the out-of-range label flag travels with the class counts
-  unsigned long long bad_flag = 0;
-  DVL_CUDA(c, cudaMemcpyAsync(c->mean_pinned + 4, (unsigned long long*)c->class_counts.ptr + kMaxClasses,
-                              sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+  if (check_labels)   // the out-of-range label flag travels with the class counts
+    DVL_CUDA(c, cudaMemcpyAsync(c->mean_pinned + 4, (unsigned long long*)c->class_counts.ptr + kMaxClasses,
+                                sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
   DVL_CUDA(c, cudaStreamSynchronize(st));
-  memcpy(&bad_flag, c->mean_pinned + 4, sizeof(bad_flag));
-  if (bad_flag != 0) return set_error(c, DVL_ERR_INVALID, "a label is >= n_classes (%d)", n_classes);
+  if (check_labels) {
+    unsigned long long bad_flag = 0;
+    memcpy(&bad_flag, c->mean_pinned + 4, sizeof(bad_flag));
+    if (bad_flag != 0) return set_error(c, DVL_ERR_INVALID, "a label is >= n_classes (%d)", n_classes);
+  }
   if (out_mean4 != nullptr) memcpy(out_mean4, c->mean_pinned, 4 * sizeof(double));
   return DVL_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// streaming top-k route
+// ---------------------------------------------------------------------------------------------
+struct StreamPlan {
+  int sort_cap;        // S: entries a query keeps between chunks (top_n + boundary ties)
+  int64_t chunk0, chunk_max, cap, trigger;
+};
+
+bool plan_stream(int64_t n, int q, int64_t top_n, uint32_t flags, StreamPlan* plan, bool shard = false) {
+  if (top_n > 8192) return false;
+  if (top_n >= n && !shard) return false;        // the whole gallery is ranked: full-sort route
+  int s = 2048;
+  while (s < 2 * top_n) s <<= 1;
+  plan->sort_cap = s;
+  plan->trigger = 2 * top_n;
+  int64_t chunk0 = 8192;
+  if (shard || (flags & DVL_FLAG_STREAM_TOPK)) { // forced: keep several chunks even on a small gallery
+    chunk0 = round_up((n + 3) / 4, 256);
+    if (chunk0 > 8192) chunk0 = 8192;
+  } else if (n < 4 * chunk0 || (flags & DVL_FLAG_FULL_SORT)) {
+    return false;
+  }
+  if (chunk0 < plan->trigger) chunk0 = round_up(plan->trigger, 256);
+  int64_t chunk_max = 65536;
+  while (chunk_max > chunk0 && (double)q * (double)(s + chunk_max) * 8.0 > 6.0e9) chunk_max >>= 1;
+  if (chunk_max < chunk0) chunk_max = chunk0;
+  plan->chunk0 = chunk0;
+  plan->chunk_max = chunk_max;
+  plan->cap = s + chunk_max;
+  return true;
+}
+
+// Streams the local gallery through the similarity GEMM with the threshold filter and leaves, per
+// query, the sorted list of every row that ranks within top_n (boundary ties included):
+// c->cand [q][cap] (first avail[q] entries), labels in c->topk_labs [q][ldl], lengths in c->topk_avail.
+int stream_topk(Ctx* c, const Operands& op, const uint8_t* labels, int64_t n, int64_t index_base, int d, int q,
+                int64_t top_n, const StreamPlan& plan, int32_t* idx_out, int64_t idx_cap, cudaStream_t st) {
+  const int64_t ldl = round_up(plan.sort_cap, 256);
+  DVL_TRY(ensure(c, c->cand, (size_t)q * plan.cap * 8));
+  DVL_TRY(ensure(c, c->cand_cnt, (size_t)q * 4));
+  DVL_TRY(ensure(c, c->cand_tau, (size_t)q * 4));
+  DVL_TRY(ensure(c, c->cand_flags, (size_t)q * 4));
+  DVL_TRY(ensure(c, c->topk_labs, (size_t)q * ldl));
+  DVL_TRY(ensure(c, c->topk_avail, (size_t)q * 4));
+  unsigned long long* cand = (unsigned long long*)c->cand.ptr;
+  uint32_t* cnt = (uint32_t*)c->cand_cnt.ptr;
+  float* tau = (float*)c->cand_tau.ptr;
+  uint32_t* cflags = (uint32_t*)c->cand_flags.ptr;
+
+  SelectArgs sel;
+  sel.cand = cand;
+  sel.row_stride = plan.cap;
+  sel.segs = 1;
+  sel.cnt = cnt;
+  sel.cap = plan.cap;
+  sel.tau = tau;
+  sel.flags = cflags;
+  sel.k = top_n;
+  sel.sort_cap = plan.sort_cap;
+  sel.trigger = plan.trigger;
+  sel.labs = (uint8_t*)c->topk_labs.ptr;
+  sel.ldl = ldl;
+  sel.avail = (int32_t*)c->topk_avail.ptr;
+  sel.q_count = q;
+
+  int64_t row = 0;
+  int64_t chunk = plan.chunk0;
+  bool first = true;
+  while (row < n) {
+    const int64_t row1 = (row + chunk < n) ? row + chunk : n;
+    {
+      StageScope scope(c, DVL_STAGE_GEMM, st);
+      GemmArgs g = gemm_args(op, n, d, q);
+      g.mode = first ? kGemmSeed : kGemmFilter;
+      g.row0 = row;
+      g.row1 = row1;
+      g.tau = tau;
+      g.cand = cand;
+      g.cand_cnt = cnt;
+      g.cap = plan.cap;
+      g.labels = labels;
+      g.index_base = index_base;
+      if (first) DVL_TRY(launch_topk_reset(c, cnt, tau, cflags, q, (uint32_t)(row1 - row), true, st));
+      DVL_TRY(launch_sim_gemm(c, g, st));
+    }
+    row = row1;
+    first = false;
+    if (row < n) {
+      StageScope scope(c, DVL_STAGE_SELECT, st);
+      sel.final_pass = false;
+      DVL_TRY(launch_select(c, sel, st));
+      chunk = (2 * chunk < plan.chunk_max) ? 2 * chunk : plan.chunk_max;
+    }
+  }
+  StageScope scope(c, DVL_STAGE_SELECT, st);
+  sel.final_pass = true;
+  sel.idx_out = idx_out;
+  sel.idx_cap = idx_cap;
+  return launch_select(c, sel, st);
 }
 
 struct DeviceGuard {
@@ -269,8 +412,9 @@ DVL_API int dvl_destroy(dvl_ctx* c) {
   dvl::DevBuf* bufs[] = {&c->gal_planes, &c->qry_planes, &c->gal_inv_norm, &c->qry_inv_norm, &c->keys[0], &c->keys[1],
                          &c->labs[0], &c->labs[1], &c->idxs[0], &c->idxs[1], &c->tile_hist, &c->class_counts,
                          &c->log_tab, &c->per_query, &c->mean_dev, &c->scores_tmp, &c->seg_len, &c->sub_cnt, &c->partial,
-                         &c->h_gallery,
-                         &c->h_queries, &c->h_labels};
+                         &c->h_gallery, &c->h_queries, &c->h_labels, &c->cand, &c->cand_cnt, &c->cand_tau,
+                         &c->cand_flags, &c->topk_labs, &c->topk_avail, &c->fb_queries, &c->fb_per_query, &c->fb_len,
+                         &c->fb_idx, &c->merge_sorted, &c->tab_chunks};
   for (dvl::DevBuf* b : bufs)
     if (b->ptr != nullptr) cudaFree(b->ptr);
   if (c->mean_pinned != nullptr) cudaFreeHost(c->mean_pinned);
@@ -340,10 +484,73 @@ DVL_API int dvl_rank_and_score(dvl_ctx* c, const float* scores, int64_t ld_score
   cudaStream_t st = (cudaStream_t)stream;
   const int64_t ldk = dvl::round_up(n, 256);
   DVL_TRY(dvl::ensure(c, c->keys[0], (size_t)q * ldk * 4));
+  DVL_TRY(dvl::ensure(c, c->per_query, (size_t)q * 4 * sizeof(double)));
+  DVL_TRY(dvl::ensure(c, c->seg_len, (size_t)q * sizeof(int32_t)));
+  DVL_TRY(dvl::run_label_stats(c, labels, n, n_classes, (n > top_n ? n : top_n) + 2, st));
   DVL_TRY(dvl::launch_scores_to_keys(c, scores, ld_scores, (uint32_t*)c->keys[0].ptr, ldk, n, q, st));
-  return dvl::run_sort_and_score(c, labels, n, q, n_classes, top_n, ldk, out_mean4, out_per_query, out_ranked_len,
-                                 out_ranked_idx, ranked_cap, st);
+  double* per_query = out_per_query != nullptr ? out_per_query : (double*)c->per_query.ptr;
+  int32_t* ranked_len = out_ranked_len != nullptr ? out_ranked_len : (int32_t*)c->seg_len.ptr;
+  DVL_TRY(dvl::rank_full(c, labels, n, n, q, n_classes, top_n, ldk, per_query, ranked_len, out_ranked_idx, ranked_cap,
+                         st));
+  return dvl::finish(c, per_query, q, n_classes, out_mean4, true, st);
 }
+
+namespace dvl {
+namespace {
+
+// Re-ranks the queries the streaming route flagged (tie run longer than its list) by the full-sort
+// route and patches their rows of per_query / ranked_len / ranked_idx.  Rare by construction.
+int rerank_flagged(Ctx* c, const void* gallery, int gdt, const void* queries, int qdt, const uint8_t* labels,
+                   int64_t n, int d, int q, int n_classes, int64_t top_n, int precision, uint32_t flags,
+                   double* per_query, int32_t* ranked_len, int32_t* ranked_idx, int64_t ranked_cap,
+                   cudaStream_t st) {
+  std::vector<uint32_t> host_flags((size_t)q);
+  DVL_CUDA(c, cudaMemcpyAsync(host_flags.data(), c->cand_flags.ptr, (size_t)q * 4, cudaMemcpyDeviceToHost, st));
+  DVL_CUDA(c, cudaStreamSynchronize(st));
+  std::vector<int> flagged;
+  for (int i = 0; i < q; ++i)
+    if (host_flags[(size_t)i] != 0u) flagged.push_back(i);
+  if (flagged.empty()) return DVL_OK;
+  const size_t row_bytes = (size_t)d * dtype_size(qdt);
+  const int64_t ldk = round_up(n, 256);
+  // batches bounded by ~4 GB of sort workspace
+  int batch = (int)(4.0e9 / ((double)ldk * 20.0));
+  if (batch < 1) batch = 1;
+  for (size_t b0 = 0; b0 < flagged.size(); b0 += (size_t)batch) {
+    const int f = (int)((flagged.size() - b0 < (size_t)batch) ? flagged.size() - b0 : (size_t)batch);
+    DVL_TRY(ensure(c, c->fb_queries, (size_t)f * row_bytes));
+    DVL_TRY(ensure(c, c->fb_per_query, (size_t)f * 4 * sizeof(double)));
+    DVL_TRY(ensure(c, c->fb_len, (size_t)f * 4));
+    if (ranked_idx != nullptr) DVL_TRY(ensure(c, c->fb_idx, (size_t)f * ranked_cap * 4));
+    DVL_TRY(ensure(c, c->keys[0], (size_t)f * ldk * 4));
+    {
+      StageScope scope(c, DVL_STAGE_COPY, st);
+      for (int i = 0; i < f; ++i)
+        DVL_CUDA(c, cudaMemcpyAsync((char*)c->fb_queries.ptr + (size_t)i * row_bytes,
+                                    (const char*)queries + (size_t)flagged[b0 + i] * row_bytes, row_bytes,
+                                    cudaMemcpyDeviceToDevice, st));
+    }
+    DVL_TRY(run_similarity(c, gallery, gdt, c->fb_queries.ptr, qdt, n, d, f, precision, flags,
+                           (uint32_t*)c->keys[0].ptr, ldk, nullptr, 0, st));
+    DVL_TRY(rank_full(c, labels, n, n, f, n_classes, top_n, ldk, (double*)c->fb_per_query.ptr,
+                      (int32_t*)c->fb_len.ptr, ranked_idx != nullptr ? (int32_t*)c->fb_idx.ptr : nullptr, ranked_cap,
+                      st));
+    StageScope scope(c, DVL_STAGE_COPY, st);
+    for (int i = 0; i < f; ++i) {
+      const int qi = flagged[b0 + i];
+      DVL_CUDA(c, cudaMemcpyAsync(per_query + (size_t)qi * 4, (double*)c->fb_per_query.ptr + (size_t)i * 4,
+                                  4 * sizeof(double), cudaMemcpyDeviceToDevice, st));
+      DVL_CUDA(c, cudaMemcpyAsync(ranked_len + qi, (int32_t*)c->fb_len.ptr + i, 4, cudaMemcpyDeviceToDevice, st));
+      if (ranked_idx != nullptr)
+        DVL_CUDA(c, cudaMemcpyAsync(ranked_idx + (size_t)qi * ranked_cap, (int32_t*)c->fb_idx.ptr + (size_t)i * ranked_cap,
+                                    (size_t)ranked_cap * 4, cudaMemcpyDeviceToDevice, st));
+    }
+  }
+  return DVL_OK;
+}
+
+}  // namespace
+}  // namespace dvl
 
 DVL_API int dvl_eval_ranking(dvl_ctx* c, const void* gallery, int gdt, const void* queries, int qdt, const uint8_t* labels,
                      int64_t n, int32_t d, int32_t q, int32_t n_classes, int64_t top_n, int precision,
@@ -352,8 +559,44 @@ DVL_API int dvl_eval_ranking(dvl_ctx* c, const void* gallery, int gdt, const voi
   DVL_TRY(dvl::check_common(c, n, d, q, n_classes, top_n, precision, gdt, qdt));
   if (gallery == nullptr || queries == nullptr || labels == nullptr)
     return dvl::set_error(c, DVL_ERR_INVALID, "null input pointer");
+  if (out_ranked_idx != nullptr && ranked_cap < 1) return dvl::set_error(c, DVL_ERR_INVALID, "ranked_cap must be >= 1");
   dvl::DeviceGuard guard(c->device);
   cudaStream_t st = (cudaStream_t)stream;
+  DVL_TRY(dvl::ensure(c, c->per_query, (size_t)q * 4 * sizeof(double)));
+  DVL_TRY(dvl::ensure(c, c->seg_len, (size_t)q * sizeof(int32_t)));
+  double* per_query = out_per_query != nullptr ? out_per_query : (double*)c->per_query.ptr;
+  int32_t* ranked_len = out_ranked_len != nullptr ? out_ranked_len : (int32_t*)c->seg_len.ptr;
+  DVL_TRY(dvl::run_label_stats(c, labels, n, n_classes, (n > top_n ? n : top_n) + 2, st));
+
+  dvl::StreamPlan plan;
+  const bool stream_route = out_scores == nullptr && dvl::plan_stream(n, q, top_n, flags, &plan);
+  if (stream_route) {
+    dvl::Operands op;
+    DVL_TRY(dvl::prepare_operands(c, gallery, gdt, queries, qdt, n, d, q, precision, flags, &op, st));
+    DVL_TRY(dvl::stream_topk(c, op, labels, n, 0, d, q, top_n, plan, out_ranked_idx, ranked_cap, st));
+    dvl::MetricArgs m;
+    m.keys = nullptr;
+    m.labs = (const uint8_t*)c->topk_labs.ptr;
+    m.ldk = 0;
+    m.ldl = dvl::round_up(plan.sort_cap, 256);
+    m.n_avail = plan.sort_cap;
+    m.n_gallery = n;
+    m.top_n = top_n;
+    m.q = q;
+    m.n_classes = n_classes;
+    m.class_counts = (const unsigned long long*)c->class_counts.ptr;
+    m.avail = (const int32_t*)c->topk_avail.ptr;
+    m.per_query = per_query;
+    m.ranked_len = ranked_len;
+    {
+      dvl::StageScope scope(c, DVL_STAGE_METRICS, st);
+      DVL_TRY(dvl::launch_metrics(c, m, st));
+    }
+    DVL_TRY(dvl::rerank_flagged(c, gallery, gdt, queries, qdt, labels, n, d, q, n_classes, top_n, precision, flags,
+                                per_query, ranked_len, out_ranked_idx, ranked_cap, st));
+    return dvl::finish(c, per_query, q, n_classes, out_mean4, true, st);
+  }
+
   const int64_t ldk = dvl::round_up(n, 256);
   DVL_TRY(dvl::ensure(c, c->keys[0], (size_t)q * ldk * 4));
   float* scores_tmp = nullptr;
@@ -366,8 +609,9 @@ DVL_API int dvl_eval_ranking(dvl_ctx* c, const void* gallery, int gdt, const voi
   if (out_scores != nullptr)
     DVL_CUDA(c, cudaMemcpy2DAsync(out_scores, (size_t)n * 4, scores_tmp, (size_t)ldk * 4, (size_t)n * 4, q,
                                   cudaMemcpyDeviceToDevice, st));
-  return dvl::run_sort_and_score(c, labels, n, q, n_classes, top_n, ldk, out_mean4, out_per_query, out_ranked_len,
-                                 out_ranked_idx, ranked_cap, st);
+  DVL_TRY(dvl::rank_full(c, labels, n, n, q, n_classes, top_n, ldk, per_query, ranked_len, out_ranked_idx, ranked_cap,
+                         st));
+  return dvl::finish(c, per_query, q, n_classes, out_mean4, true, st);
 }
 
 DVL_API int dvl_eval_ranking_host(dvl_ctx* c, const void* gallery_host, int gdt, const void* queries_host, int qdt,
@@ -401,6 +645,143 @@ DVL_API int dvl_eval_ranking_host(dvl_ctx* c, const void* gallery_host, int gdt,
     DVL_CUDA(c, cudaStreamSynchronize(st));
   }
   return DVL_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// multi-GPU: gallery shards.  The host (torch.distributed over NCCL) moves the small per-query
+// lists between these stages; see debias_vision_lang_b200/sharded.py.
+// ---------------------------------------------------------------------------------------------
+DVL_API int dvl_shard_topk(dvl_ctx* c, const void* gallery, int gdt, const void* queries, int qdt, const uint8_t* labels,
+                   int64_t n_local, int64_t index_base, int32_t d, int32_t q, int32_t n_classes, int64_t top_n,
+                   int precision, uint32_t flags, float* out_tau, uint32_t* out_flags,
+                   unsigned long long* out_class_counts, int32_t* out_list_cap, void* stream) {
+  DVL_TRY(dvl::check_common(c, n_local, d, q, n_classes, top_n, precision, gdt, qdt));
+  if (gallery == nullptr || queries == nullptr || labels == nullptr || out_tau == nullptr || out_flags == nullptr ||
+      out_class_counts == nullptr)
+    return dvl::set_error(c, DVL_ERR_INVALID, "null pointer");
+  dvl::DeviceGuard guard(c->device);
+  cudaStream_t st = (cudaStream_t)stream;
+  dvl::StreamPlan plan;
+  // a shard always streams: top_n >= n_local just means the whole shard is kept
+  if (top_n > 8192) return dvl::set_error(c, DVL_ERR_UNSUPPORTED, "sharded ranking supports top_n <= 8192");
+  // a shard with fewer than top_n rows keeps all of them and leaves tau at -inf: its worst score says
+  // nothing about the global top_n-th
+  if (!dvl::plan_stream(n_local, q, top_n, flags, &plan, true))
+    return dvl::set_error(c, DVL_ERR_UNSUPPORTED, "no streaming plan for this shard");
+  DVL_TRY(dvl::run_label_stats(c, labels, n_local, n_classes, top_n + 2, st));
+  dvl::Operands op;
+  DVL_TRY(dvl::prepare_operands(c, gallery, gdt, queries, qdt, n_local, d, q, precision, flags, &op, st));
+  DVL_TRY(dvl::stream_topk(c, op, labels, n_local, index_base, d, q, top_n, plan, nullptr, 0, st));
+  c->shard_plan_cap = plan.cap;
+  c->shard_sort_cap = plan.sort_cap;
+  c->shard_q = q;
+  DVL_CUDA(c, cudaMemcpyAsync(out_tau, c->cand_tau.ptr, (size_t)q * 4, cudaMemcpyDeviceToDevice, st));
+  DVL_CUDA(c, cudaMemcpyAsync(out_flags, c->cand_flags.ptr, (size_t)q * 4, cudaMemcpyDeviceToDevice, st));
+  DVL_CUDA(c, cudaMemcpyAsync(out_class_counts, c->class_counts.ptr, sizeof(unsigned long long) * (dvl::kMaxClasses + 1),
+                              cudaMemcpyDeviceToDevice, st));
+  if (out_list_cap != nullptr) *out_list_cap = plan.sort_cap;
+  DVL_CUDA(c, cudaStreamSynchronize(st));
+  return DVL_OK;
+}
+
+DVL_API int dvl_shard_trim(dvl_ctx* c, const float* tau_bound, int32_t q, int32_t* out_cnt, void* stream) {
+  if (c == nullptr) return DVL_ERR_INVALID;
+  if (q != c->shard_q || c->shard_plan_cap <= 0) return dvl::set_error(c, DVL_ERR_INVALID, "dvl_shard_topk has not run");
+  dvl::DeviceGuard guard(c->device);
+  cudaStream_t st = (cudaStream_t)stream;
+  dvl::StageScope scope(c, DVL_STAGE_SELECT, st);
+  return dvl::launch_trim_count(c, (const unsigned long long*)c->cand.ptr, c->shard_plan_cap,
+                                (const int32_t*)c->topk_avail.ptr, tau_bound, q, out_cnt, st);
+}
+
+DVL_API int dvl_shard_pack(dvl_ctx* c, const int32_t* cnt, int32_t q, int64_t len, unsigned long long* out, void* stream) {
+  if (c == nullptr) return DVL_ERR_INVALID;
+  if (q != c->shard_q || c->shard_plan_cap <= 0) return dvl::set_error(c, DVL_ERR_INVALID, "dvl_shard_topk has not run");
+  if (len < 1 || len > c->shard_sort_cap) return dvl::set_error(c, DVL_ERR_INVALID, "bad packed list length");
+  dvl::DeviceGuard guard(c->device);
+  cudaStream_t st = (cudaStream_t)stream;
+  dvl::StageScope scope(c, DVL_STAGE_SELECT, st);
+  return dvl::launch_pack_lists(c, (const unsigned long long*)c->cand.ptr, c->shard_plan_cap, cnt, q, len, out, st);
+}
+
+DVL_API int dvl_merge_topk(dvl_ctx* c, const unsigned long long* gathered, int32_t world, int32_t q_total, int64_t len,
+                   int32_t q0, int32_t qn, int64_t n_global, const unsigned long long* class_counts_global,
+                   int32_t n_classes, int64_t top_n, double* out_per_query, int32_t* out_ranked_len,
+                   int32_t* out_ranked_idx, int64_t ranked_cap, uint32_t* out_flags, void* stream) {
+  if (c == nullptr) return DVL_ERR_INVALID;
+  if (gathered == nullptr || class_counts_global == nullptr || out_per_query == nullptr || out_ranked_len == nullptr ||
+      out_flags == nullptr || world < 1 || qn < 1 || q0 < 0 || q0 + qn > q_total || len < 1 || top_n < 1)
+    return dvl::set_error(c, DVL_ERR_INVALID, "bad merge arguments");
+  if (n_classes < 1 || n_classes > DVL_MAX_CLASSES) return dvl::set_error(c, DVL_ERR_INVALID, "n_classes out of range");
+  dvl::DeviceGuard guard(c->device);
+  cudaStream_t st = (cudaStream_t)stream;
+  int s = 2048;
+  while (s < 2 * top_n && s < 16384) s <<= 1;
+  const int64_t ldl = dvl::round_up(s, 256);
+  DVL_TRY(dvl::ensure(c, c->merge_sorted, (size_t)qn * s * 8));
+  DVL_TRY(dvl::ensure(c, c->topk_labs, (size_t)qn * ldl));
+  DVL_TRY(dvl::ensure(c, c->topk_avail, (size_t)qn * 4));
+  DVL_TRY(dvl::ensure(c, c->class_counts, sizeof(unsigned long long) * (dvl::kMaxClasses + 1)));
+  DVL_CUDA(c, cudaMemcpyAsync(c->class_counts.ptr, class_counts_global, sizeof(unsigned long long) * dvl::kMaxClasses,
+                              cudaMemcpyDeviceToDevice, st));
+  DVL_CUDA(c, cudaMemsetAsync(out_flags, 0, (size_t)qn * 4, st));
+  {
+    dvl::StageScope scope(c, DVL_STAGE_PREP, st);
+    DVL_TRY(dvl::ensure_metric_tables(c, (s > top_n ? s : top_n) + 2, st));
+  }
+  dvl::SelectArgs sel;
+  sel.cand = const_cast<unsigned long long*>(gathered) + (int64_t)q0 * len;
+  sel.row_stride = len;
+  sel.seg_stride = (int64_t)q_total * len;
+  sel.segs = world;
+  sel.seg_len = len;
+  sel.cnt = nullptr;
+  sel.cap = 0;
+  sel.tau = nullptr;
+  sel.flags = out_flags;
+  sel.k = top_n;
+  sel.sort_cap = s;
+  sel.trigger = 0;
+  sel.final_pass = true;
+  sel.sorted_out = (unsigned long long*)c->merge_sorted.ptr;
+  sel.labs = (uint8_t*)c->topk_labs.ptr;
+  sel.ldl = ldl;
+  sel.idx_out = out_ranked_idx;
+  sel.idx_cap = ranked_cap;
+  sel.avail = (int32_t*)c->topk_avail.ptr;
+  sel.q_offset = 0;
+  sel.q_count = qn;
+  {
+    dvl::StageScope scope(c, DVL_STAGE_SELECT, st);
+    DVL_TRY(dvl::launch_select(c, sel, st));
+  }
+  dvl::MetricArgs m;
+  m.keys = nullptr;
+  m.labs = (const uint8_t*)c->topk_labs.ptr;
+  m.ldk = 0;
+  m.ldl = ldl;
+  m.n_avail = s;
+  m.n_gallery = n_global;
+  m.top_n = top_n;
+  m.q = qn;
+  m.n_classes = n_classes;
+  m.class_counts = (const unsigned long long*)c->class_counts.ptr;
+  m.avail = (const int32_t*)c->topk_avail.ptr;
+  m.per_query = out_per_query;
+  m.ranked_len = out_ranked_len;
+  {
+    dvl::StageScope scope(c, DVL_STAGE_METRICS, st);
+    DVL_TRY(dvl::launch_metrics(c, m, st));
+  }
+  DVL_CUDA(c, cudaStreamSynchronize(st));
+  return DVL_OK;
+}
+
+DVL_API int dvl_mean(dvl_ctx* c, const double* per_query, int32_t q, double* out_mean4, void* stream) {
+  if (c == nullptr) return DVL_ERR_INVALID;
+  if (per_query == nullptr || q < 1) return dvl::set_error(c, DVL_ERR_INVALID, "bad arguments");
+  dvl::DeviceGuard guard(c->device);
+  return dvl::finish(c, per_query, q, 0, out_mean4, false, (cudaStream_t)stream);
 }
 
 }  // extern "C"

@@ -9,7 +9,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 PKG = os.path.dirname(HERE)
 OUT = os.path.join(PKG, "libdvl_b200.so")
-SOURCES = ["api.cu", "prep.cu", "gemm.cu", "segsort.cu", "metrics.cu"]
+SOURCES = ["api.cu", "prep.cu", "gemm.cu", "segsort.cu", "topk.cu", "metrics.cu"]
 HEADERS = ["dvl_common.cuh", "dvl_internal.h", os.path.join("..", "..", "include", "dvl_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "--expt-relaxed-constexpr"]

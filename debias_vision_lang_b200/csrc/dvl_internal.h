@@ -31,6 +31,13 @@ struct Ctx {
   DevBuf keys[2], labs[2], idxs[2];
   DevBuf tile_hist, class_counts, log_tab, per_query, mean_dev, scores_tmp, seg_len, sub_cnt, partial;
   DevBuf h_gallery, h_queries, h_labels;   // staging for the host-input entry point
+  // streaming top-k state
+  DevBuf cand, cand_cnt, cand_tau, cand_flags, topk_labs, topk_avail, fb_queries, fb_per_query, fb_len, fb_idx;
+  DevBuf merge_sorted, tab_chunks;
+  bool select_attr_set = false;
+  int64_t shard_plan_cap = 0;
+  int shard_sort_cap = 0;
+  int shard_q = 0;
   double* mean_pinned = nullptr;           // 4 doubles, pinned host
   int64_t log_tab_len = 0;
   // driver entry point for tensor-map encoding (resolved once, no -lcuda link dependency)
@@ -90,7 +97,16 @@ int launch_class_counts(Ctx* c, const uint8_t* labels, int64_t n, int n_classes,
                         cudaStream_t st);
 
 // ---- gemm.cu ---------------------------------------------------------------------------
+enum { kGemmStore = 0, kGemmSeed = 1, kGemmFilter = 2 };
 struct GemmArgs {
+  int mode = kGemmStore;
+  int64_t row0 = 0, row1 = 0;       // gallery rows [row0, row1) handled by this launch
+  const float* tau = nullptr;
+  unsigned long long* cand = nullptr;
+  uint32_t* cand_cnt = nullptr;
+  int64_t cap = 0;
+  const uint8_t* labels = nullptr;
+  int64_t index_base = 0;
   const __nv_bfloat16* qry_planes;  // [planes][q][dp]
   const __nv_bfloat16* gal_planes;  // [planes][n][dp]
   int planes;                       // 1 (bf16) or 3 (fp32 via bf16x3)
@@ -125,6 +141,37 @@ struct SortArgs {
 int launch_segmented_sort(Ctx* c, const SortArgs& a, int* out_buf, cudaStream_t st);
 int launch_scores_to_keys(Ctx* c, const float* scores, int64_t lds, uint32_t* keys, int64_t ldk, int64_t n, int q,
                           cudaStream_t st);
+
+// ---- topk.cu ---------------------------------------------------------------------------
+struct SelectArgs {
+  unsigned long long* cand = nullptr;
+  int64_t row_stride = 0, seg_stride = 0;
+  int segs = 1;
+  int64_t seg_len = 0;
+  uint32_t* cnt = nullptr;
+  int64_t cap = 0;
+  float* tau = nullptr;
+  uint32_t* flags = nullptr;
+  int64_t k = 0;
+  int sort_cap = 0;
+  int64_t trigger = 0;
+  bool final_pass = false;
+  unsigned long long* sorted_out = nullptr;
+  uint8_t* labs = nullptr;
+  int64_t ldl = 0;
+  int32_t* idx_out = nullptr;
+  int64_t idx_cap = 0;
+  int32_t* avail = nullptr;
+  int q_offset = 0;
+  int q_count = 0;
+};
+int launch_topk_reset(Ctx* c, uint32_t* cnt, float* tau, uint32_t* flags, int q, uint32_t cnt_value, bool reset_all,
+                      cudaStream_t st);
+int launch_select(Ctx* c, const SelectArgs& a, cudaStream_t st);
+int launch_trim_count(Ctx* c, const unsigned long long* sorted, int64_t row_stride, const int32_t* avail,
+                      const float* tau_bound, int q, int32_t* out_cnt, cudaStream_t st);
+int launch_pack_lists(Ctx* c, const unsigned long long* sorted, int64_t row_stride, const int32_t* cnt, int q,
+                      int64_t len, unsigned long long* out, cudaStream_t st);
 
 // ---- metrics.cu ------------------------------------------------------------------------
 struct MetricArgs {

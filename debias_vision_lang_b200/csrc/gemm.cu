@@ -12,8 +12,13 @@
 //   warp 0      TMA producer (one lane)      full/empty mbarrier ring, kStages deep
 //   warp 1      TMEM allocator + MMA issuer (one lane), double-buffered fp32 accumulators
 //               (2 x 256 TMEM columns) so the epilogue of tile t overlaps the MMAs of t+1
-//   warps 2..5  epilogue: tcgen05.ld 32 lanes x 32 columns -> fused scale (L2 normalisation)
-//               -> ranking key / fp32 score -> 128-byte row segments to HBM
+//   warps 2..5  epilogue: tcgen05.ld 32 lanes x 32 columns -> fused scale (L2 normalisation) ->
+//               STORE : ranking key / fp32 score, 128-byte row segments to HBM (full-sort route)
+//               SEED  : every (key, index, label) candidate of the first gallery chunk, dense
+//               FILTER: streaming top-k -- one compare per similarity against the query's
+//                       running threshold tau_q held in a register; the rare survivors are
+//                       appended to the query's candidate list.  The similarity matrix never
+//                       reaches HBM.
 //
 // fp32 mode: operands arrive as three exact bf16 planes each; the K loop runs over the six
 // (i, j) plane pairs with i + j <= 4, smallest terms first, all into the same accumulator.
@@ -41,14 +46,18 @@ constexpr int kStageBytes = kABytes + kBBytes;
 constexpr int kTmemCols = 512;         // 2 accumulator buffers x 256 columns
 constexpr int kNumThreads = 192;       // 6 warps
 constexpr int kEpiThreads = 128;
-constexpr size_t kSmemBytes = 1024 /*align slack*/ + (size_t)kStages * kStageBytes + 256 /*barriers*/;
+constexpr int kEpiScratchBytes = kEpiThreads * 33 * 4;   // FILTER: one 32-word row per epilogue thread
+constexpr size_t kSmemBytes =
+    1024 /*align slack*/ + (size_t)kStages * kStageBytes + 256 /*barriers*/ + kEpiScratchBytes;
 
 // plane pairs (query plane, gallery plane), smallest product magnitude first
 __constant__ int c_term_a[6] = {0, 1, 2, 0, 1, 0};
 __constant__ int c_term_b[6] = {2, 1, 0, 1, 0, 0};
 
 struct KernelParams {
-  int64_t n;
+  int mode;          // kGemmStore / kGemmSeed / kGemmFilter
+  int64_t row0;      // first gallery row of this launch (multiple of 256)
+  int64_t n;         // one past the last gallery row of this launch
   int q;
   int n_qtiles;
   int64_t n_tiles;
@@ -60,7 +69,19 @@ struct KernelParams {
   int64_t ldk;
   float* scores;
   int64_t lds;
+  // streaming top-k
+  const float* tau;            // [q] running threshold (score); a similarity survives if s >= tau
+  unsigned long long* cand;    // [q][cap] entries key<<32 | global index<<4 | label
+  uint32_t* cand_cnt;          // [q]
+  int64_t cap;
+  const uint8_t* labels;       // [n] labels of this gallery shard
+  int64_t index_base;          // global index of local row 0
 };
+
+__device__ __forceinline__ unsigned long long make_entry(float s, int64_t gidx, uint32_t label) {
+  return (static_cast<unsigned long long>(score_to_key(s)) << 32) | (static_cast<unsigned long long>(gidx) << 4) |
+         static_cast<unsigned long long>(label & 0xFu);
+}
 
 __global__ void __launch_bounds__(kNumThreads, 1)
 sim_gemm_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_g,
@@ -75,6 +96,7 @@ sim_gemm_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
   auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * kStages + a); };
   auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * kStages + 2 + a); };
   const uint32_t tmem_slot = bar_base + 8u * (2 * kStages + 4);
+  uint32_t* epi_scratch = reinterpret_cast<uint32_t*>(smem_raw + (bar_base + 256u - smem_u32(smem_raw)));
   volatile uint32_t* tmem_slot_ptr =
       reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
 
@@ -122,7 +144,7 @@ sim_gemm_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
           mbar_arrive_expect_tx(full_bar(stage), kStageBytes);
           const uint32_t sa = smem_base + stage * kStageBytes;
           tma_load_3d(sa, &map_q, full_bar(stage), kb * BK, qt * BM, pa);
-          tma_load_3d(sa + kABytes, &map_g, full_bar(stage), kb * BK, (int)(gb * BN), pb);
+          tma_load_3d(sa + kABytes, &map_g, full_bar(stage), kb * BK, (int)(p.row0 + gb * BN), pb);
           if (++stage == kStages) { stage = 0; phase ^= 1u; }
         }
       }
@@ -171,6 +193,8 @@ sim_gemm_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
       const int qrow = qt * BM + row_in_tile;
       const bool row_ok = qrow < p.q;
       const float qs = (p.qry_scale != nullptr && row_ok) ? __ldg(p.qry_scale + qrow) : 1.0f;
+      float tau = __int_as_float(0x7f800000);       // +inf: padded query rows keep nothing
+      if (p.mode == kGemmFilter && row_ok) tau = __ldg(p.tau + qrow);
       mbar_wait(tfull_bar(as), aphase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + (uint32_t)(as * BN) + ((uint32_t)(quarter * 32) << 16);
@@ -179,7 +203,7 @@ sim_gemm_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
         uint32_t v[32];
         tmem_ld_32x32(taddr + (uint32_t)(chunk * 32), v);
         tmem_ld_wait();
-        const int64_t col0 = gb * BN + chunk * 32;
+        const int64_t col0 = p.row0 + gb * BN + chunk * 32;
         if (p.qry_scale != nullptr || p.gal_scale != nullptr) {
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
@@ -188,18 +212,61 @@ sim_gemm_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
             v[j] = __float_as_uint(s);
           }
         }
-        if (row_ok) {
-          if (p.scores != nullptr) {
-            float* dst = p.scores + (int64_t)qrow * p.lds + col0;
+        if (p.mode == kGemmStore) {
+          if (row_ok) {
+            if (p.scores != nullptr) {
+              float* dst = p.scores + (int64_t)qrow * p.lds + col0;
 #pragma unroll
-            for (int j = 0; j < 32; j += 4) st_global_v4(dst + j, v[j], v[j + 1], v[j + 2], v[j + 3]);
+              for (int j = 0; j < 32; j += 4) st_global_v4(dst + j, v[j], v[j + 1], v[j + 2], v[j + 3]);
+            }
+            if (p.keys != nullptr) {
+              uint32_t* dst = p.keys + (int64_t)qrow * p.ldk + col0;
+#pragma unroll
+              for (int j = 0; j < 32; j += 4)
+                st_global_v4(dst + j, score_to_key(__uint_as_float(v[j])), score_to_key(__uint_as_float(v[j + 1])),
+                             score_to_key(__uint_as_float(v[j + 2])), score_to_key(__uint_as_float(v[j + 3])));
+            }
           }
-          if (p.keys != nullptr) {
-            uint32_t* dst = p.keys + (int64_t)qrow * p.ldk + col0;
+        } else if (p.mode == kGemmSeed) {
+          // first chunk: every row is a candidate, position = column (no atomics, 256 B per thread)
+          if (row_ok && col0 < p.n) {
+            unsigned long long* dst = p.cand + (int64_t)qrow * p.cap + (col0 - p.row0);
+            const uint4 l0 = __ldg(reinterpret_cast<const uint4*>(p.labels + col0));
+            const uint4 l1 = __ldg(reinterpret_cast<const uint4*>(p.labels + col0) + 1);
+            const uint32_t lw[8] = {l0.x, l0.y, l0.z, l0.w, l1.x, l1.y, l1.z, l1.w};
 #pragma unroll
-            for (int j = 0; j < 32; j += 4)
-              st_global_v4(dst + j, score_to_key(__uint_as_float(v[j])), score_to_key(__uint_as_float(v[j + 1])),
-                           score_to_key(__uint_as_float(v[j + 2])), score_to_key(__uint_as_float(v[j + 3])));
+            for (int j = 0; j < 32; j += 2) {
+              // rows past the end of the gallery become NaN-keyed entries that are never ranked
+              const unsigned long long e0 = (col0 + j < p.n)
+                  ? make_entry(__uint_as_float(v[j]), p.index_base + col0 + j, (lw[j >> 2] >> (8 * (j & 3))) & 0xFFu)
+                  : ~0ull;
+              const unsigned long long e1 = (col0 + j + 1 < p.n)
+                  ? make_entry(__uint_as_float(v[j + 1]), p.index_base + col0 + j + 1,
+                               (lw[(j + 1) >> 2] >> (8 * ((j + 1) & 3))) & 0xFFu)
+                  : ~0ull;
+              st_global_v4(dst + j, (uint32_t)e0, (uint32_t)(e0 >> 32), (uint32_t)e1, (uint32_t)(e1 >> 32));
+            }
+          }
+        } else {
+          // streaming top-k: one compare per similarity; survivors are rare once tau has tightened
+          uint32_t mask = 0;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) mask |= (__uint_as_float(v[j]) >= tau ? 1u : 0u) << j;
+          const int64_t left = p.n - col0;
+          if (left < 32) mask &= (left <= 0) ? 0u : ((1u << left) - 1u);
+          if (mask != 0u) {
+            uint32_t* mine = epi_scratch + (threadIdx.x - 64) * 33;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) mine[j] = v[j];
+            while (mask != 0u) {
+              const int j = __ffs(mask) - 1;
+              mask &= mask - 1u;
+              const int64_t col = col0 + j;
+              const uint32_t pos = atomicAdd(p.cand_cnt + qrow, 1u);
+              if ((int64_t)pos < p.cap)
+                p.cand[(int64_t)qrow * p.cap + pos] =
+                    make_entry(__uint_as_float(mine[j]), p.index_base + col, __ldg(p.labels + col));
+            }
           }
         }
       }
@@ -246,15 +313,31 @@ int make_map(Ctx* c, CUtensorMap* map, const void* base, int64_t rows, int d, in
 int launch_sim_gemm(Ctx* c, const GemmArgs& a, cudaStream_t st) {
   if (a.dp % 8 != 0) return set_error(c, DVL_ERR_INVALID, "plane row pitch must be a multiple of 8 elements");
   if (a.n <= 0 || a.q <= 0 || a.d <= 0) return set_error(c, DVL_ERR_INVALID, "empty similarity problem");
+  if (a.row0 < 0 || a.row0 % BN != 0 || a.row1 <= a.row0 || a.row1 > a.n)
+    return set_error(c, DVL_ERR_INVALID, "bad gallery row range [%lld, %lld)", (long long)a.row0, (long long)a.row1);
+  if (a.mode != kGemmStore && (a.cand == nullptr || a.cand_cnt == nullptr || a.labels == nullptr || a.cap < 1))
+    return set_error(c, DVL_ERR_INVALID, "streaming top-k launch without candidate buffers");
+  if (a.mode == kGemmFilter && a.tau == nullptr) return set_error(c, DVL_ERR_INVALID, "filter launch without thresholds");
+  if (a.mode == kGemmSeed && (a.row1 - a.row0 > a.cap || (reinterpret_cast<uintptr_t>(a.labels) & 15) != 0))
+    return set_error(c, DVL_ERR_INVALID, "seed chunk larger than the candidate capacity or unaligned labels");
+  if (a.index_base + a.n > (1ll << 28)) return set_error(c, DVL_ERR_UNSUPPORTED, "global gallery index needs more than 28 bits");
   if (a.n > 0x7FFFFF00ll) return set_error(c, DVL_ERR_UNSUPPORTED, "gallery shard larger than 2^31 rows");
   CUtensorMap map_q, map_g;
   DVL_TRY(make_map(c, &map_q, a.qry_planes, a.q, a.d, a.dp, a.planes, BM));
   DVL_TRY(make_map(c, &map_g, a.gal_planes, a.n, a.d, a.dp, a.planes, BN));
   KernelParams p;
-  p.n = a.n;
+  p.mode = a.mode;
+  p.row0 = a.row0;
+  p.n = a.row1;
   p.q = a.q;
   p.n_qtiles = (a.q + BM - 1) / BM;
-  p.n_tiles = (int64_t)p.n_qtiles * ((a.n + BN - 1) / BN);
+  p.n_tiles = (int64_t)p.n_qtiles * ((a.row1 - a.row0 + BN - 1) / BN);
+  p.tau = a.tau;
+  p.cand = a.cand;
+  p.cand_cnt = a.cand_cnt;
+  p.cap = a.cap;
+  p.labels = a.labels;
+  p.index_base = a.index_base;
   p.k_blocks = (a.d + BK - 1) / BK;
   p.n_terms = (a.planes == 3) ? 6 : 1;
   p.qry_scale = a.qry_scale;
@@ -263,6 +346,7 @@ int launch_sim_gemm(Ctx* c, const GemmArgs& a, cudaStream_t st) {
   p.ldk = a.ldk;
   p.scores = a.scores;
   p.lds = a.lds;
+  if (a.mode == kGemmStore && a.row0 != 0) return set_error(c, DVL_ERR_INVALID, "store mode takes the whole gallery");
   if (a.keys != nullptr && (a.ldk % 4 != 0 || a.ldk < ((a.n + BN - 1) / BN) * BN))
     return set_error(c, DVL_ERR_INVALID, "key pitch must cover whole 256-column tiles");
   if (a.scores != nullptr && (a.lds % 4 != 0 || a.lds < ((a.n + BN - 1) / BN) * BN))

@@ -36,52 +36,70 @@ constexpr int kWarpsPerCta = 4;
 constexpr double kLn2 = 0.693147180559945309417232121458176568;
 
 // ---- tables ------------------------------------------------------------------------------
-// single CTA so that the prefix sums have one fixed summation order
-__global__ void __launch_bounds__(1024) metric_tables_kernel(double* __restrict__ dxl, double* __restrict__ pwi,
-                                                             double* __restrict__ pw, double* __restrict__ pwl,
-                                                             int64_t len) {
-  __shared__ double sh[3][1024];
-  const int t = threadIdx.x;
-  const int64_t per = (len + 1023) / 1024;
-  const int64_t lo = (int64_t)t * per;
-  const int64_t hi = (lo + per < len) ? lo + per : len;
+// Prefix sums in a fixed blocking (chunks of kTabChunk entries, chunk totals added up in index
+// order), so that an entry's value depends only on its index -- not on the table length or on
+// which context built it: sharded and unsharded runs then agree bit for bit.
+constexpr int kTabChunk = 256;
+
+__device__ __forceinline__ void table_terms(int64_t i, double* w, double* wl, double* wi) {
+  const double ww = kLn2 / log((double)(i + 1));
+  *w = ww;
+  *wl = ww * log((double)i);
+  *wi = ww / (double)i;
+}
+
+__global__ void __launch_bounds__(256) table_chunk_sums_kernel(double* __restrict__ chunk_sums, int64_t len,
+                                                               int64_t chunks) {
+  const int64_t ch = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (ch >= chunks) return;
+  const int64_t lo = ch * kTabChunk;
+  const int64_t hi = (lo + kTabChunk < len) ? lo + kTabChunk : len;
   double sw = 0.0, swl = 0.0, swi = 0.0;
-  for (int64_t i = lo; i < hi; ++i) {
-    if (i == 0) continue;
-    const double w = kLn2 / log((double)(i + 1));
+  for (int64_t i = (lo > 0 ? lo : 1); i < hi; ++i) {
+    double w, wl, wi;
+    table_terms(i, &w, &wl, &wi);
     sw += w;
-    swl += w * log((double)i);
-    swi += w / (double)i;
+    swl += wl;
+    swi += wi;
   }
-  sh[0][t] = sw;
-  sh[1][t] = swl;
-  sh[2][t] = swi;
-  __syncthreads();
-  if (t < 3) {
-    double a = 0.0;
-    for (int k = 0; k < 1024; ++k) {
-      const double x = sh[t][k];
-      sh[t][k] = a;
-      a += x;
-    }
+  chunk_sums[3 * ch] = sw;
+  chunk_sums[3 * ch + 1] = swl;
+  chunk_sums[3 * ch + 2] = swi;
+}
+
+__global__ void table_chunk_scan_kernel(double* __restrict__ chunk_sums, int64_t chunks) {
+  const int k = threadIdx.x;          // 3 threads: one running sum each, strictly in index order
+  if (k >= 3) return;
+  double run = 0.0;
+  for (int64_t ch = 0; ch < chunks; ++ch) {
+    const double v = chunk_sums[3 * ch + k];
+    chunk_sums[3 * ch + k] = run;
+    run += v;
   }
-  __syncthreads();
-  sw = sh[0][t];
-  swl = sh[1][t];
-  swi = sh[2][t];
+}
+
+__global__ void __launch_bounds__(256) table_fill_kernel(const double* __restrict__ chunk_sums,
+                                                         double* __restrict__ dxl, double* __restrict__ pwi,
+                                                         double* __restrict__ pw, double* __restrict__ pwl,
+                                                         int64_t len, int64_t chunks) {
+  const int64_t ch = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (ch >= chunks) return;
+  const int64_t lo = ch * kTabChunk;
+  const int64_t hi = (lo + kTabChunk < len) ? lo + kTabChunk : len;
+  double sw = chunk_sums[3 * ch], swl = chunk_sums[3 * ch + 1], swi = chunk_sums[3 * ch + 2];
   for (int64_t i = lo; i < hi; ++i) {
     if (i == 0) {
       dxl[0] = 0.0; pwi[0] = 0.0; pw[0] = 0.0; pwl[0] = 0.0;
       continue;
     }
-    const double di = (double)i;
-    const double ln_i = log(di);
-    const double w = kLn2 / log((double)(i + 1));
+    double w, wl, wi;
+    table_terms(i, &w, &wl, &wi);
     sw += w;
-    swl += w * ln_i;
-    swi += w / di;
+    swl += wl;
+    swi += wi;
+    const double di = (double)i;
     // i ln i - (i-1) ln(i-1) = ln i + (i-1) ln(1 + 1/(i-1)), without the cancellation
-    dxl[i] = (i == 1) ? 0.0 : ln_i + (di - 1.0) * log1p(1.0 / (di - 1.0));
+    dxl[i] = (i == 1) ? 0.0 : log(di) + (di - 1.0) * log1p(1.0 / (di - 1.0));
     pwi[i] = swi;
     pw[i] = sw;
     pwl[i] = swl;
@@ -358,10 +376,18 @@ __global__ void __launch_bounds__(256) copy_ranked_kernel(const int32_t* __restr
 int ensure_metric_tables(Ctx* c, int64_t len, cudaStream_t st) {
   if (len <= c->log_tab_len) return DVL_OK;
   const int64_t want = len + len / 8 + 1024;
+  const int64_t chunks = (want + kTabChunk - 1) / kTabChunk;
   DVL_TRY(ensure(c, c->log_tab, (size_t)want * 4 * sizeof(double)));
+  DVL_TRY(ensure(c, c->tab_chunks, (size_t)chunks * 3 * sizeof(double)));
   double* base = (double*)c->log_tab.ptr;
-  metric_tables_kernel<<<1, 1024, 0, st>>>(base, base + want, base + 2 * want, base + 3 * want, want);
-  DVL_LAUNCH_CHECK(c, "metric_tables_kernel");
+  double* sums = (double*)c->tab_chunks.ptr;
+  const unsigned blocks = (unsigned)((chunks + 255) / 256);
+  table_chunk_sums_kernel<<<blocks, 256, 0, st>>>(sums, want, chunks);
+  DVL_LAUNCH_CHECK(c, "table_chunk_sums_kernel");
+  table_chunk_scan_kernel<<<1, 32, 0, st>>>(sums, chunks);
+  DVL_LAUNCH_CHECK(c, "table_chunk_scan_kernel");
+  table_fill_kernel<<<blocks, 256, 0, st>>>(sums, base, base + want, base + 2 * want, base + 3 * want, want, chunks);
+  DVL_LAUNCH_CHECK(c, "table_fill_kernel");
   c->log_tab_len = want;
   return DVL_OK;
 }

@@ -1,0 +1,288 @@
+// Ranking stage, streaming top-k route (SURVEY.md row a3 for top_n << N; the north_star's
+// kernel (b)).  The similarity GEMM's epilogue (gemm.cu, SEED / FILTER modes) appends to each
+// query's candidate list every gallery row whose score is >= the query's running threshold
+// tau_q.  This file holds the other half:
+//
+//   select_kernel, one CTA per query
+//     * radix-select (4 x 8-bit passes over the list, shared-memory histograms) of the top_n-th
+//       smallest ranking key  ->  new threshold;
+//     * keeps every entry with key <= that key -- i.e. the top_n best AND every row tied with
+//       the top_n-th (pandas nlargest keep="all", selectn.py:176-182) -- compacted through
+//       shared memory, so tau_q only ever tightens and nothing that can still rank is dropped;
+//     * final pass: bitonic sort of the kept entries in shared memory.  An entry is
+//       key<<32 | global index<<4 | label, so ascending u64 order IS the reference's order
+//       (score descending, lowest index first) no matter in which order the GEMM CTAs appended;
+//       emits the ranked labels (for metrics.cu) and indices.
+//   A query whose tie run does not fit the list (e.g. an all-zero query: every row ties) is
+//   flagged and re-ranked by the full-sort route, so the result is exact for any input.
+//
+// The same kernel merges the per-shard lists of a multi-GPU run (segments = shards).
+#include "dvl_common.cuh"
+#include "dvl_internal.h"
+
+namespace dvl {
+
+namespace {
+
+constexpr int kSelThreads = 256;
+
+struct SelectParams {
+  // candidate lists: query q's entries are `segs` runs of up to seg_len entries,
+  // run s starting at cand + s*seg_stride + q*row_stride (local lists: segs = 1)
+  unsigned long long* cand;
+  int64_t row_stride, seg_stride;
+  int segs;
+  int64_t seg_len;          // entries per segment when segs > 1 (fixed); unused for segs == 1
+  uint32_t* cnt;            // [q] entries in use (segs == 1); null for segs > 1
+  int64_t cap;              // capacity of a local list
+  float* tau;               // [q] threshold to update, or null
+  uint32_t* flags;          // [q] tie-overflow flags
+  int64_t k;
+  int sort_cap;             // S: entries that fit the shared-memory list
+  int64_t trigger;          // skip (non-final) while the list is shorter than this
+  int final_pass;
+  // final outputs
+  unsigned long long* sorted_out;   // [q][sort_cap] or null (defaults to in place for segs == 1)
+  uint8_t* labs;            // [q][ldl]
+  int64_t ldl;
+  int32_t* idx_out;         // [q][idx_cap] or null
+  int64_t idx_cap;
+  int32_t* avail;           // [q] ranked rows m_q
+  int q_offset;             // queries handled: blockIdx.x + q_offset
+};
+
+__device__ __forceinline__ unsigned long long load_entry(const SelectParams& p, int q, int64_t i) {
+  if (p.segs == 1) return p.cand[(int64_t)q * p.row_stride + i];
+  const int64_t s = i / p.seg_len;
+  return p.cand[s * p.seg_stride + (int64_t)q * p.row_stride + (i - s * p.seg_len)];
+}
+
+__global__ void __launch_bounds__(kSelThreads) select_kernel(const SelectParams p) {
+  extern __shared__ unsigned long long sm_list[];     // sort_cap entries
+  __shared__ uint32_t hist[256];
+  __shared__ uint32_t sh_prefix, sh_remaining, sh_kept;
+  const int q = blockIdx.x + p.q_offset;
+  const int tid = threadIdx.x;
+  if (p.flags[q] != 0u) {                              // already handed to the full-sort route
+    if (p.final_pass && tid == 0 && p.avail != nullptr) p.avail[q] = 0;
+    return;
+  }
+  int64_t n;
+  if (p.segs == 1) {
+    n = p.cnt[q];
+    if (n > p.cap) n = p.cap;                          // cannot happen by construction (cap = S + chunk)
+  } else {
+    n = (int64_t)p.segs * p.seg_len;
+  }
+  if (!p.final_pass && n < p.trigger) return;
+
+  // ---- the k-th smallest key ----
+  uint32_t kth = 0xFFFFFFFFu;
+  if (n > p.k) {
+    if (tid == 0) { sh_prefix = 0u; sh_remaining = (uint32_t)p.k; }
+    uint32_t known_mask = 0u;
+    for (int shift = 24; shift >= 0; shift -= 8) {
+      hist[tid] = 0u;
+      __syncthreads();
+      const uint32_t prefix = sh_prefix;
+      for (int64_t i = tid; i < n; i += kSelThreads) {
+        const uint32_t key = (uint32_t)(load_entry(p, q, i) >> 32);
+        if ((key & known_mask) == prefix) atomicAdd(&hist[(key >> shift) & 0xFFu], 1u);
+      }
+      __syncthreads();
+      if (tid == 0) {
+        uint32_t remaining = sh_remaining, d = 0;
+        for (; d < 255u; ++d) {
+          if (hist[d] >= remaining) break;
+          remaining -= hist[d];
+        }
+        sh_prefix = prefix | (d << shift);
+        sh_remaining = remaining;
+      }
+      known_mask |= 0xFFu << shift;
+      __syncthreads();
+    }
+    kth = sh_prefix;
+  }
+
+  // ---- keep everything that still can rank: key <= kth (ties at the boundary included) ----
+  if (tid == 0) sh_kept = 0u;
+  __syncthreads();
+  for (int64_t i = tid; i < n; i += kSelThreads) {
+    const unsigned long long e = load_entry(p, q, i);
+    if ((uint32_t)(e >> 32) <= kth && e != ~0ull) {
+      const uint32_t pos = atomicAdd(&sh_kept, 1u);
+      if (pos < (uint32_t)p.sort_cap) sm_list[pos] = e;
+    }
+  }
+  __syncthreads();
+  const uint32_t kept = sh_kept;
+  if (kept > (uint32_t)p.sort_cap) {
+    if (tid == 0) {
+      p.flags[q] = 1u;
+      if (p.cnt != nullptr) p.cnt[q] = 0u;
+      if (p.tau != nullptr) p.tau[q] = __int_as_float(0x7f800000);   // stop collecting for this query
+      if (p.final_pass && p.avail != nullptr) p.avail[q] = 0;
+    }
+    return;
+  }
+
+  if (!p.final_pass) {
+    unsigned long long* dst = p.cand + (int64_t)q * p.row_stride;
+    for (uint32_t i = tid; i < kept; i += kSelThreads) dst[i] = sm_list[i];
+    if (tid == 0) {
+      p.cnt[q] = kept;
+      if (n >= p.k && kth != kNanKey) p.tau[q] = key_to_score(kth);
+    }
+    return;
+  }
+
+  // ---- final: sort, emit ----
+  uint32_t pow2 = 1;
+  while (pow2 < kept) pow2 <<= 1;
+  for (uint32_t i = kept + tid; i < pow2; i += kSelThreads) sm_list[i] = ~0ull;
+  __syncthreads();
+  for (uint32_t size = 2; size <= pow2; size <<= 1) {
+    for (uint32_t stride = size >> 1; stride > 0; stride >>= 1) {
+      for (uint32_t t = tid; t < (pow2 >> 1); t += kSelThreads) {
+        const uint32_t i = 2 * t - (t & (stride - 1));
+        const uint32_t j = i + stride;
+        const bool up = (i & size) == 0;
+        const unsigned long long a = sm_list[i], b = sm_list[j];
+        if ((a > b) == up) {
+          sm_list[i] = b;
+          sm_list[j] = a;
+        }
+      }
+      __syncthreads();
+    }
+  }
+  // rows with a NaN score are never ranked (selectn.py:133-134): they sort last
+  if (tid == 0) sh_kept = kept;
+  __syncthreads();
+  for (uint32_t i = tid; i < kept; i += kSelThreads) {
+    const bool nan_here = (uint32_t)(sm_list[i] >> 32) == kNanKey;
+    const bool nan_prev = i > 0 && (uint32_t)(sm_list[i - 1] >> 32) == kNanKey;
+    if (nan_here && !nan_prev) sh_kept = i;
+  }
+  __syncthreads();
+  const uint32_t m = sh_kept;
+  unsigned long long* sorted = (p.sorted_out != nullptr) ? p.sorted_out + (int64_t)q * p.sort_cap
+                                                         : p.cand + (int64_t)q * p.row_stride;
+  uint8_t* labs = p.labs + (int64_t)q * p.ldl;
+  for (uint32_t i = tid; i < m; i += kSelThreads) {
+    const unsigned long long e = sm_list[i];
+    sorted[i] = e;
+    labs[i] = (uint8_t)(e & 0xFull);
+    if (p.idx_out != nullptr && (int64_t)i < p.idx_cap)
+      p.idx_out[(int64_t)q * p.idx_cap + i] = (int32_t)((e >> 4) & 0x0FFFFFFFull);
+  }
+  if (tid == 0) {
+    if (p.cnt != nullptr) p.cnt[q] = m;
+    p.avail[q] = (int32_t)m;
+  }
+}
+
+__global__ void __launch_bounds__(256) fill_topk_state_kernel(uint32_t* cnt, float* tau, uint32_t* flags, int q,
+                                                             uint32_t cnt_value, int reset_all) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= q) return;
+  cnt[i] = cnt_value;
+  if (reset_all) {
+    tau[i] = __int_as_float(0xff800000);   // -inf: everything is a candidate
+    flags[i] = 0u;
+  }
+}
+
+// sorted list -> number of entries that can still rank globally: key <= key(tau_bound)
+__global__ void __launch_bounds__(256) trim_count_kernel(const unsigned long long* __restrict__ sorted,
+                                                         int64_t row_stride, const int32_t* __restrict__ avail,
+                                                         const float* __restrict__ tau_bound, int q,
+                                                         int32_t* __restrict__ out_cnt) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= q) return;
+  const uint32_t bound = score_to_key(tau_bound[i]);
+  const unsigned long long* e = sorted + (int64_t)i * row_stride;
+  int lo = 0, hi = avail[i];
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    if ((uint32_t)(e[mid] >> 32) <= bound) lo = mid + 1; else hi = mid;
+  }
+  out_cnt[i] = lo;
+}
+
+__global__ void __launch_bounds__(256) pack_lists_kernel(const unsigned long long* __restrict__ sorted,
+                                                         int64_t row_stride, const int32_t* __restrict__ cnt,
+                                                         int64_t len, unsigned long long* __restrict__ out) {
+  const int q = blockIdx.y;
+  const int64_t n = cnt[q];
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < len; i += (int64_t)gridDim.x * blockDim.x)
+    out[(int64_t)q * len + i] = (i < n) ? sorted[(int64_t)q * row_stride + i] : ~0ull;
+}
+
+}  // namespace
+
+int launch_topk_reset(Ctx* c, uint32_t* cnt, float* tau, uint32_t* flags, int q, uint32_t cnt_value, bool reset_all,
+                      cudaStream_t st) {
+  fill_topk_state_kernel<<<(q + 255) / 256, 256, 0, st>>>(cnt, tau, flags, q, cnt_value, reset_all ? 1 : 0);
+  DVL_LAUNCH_CHECK(c, "fill_topk_state_kernel");
+  return DVL_OK;
+}
+
+int launch_select(Ctx* c, const SelectArgs& a, cudaStream_t st) {
+  if (a.sort_cap < 2 || (a.sort_cap & (a.sort_cap - 1)) != 0 || a.sort_cap > 16384)
+    return set_error(c, DVL_ERR_INVALID, "select list capacity must be a power of two <= 16384");
+  SelectParams p;
+  p.cand = a.cand;
+  p.row_stride = a.row_stride;
+  p.seg_stride = a.seg_stride;
+  p.segs = a.segs;
+  p.seg_len = a.seg_len;
+  p.cnt = a.cnt;
+  p.cap = a.cap;
+  p.tau = a.tau;
+  p.flags = a.flags;
+  p.k = a.k;
+  p.sort_cap = a.sort_cap;
+  p.trigger = a.trigger;
+  p.final_pass = a.final_pass ? 1 : 0;
+  p.sorted_out = a.sorted_out;
+  p.labs = a.labs;
+  p.ldl = a.ldl;
+  p.idx_out = a.idx_out;
+  p.idx_cap = a.idx_cap;
+  p.avail = a.avail;
+  p.q_offset = a.q_offset;
+  const size_t smem = (size_t)a.sort_cap * sizeof(unsigned long long);
+  if (smem > 48 * 1024 && !c->select_attr_set) {
+    DVL_CUDA(c, cudaFuncSetAttribute(select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 16384 * 8));
+    c->select_attr_set = true;
+  }
+  select_kernel<<<(unsigned)a.q_count, kSelThreads, smem, st>>>(p);
+  DVL_LAUNCH_CHECK(c, "select_kernel");
+  return DVL_OK;
+}
+
+int launch_trim_count(Ctx* c, const unsigned long long* sorted, int64_t row_stride, const int32_t* avail,
+                      const float* tau_bound, int q, int32_t* out_cnt, cudaStream_t st) {
+  trim_count_kernel<<<(q + 255) / 256, 256, 0, st>>>(sorted, row_stride, avail, tau_bound, q, out_cnt);
+  DVL_LAUNCH_CHECK(c, "trim_count_kernel");
+  return DVL_OK;
+}
+
+int launch_pack_lists(Ctx* c, const unsigned long long* sorted, int64_t row_stride, const int32_t* cnt, int q,
+                      int64_t len, unsigned long long* out, cudaStream_t st) {
+  int64_t bx = (len + 255) / 256;
+  if (bx < 1) bx = 1;
+  if (bx > 64) bx = 64;
+  for (int q0 = 0; q0 < q; q0 += 65535) {
+    const int qn = (q - q0) < 65535 ? (q - q0) : 65535;
+    dim3 grid((unsigned)bx, (unsigned)qn);
+    pack_lists_kernel<<<grid, 256, 0, st>>>(sorted + (int64_t)q0 * row_stride, row_stride, cnt + q0, len,
+                                            out + (int64_t)q0 * len);
+    DVL_LAUNCH_CHECK(c, "pack_lists_kernel");
+  }
+  return DVL_OK;
+}
+
+}  // namespace dvl

@@ -1,0 +1,262 @@
+"""Gallery-sharded bias measurement over the GPUs of one box.
+
+One process per GPU.  Rank r owns a contiguous block of gallery rows (so "lowest global index"
+-- the reference's tie rule -- does not depend on the shard layout), every rank holds all
+queries.  The only exchange step of the path is small: per-query thresholds, label histograms
+and the per-shard candidate lists travel through ``torch.distributed`` (NCCL all-reduce /
+all-gather over NVLink); everything else is the C ABI's sharded stages
+(``dvl_shard_topk`` -> ``dvl_shard_trim`` -> ``dvl_shard_pack`` -> ``dvl_merge_topk`` -> ``dvl_mean``).
+
+    local streaming top-k  ->  all-reduce(max) tau        (no row below it can rank globally)
+                               all-reduce(sum) label histogram, all-reduce(max) flags
+    trim to tau            ->  all-reduce(max) list length
+    pack                   ->  all-gather  [world, Q, len] u64 entries
+    merge own query slice  ->  all-gather  per-query MaxSkew/NDKL
+    mean (same reduction tree as one GPU: the result is bit-identical to the unsharded run)
+
+A query whose boundary tie run does not fit a candidate list (say an all-zero query) is flagged
+and re-ranked exactly: every rank computes that query's dense scores for its shard, the rows are
+all-gathered and ranked by the full-sort route.
+
+``evaluate_sharded`` takes a ``comm`` object with ``all_reduce_max/sum``, ``all_gather`` so that
+the protocol can be exercised on CPU with gloo (tests) and emulated in one process (several
+contexts on one GPU); ``TorchDistComm`` is the real thing.
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict, List, Optional, Sequence, Tuple, Union
+
+import numpy as np
+import torch
+
+from . import _capi
+
+__all__ = ["shard_bounds", "TorchDistComm", "LocalComm", "evaluate_sharded", "measure_sharded"]
+
+
+def shard_bounds(n: int, world: int, rank: int) -> Tuple[int, int]:
+    """Contiguous row blocks of ceil(n/world) rows (256-row aligned so that every shard but the
+    last is a whole number of GEMM tiles)."""
+    block = -(-n // world)
+    block = -(-block // 256) * 256
+    lo = min(n, rank * block)
+    return lo, min(n, lo + block)
+
+
+class TorchDistComm:
+    """Collectives over a torch.distributed process group (NCCL on GPUs, gloo in CPU tests)."""
+
+    def __init__(self, group=None):
+        import torch.distributed as dist
+        self.dist = dist
+        self.group = group
+        self.world = dist.get_world_size(group)
+        self.rank = dist.get_rank(group)
+
+    def all_reduce_max(self, t: torch.Tensor) -> torch.Tensor:
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX, group=self.group)
+        return t
+
+    def all_reduce_sum(self, t: torch.Tensor) -> torch.Tensor:
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM, group=self.group)
+        return t
+
+    def all_gather(self, t: torch.Tensor) -> torch.Tensor:
+        """[world, *t.shape]; every rank contributes the same shape."""
+        out = torch.empty((self.world,) + tuple(t.shape), dtype=t.dtype, device=t.device)
+        self.dist.all_gather_into_tensor(out.view(-1), t.contiguous().view(-1), group=self.group)
+        return out
+
+
+class LocalComm:
+    """Single-process stand-in: `world` emulated ranks call in lock step from one thread; each
+    collective is executed when the last rank has contributed (used to emulate N shards on one
+    GPU, and by the unit tests)."""
+
+    def __init__(self, world: int):
+        self.world = world
+        self.rank = 0
+        self._pending: Dict[str, List[torch.Tensor]] = {}
+
+    # The emulation drives ranks phase by phase (see evaluate_sharded_emulated), so the
+    # collectives here operate on lists.
+    @staticmethod
+    def reduce_max(ts: Sequence[torch.Tensor]) -> torch.Tensor:
+        return torch.stack(list(ts)).max(dim=0).values
+
+    @staticmethod
+    def reduce_sum(ts: Sequence[torch.Tensor]) -> torch.Tensor:
+        return torch.stack(list(ts)).sum(dim=0)
+
+    @staticmethod
+    def gather(ts: Sequence[torch.Tensor]) -> torch.Tensor:
+        return torch.stack(list(ts)).contiguous()
+
+
+def _flags_and_precision(opts: Optional[dict]):
+    opts = dict(opts or {})
+    precision = {"fp32": _capi.PRECISION_FP32, "bf16": _capi.PRECISION_BF16}[opts.get("precision", "fp32")]
+    flags = 0
+    if opts.get("normalize_gallery", False):
+        flags |= _capi.FLAG_NORMALIZE_GALLERY
+    if opts.get("normalize_queries", False):
+        flags |= _capi.FLAG_NORMALIZE_QUERIES
+    return precision, flags
+
+
+def _query_slice(q: int, world: int, rank: int) -> Tuple[int, int]:
+    block = -(-q // world)
+    lo = min(q, rank * block)
+    return lo, min(q, lo + block) - lo
+
+
+def evaluate_sharded(ctx, comm, gallery_local: torch.Tensor, queries: torch.Tensor, labels_local_u8: torch.Tensor,
+                     index_base: int, n_global: int, n_classes: int, top_n: int, opts: Optional[dict] = None,
+                     ranked_cap: int = 0) -> Dict[str, object]:
+    """One rank's part of the sharded evaluation.  Returns the same dict on every rank:
+    ``{"maxskew": {...}, "ndkl": {...}, "per_query": [Q,4] f64, "ranked_len": [Q] i32, "n_flagged": int}``."""
+    precision, flags = _flags_and_precision(opts)
+    world, rank = comm.world, comm.rank
+    q = queries.shape[0]
+    if top_n < 1:
+        raise ZeroDivisionError("top_n must be >= 1")
+
+    # 1. local streaming top-k (a rank may own no rows when the gallery is tiny)
+    dev = queries.device
+    have_rows = gallery_local.shape[0] > 0
+    if have_rows:
+        tau, oflags, counts, _ = ctx.shard_topk(gallery_local, queries, labels_local_u8, index_base, n_classes,
+                                                top_n, precision, flags)
+    else:
+        tau = torch.full((q,), float("-inf"), dtype=torch.float32, device=dev)
+        oflags = torch.zeros((q,), dtype=torch.int32, device=dev)
+        counts = torch.zeros((_capi.MAX_CLASSES + 1,), dtype=torch.int64, device=dev)
+    tau = comm.all_reduce_max(tau)
+    counts = comm.all_reduce_sum(counts)
+    oflags = comm.all_reduce_max(oflags)
+    if int(counts[_capi.MAX_CLASSES].item()) != 0:
+        raise _capi.DvlError(-1, f"a label is >= n_classes ({n_classes})")
+    # 2. what can still rank globally
+    cnt = ctx.shard_trim(tau) if have_rows else torch.zeros((q,), dtype=torch.int32, device=dev)
+    length = comm.all_reduce_max(cnt.max().reshape(1).to(torch.int64))
+    length = max(1, int(length.item()))
+    # 3. exchange
+    packed = ctx.shard_pack(cnt, length) if have_rows else torch.full((q, length), -1, dtype=torch.int64, device=dev)
+    gathered = comm.all_gather(packed)                      # [world, Q, len]
+    # 4. merge this rank's slice of the queries
+    q0, qn = _query_slice(q, world, rank)
+    block = -(-q // world)
+    per_query_blk = torch.zeros((block, 4), dtype=torch.float64, device=queries.device)
+    ranked_len_blk = torch.zeros((block,), dtype=torch.int32, device=queries.device)
+    flags_blk = torch.zeros((block,), dtype=torch.int32, device=queries.device)
+    idx_blk = torch.full((block, ranked_cap), -1, dtype=torch.int32, device=queries.device) if ranked_cap else None
+    if qn > 0:
+        res = ctx.merge_topk(gathered, q0, qn, n_global, counts[:_capi.MAX_CLASSES].contiguous(), n_classes, top_n,
+                             ranked_cap)
+        per_query_blk[:qn] = res["per_query"]
+        ranked_len_blk[:qn] = res["ranked_len"]
+        flags_blk[:qn] = res["flags"]
+        if ranked_cap:
+            idx_blk[:qn] = res["ranked_idx"]
+    per_query = comm.all_gather(per_query_blk).reshape(-1, 4)[:q].contiguous()
+    ranked_len = comm.all_gather(ranked_len_blk).reshape(-1)[:q].contiguous()
+    merge_flags = comm.all_gather(flags_blk).reshape(-1)[:q]
+    ranked_idx = comm.all_gather(idx_blk).reshape(-1, ranked_cap)[:q].contiguous() if ranked_cap else None
+    flagged = torch.nonzero((oflags != 0) | (merge_flags != 0)).reshape(-1)
+    n_flagged = int(flagged.numel())
+    # 5. exact re-rank of flagged queries (tie run longer than a candidate list)
+    if n_flagged:
+        n_local = gallery_local.shape[0]
+        rows_blk = shard_bounds(n_global, world, 0)[1]
+        fq = queries[flagged].contiguous()
+        local_scores = torch.zeros((n_flagged, rows_blk), dtype=torch.float32, device=queries.device)
+        if n_local:
+            local_scores[:, :n_local] = ctx.similarity(gallery_local, fq, precision, flags)
+        lab_blk = torch.zeros((rows_blk,), dtype=torch.uint8, device=queries.device)
+        lab_blk[:n_local] = labels_local_u8
+        all_scores = comm.all_gather(local_scores)          # [world, F, rows_blk]
+        all_labels = comm.all_gather(lab_blk).reshape(-1)[:n_global].contiguous()
+        full = all_scores.permute(1, 0, 2).reshape(n_flagged, -1)[:, :n_global].contiguous()
+        rr = ctx.rank_and_score(full, all_labels, n_classes, top_n, ranked_cap)
+        per_query[flagged] = rr["per_query"]
+        ranked_len[flagged] = rr["ranked_len"]
+        if ranked_cap:
+            ranked_idx[flagged] = rr["ranked_idx"]
+    mean = ctx.mean(per_query)
+    out = {"maxskew": {"eq_opp": mean[0], "dem_par": mean[1]}, "ndkl": {"eq_opp": mean[2], "dem_par": mean[3]},
+           "per_query": per_query, "ranked_len": ranked_len, "n_flagged": n_flagged, "list_len": length}
+    if ranked_cap:
+        out["ranked_idx"] = ranked_idx
+    return out
+
+
+def evaluate_sharded_emulated(contexts: Sequence, gallery: torch.Tensor, queries: torch.Tensor, labels_u8: torch.Tensor,
+                              n_classes: int, top_n: int, opts: Optional[dict] = None, ranked_cap: int = 0):
+    """All `len(contexts)` ranks in ONE process on one GPU, stage by stage (no kernel ever waits on
+    another rank): the same C-ABI stage calls as `evaluate_sharded`, with the collectives replaced
+    by tensor ops.  Used by the GPU tests and by bench.py --emulate-shards."""
+    precision, flags = _flags_and_precision(opts)
+    world = len(contexts)
+    n, q = gallery.shape[0], queries.shape[0]
+    bounds = [shard_bounds(n, world, r) for r in range(world)]
+    shards = [(gallery[lo:hi].contiguous(), labels_u8[lo:hi].contiguous(), lo) for lo, hi in bounds]
+    s1 = [ctx.shard_topk(g, queries, l, lo, n_classes, top_n, precision, flags) if g.shape[0] else None
+          for ctx, (g, l, lo) in zip(contexts, shards)]
+    live = [r for r in range(world) if s1[r] is not None]
+    tau = LocalComm.reduce_max([s1[r][0] for r in live])
+    oflags = LocalComm.reduce_max([s1[r][1] for r in live])
+    counts = LocalComm.reduce_sum([s1[r][2] for r in live])
+    if int(counts[_capi.MAX_CLASSES].item()) != 0:
+        raise _capi.DvlError(-1, f"a label is >= n_classes ({n_classes})")
+    cnts = {r: contexts[r].shard_trim(tau) for r in live}
+    length = max(1, max(int(c.max().item()) for c in cnts.values()))
+    empty = torch.full((q, length), -1, dtype=torch.int64, device=queries.device)
+    gathered = LocalComm.gather([contexts[r].shard_pack(cnts[r], length) if r in cnts else empty for r in range(world)])
+    per_query = torch.zeros((q, 4), dtype=torch.float64, device=queries.device)
+    ranked_len = torch.zeros((q,), dtype=torch.int32, device=queries.device)
+    merge_flags = torch.zeros((q,), dtype=torch.int32, device=queries.device)
+    ranked_idx = torch.full((q, ranked_cap), -1, dtype=torch.int32, device=queries.device) if ranked_cap else None
+    for r in range(world):
+        q0, qn = _query_slice(q, world, r)
+        if qn <= 0:
+            continue
+        res = contexts[r].merge_topk(gathered, q0, qn, n, counts[:_capi.MAX_CLASSES].contiguous(), n_classes, top_n,
+                                     ranked_cap)
+        per_query[q0:q0 + qn] = res["per_query"]
+        ranked_len[q0:q0 + qn] = res["ranked_len"]
+        merge_flags[q0:q0 + qn] = res["flags"]
+        if ranked_cap:
+            ranked_idx[q0:q0 + qn] = res["ranked_idx"]
+    flagged = torch.nonzero((oflags != 0) | (merge_flags != 0)).reshape(-1)
+    if flagged.numel():
+        fq = queries[flagged].contiguous()
+        parts = [contexts[r].similarity(shards[r][0], fq, precision, flags) for r in live]
+        full = torch.cat(parts, dim=1).contiguous()
+        rr = contexts[0].rank_and_score(full, labels_u8, n_classes, top_n, ranked_cap)
+        per_query[flagged] = rr["per_query"]
+        ranked_len[flagged] = rr["ranked_len"]
+        if ranked_cap:
+            ranked_idx[flagged] = rr["ranked_idx"]
+    mean = contexts[0].mean(per_query)
+    out = {"maxskew": {"eq_opp": mean[0], "dem_par": mean[1]}, "ndkl": {"eq_opp": mean[2], "dem_par": mean[3]},
+           "per_query": per_query, "ranked_len": ranked_len, "n_flagged": int(flagged.numel()), "list_len": length}
+    if ranked_cap:
+        out["ranked_idx"] = ranked_idx
+    return out
+
+
+def measure_sharded(labels_local, gallery_local: torch.Tensor, queries: torch.Tensor, index_base: int, n_global: int,
+                    topn: Union[int, float] = 1000, opts: Optional[dict] = None, group=None):
+    """Convenience wrapper under torchrun: labels (ints, local rows) -> the measure_bias dict."""
+    lab = np.asarray(labels_local)
+    n_classes = int(opts.get("n_classes")) if opts and "n_classes" in opts else int(lab.max()) + 1
+    top_n = math.ceil(n_global * topn) if isinstance(topn, float) else int(topn)
+    dev = gallery_local.device
+    comm = TorchDistComm(group)
+    nc = comm.all_reduce_max(torch.tensor([n_classes], dtype=torch.int64, device=dev))
+    n_classes = int(nc.item())
+    ctx = _capi.context(dev.index)
+    res = evaluate_sharded(ctx, comm, gallery_local.contiguous(), queries.contiguous(),
+                           torch.from_numpy(lab.astype(np.uint8)).to(dev), index_base, n_global, n_classes, top_n, opts)
+    return {"maxskew": res["maxskew"], "ndkl": res["ndkl"]}

@@ -67,6 +67,8 @@ typedef enum dvl_precision { DVL_PRECISION_FP32 = 0, DVL_PRECISION_BF16 = 1 } dv
 #define DVL_FLAG_NORMALIZE_GALLERY 0x2u /* NOT what eval_ranking does: cosine mode */
 #define DVL_FLAG_FULL_SORT         0x4u /* force the materialise-and-sort ranking route even when
                                            top_n << N (the route top_n >= N always takes) */
+#define DVL_FLAG_STREAM_TOPK       0x8u /* force the streaming top-k route even on a small gallery
+                                           (chunks of N/4 rows); needs top_n < N and top_n <= 8192 */
 
 /* per-query result layout: 4 doubles per query */
 #define DVL_MAXSKEW_EQ_OPP 0
@@ -165,6 +167,49 @@ DVL_API int dvl_similarity(dvl_ctx* ctx,
                    const void* gallery, int gallery_dtype, const void* queries, int query_dtype,
                    int64_t n, int32_t d, int32_t q, int precision, uint32_t flags,
                    float* out, int64_t ld_out, void* stream);
+
+/* ---- gallery sharded over several GPUs ---------------------------------
+ * One context per rank.  Rank r holds gallery rows [index_base, index_base + n_local) (contiguous
+ * blocks, so "lowest global index" is independent of the shard layout), all queries, and the labels
+ * of its rows.  The host moves three small things between the stages with its own collective
+ * library (torch.distributed / NCCL all-gather, all-reduce):
+ *   1. dvl_shard_topk   local streaming top-k.  Keeps in the context, per query, the sorted list
+ *                       of every local row that ranks within top_n locally (ties included) and
+ *                       returns tau[q] = score of the local top_n-th row (-inf if fewer rows),
+ *                       tie-overflow flags, and the local label histogram (17 x u64; slot 16 is
+ *                       the bad-label flag).
+ *      all-gather tau, take the max over ranks: no row scoring below it can rank globally;
+ *      all-reduce(sum) the label histograms; all-reduce(max) the flags.
+ *   2. dvl_shard_trim   cnt[q] = local entries with score >= tau_bound[q].
+ *      all-reduce(max) of max_q cnt[q] gives the common packed length `len`.
+ *   3. dvl_shard_pack   out [q][len] = first cnt[q] entries, padded with ~0.
+ *      all-gather the packed lists into [world][q][len].
+ *   4. dvl_merge_topk   for queries [q0, q0+qn): deterministic merge of the world lists (a u64
+ *                       entry is key<<32 | global index<<4 | label, so the merge is a sort of
+ *                       integers), m_q with boundary ties, MaxSkew + NDKL against the GLOBAL
+ *                       label histogram.  out_flags[q] != 0: tie run too long, re-rank that query
+ *                       with dvl_similarity + dvl_rank_and_score.
+ *      all-gather the per-query results;  5. dvl_mean gives the four means (same reduction
+ *      tree as the single-GPU path, so the numbers are bit-identical to it).
+ */
+DVL_API int dvl_shard_topk(dvl_ctx* ctx, const void* gallery, int gallery_dtype, const void* queries, int query_dtype,
+                           const uint8_t* labels, int64_t n_local, int64_t index_base, int32_t d, int32_t q,
+                           int32_t n_classes, int64_t top_n, int precision, uint32_t flags,
+                           float* out_tau /* dev [q] */, uint32_t* out_flags /* dev [q] */,
+                           unsigned long long* out_class_counts /* dev [17] */, int32_t* out_list_cap /* host */,
+                           void* stream);
+DVL_API int dvl_shard_trim(dvl_ctx* ctx, const float* tau_bound /* dev [q] */, int32_t q, int32_t* out_cnt /* dev [q] */,
+                           void* stream);
+DVL_API int dvl_shard_pack(dvl_ctx* ctx, const int32_t* cnt /* dev [q] */, int32_t q, int64_t len,
+                           unsigned long long* out /* dev [q][len] */, void* stream);
+DVL_API int dvl_merge_topk(dvl_ctx* ctx, const unsigned long long* gathered /* dev [world][q_total][len] */,
+                           int32_t world, int32_t q_total, int64_t len, int32_t q0, int32_t qn, int64_t n_global,
+                           const unsigned long long* class_counts_global /* dev [16] */, int32_t n_classes,
+                           int64_t top_n, double* out_per_query /* dev [qn][4] */, int32_t* out_ranked_len /* dev [qn] */,
+                           int32_t* out_ranked_idx /* dev [qn][ranked_cap] or NULL */, int64_t ranked_cap,
+                           uint32_t* out_flags /* dev [qn] */, void* stream);
+/* a7: mean over queries of a device [q][4] array into host out_mean4 (fixed reduction tree). */
+DVL_API int dvl_mean(dvl_ctx* ctx, const double* per_query, int32_t q, double* out_mean4, void* stream);
 
 #ifdef __cplusplus
 }
