@@ -108,9 +108,19 @@ def make_workload(name: str, device: str, rank: int = 0):
     return w, synthetic.BASELINE_CONFIGS[name]["precision"]
 
 
-def workload_description(name, w, precision, world):
+def workload_description(name, w, precision, world, gallery_sharded=False, n_global=None):
     n, d = w.gallery.shape
     q = w.queries.shape[0]
+    if gallery_sharded:
+        return {
+            "workload": f"{name}: {n_global}x{d} gallery sharded over {world} GPUs ({n} rows each) x {q} queries, "
+                        f"C={w.n_classes}, top_n={w.topn}, {precision} similarity",
+            "n_gallery": n_global, "depth": d, "n_queries": q, "n_classes": w.n_classes, "top_n": w.topn,
+            "precision": precision,
+            "l2_policy": f"inputs larger than L2 ({n * d * 4 / 1e6:.0f} MB gallery shard per GPU vs 126 MB L2); no explicit flush",
+            "parallelism": f"gallery-sharded x{world}: NCCL all-reduce of thresholds/histograms + all-gather of "
+                           "per-shard top-k lists, deterministic merge",
+        }
     return {
         "workload": f"{name}: {n}x{d} gallery x {q} queries, C={w.n_classes}, top_n="
                     f"{'N (measure_bias default)' if w.topn == 1.0 else w.topn}, {precision} similarity"
@@ -211,7 +221,8 @@ def run_ours(args):
 
     peaks = load_peaks()
     w, precision = make_workload(args.workload, dev, rank)
-    if world > 1 and args.workload != "cfg4shard":
+    gallery_sharded = world > 1 and args.workload in ("cfg3", "cfg5", "cfg4shard")
+    if world > 1 and not gallery_sharded:
         # query sharding: same gallery on every rank, a different slice of a world-times larger query set
         from debias_vision_lang_b200 import synthetic
         cfg = synthetic.BASELINE_CONFIGS[args.workload]
@@ -223,9 +234,31 @@ def run_ours(args):
     prec = _capi.PRECISION_FP32 if precision == "fp32" else _capi.PRECISION_BF16
     lab = torch.from_numpy(w.labels.astype(np.uint8)).to(dev)
     ctx = _capi.context(local_rank)
+    n_global = n
+    if gallery_sharded:
+        from debias_vision_lang_b200 import sharded
+        comm = sharded.TorchDistComm()
+        opts = {"precision": precision}
+        if args.workload == "cfg4shard":
+            # weak scaling: every rank generated its own 1.25 M-row shard of the 10 M-row gallery;
+            # the queries must be the same everywhere
+            dist.broadcast(w.queries, src=0)
+            n_global, index_base = n * world, n * rank
+            g_local, l_local = w.gallery, lab
+        else:
+            # strong scaling: a fixed gallery split into contiguous row blocks
+            lo, hi = sharded.shard_bounds(n, world, rank)
+            g_local, l_local, index_base = w.gallery[lo:hi].contiguous(), lab[lo:hi].contiguous(), lo
+            w.gallery = g_local
+            torch.cuda.empty_cache()
 
-    def step():
-        return ctx.eval_ranking(w.gallery, w.queries, lab, w.n_classes, top_n, prec)["mean"]
+        def step():
+            r = sharded.evaluate_sharded(ctx, comm, g_local, w.queries, l_local, index_base, n_global, w.n_classes,
+                                         top_n, opts)
+            return [r["maxskew"]["eq_opp"], r["maxskew"]["dem_par"], r["ndkl"]["eq_opp"], r["ndkl"]["dem_par"]]
+    else:
+        def step():
+            return ctx.eval_ranking(w.gallery, w.queries, lab, w.n_classes, top_n, prec)["mean"]
 
     for _ in range(max(args.warmup, 3)):
         result = step()
@@ -251,30 +284,57 @@ def run_ours(args):
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     elapsed_ms = float(t.item())
-    pairs_per_step = n * q * world
+    if gallery_sharded:
+        pairs_per_step = n_global * q          # one ranked evaluation of the whole sharded gallery
+    else:
+        pairs_per_step = n * q * world         # every rank evaluates its own queries
     value = pairs_per_step * args.steps / (elapsed_ms * 1e-3)
 
     # ---- end to end through the C ABI with pinned host buffers ----
-    g_host = w.gallery.detach().cpu().pin_memory()
+    if gallery_sharded:
+        # the sharded path's inputs are produced on each GPU by the encoders (embedding hand-off);
+        # its end-to-end number is the timed step itself plus the H2D of the local shard
+        g_host = g_local.detach().cpu().pin_memory()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        e0.record()
+        for _ in range(args.steps):
+            g_dev = g_host.to(dev, non_blocking=True)
+            r = sharded.evaluate_sharded(ctx, comm, g_dev, w.queries, l_local, index_base, n_global, w.n_classes,
+                                         top_n, opts)
+        e1.record()
+        barrier()
+        t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_ms_sharded = float(t.item())
+        h2d_sharded = int(g_host.numel() * 4) * world
+        del g_host
+    g_host = (w.gallery if not gallery_sharded else w.gallery[:1]).detach().cpu().pin_memory()
     t_host = w.queries.detach().cpu().pin_memory()
     l_host = torch.from_numpy(w.labels.astype(np.uint8)).pin_memory()
     g_np, t_np, l_np = g_host.numpy(), t_host.numpy(), l_host.numpy()
-    for _ in range(2):
-        e2e_result = ctx.eval_ranking_host(g_np, t_np, l_np, w.n_classes, top_n, prec)
-    barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(args.steps):
-        e2e_result = ctx.eval_ranking_host(g_np, t_np, l_np, w.n_classes, top_n, prec)
-    e1.record()
-    barrier()
-    e2e_ms = e0.elapsed_time(e1)
-    t = torch.tensor([e2e_ms], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_ms = float(t.item())
+    if not gallery_sharded:
+        for _ in range(2):
+            e2e_result = ctx.eval_ranking_host(g_np, t_np, l_np[:n], w.n_classes, top_n, prec)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(args.steps):
+            e2e_result = ctx.eval_ranking_host(g_np, t_np, l_np[:n], w.n_classes, top_n, prec)
+        e1.record()
+        barrier()
+        e2e_ms = e0.elapsed_time(e1)
+        t = torch.tensor([e2e_ms], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_ms = float(t.item())
+        assert max(abs(a - b) for a, b in zip(e2e_result, result)) == 0.0, "host and device entry points disagree"
+        h2d_bytes = int(g_np.nbytes + t_np.nbytes + l_np.nbytes) * world
+        e2e_api = "dvl_eval_ranking_host (C ABI, pinned host buffers)"
+    else:
+        e2e_ms, h2d_bytes = e2e_ms_sharded, h2d_sharded
+        e2e_api = "sharded.evaluate_sharded after an H2D copy of the local gallery shard from pinned memory"
     e2e_value = pairs_per_step * args.steps / (e2e_ms * 1e-3)
-    assert max(abs(a - b) for a, b in zip(e2e_result, result)) == 0.0, "host and device entry points disagree"
 
     if rank != 0:
         if world > 1:
@@ -285,7 +345,7 @@ def run_ours(args):
     stage_ms = {k: v[0] / args.steps for k, v in profile.items()}
     stage_launches = {k: v[1] // args.steps for k, v in profile.items()}
     dominant = max(stage_ms, key=lambda k: stage_ms[k])
-    pairs_rank = n * q
+    pairs_rank = w.gallery.shape[0] * q
     if dominant == "gemm":
         terms = 6 if precision == "fp32" else 1
         flops = 2.0 * pairs_rank * d                       # algorithmic: 2*D flop per pair
@@ -328,16 +388,15 @@ def run_ours(args):
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f32" if precision == "fp32" else "bf16",
+        "scaling": "strong" if (gallery_sharded and args.workload != "cfg4shard") else "weak", "vs_baseline": None,
+        "dtype": "f32" if precision == "fp32" else "bf16",
         "data": "synthetic (seeded CLIP-like embeddings and labels; no FairFace/CLIP weights offline)",
-        "config": workload_description(args.workload, w, precision, world),
+        "config": workload_description(args.workload, w, precision, world, gallery_sharded, n_global),
         "roofline": roof,
         "stage_ms": stage_ms, "stage_launches": stage_launches,
         "cpu_baseline": cpu,
         "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_ms / args.steps,
-                "h2d_bytes_per_step": int(g_np.nbytes + t_np.nbytes + l_np.nbytes) * world,
-                "d2h_bytes_per_step": 32 * world,
-                "api": "dvl_eval_ranking_host (C ABI, pinned host buffers)"},
+                "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 32 * world, "api": e2e_api},
         "gpu_launches": int(launches),
         "clocks": clocks,
         "result": {"maxskew_eq_opp": result[0], "maxskew_dem_par": result[1], "ndkl_eq_opp": result[2],
