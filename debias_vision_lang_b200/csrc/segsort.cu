@@ -89,66 +89,128 @@ __global__ void __launch_bounds__(kRadix) seg_scan_kernel(uint32_t* __restrict__
   }
 }
 
-// pass step 3: stable scatter of one tile
+// pass step 3: stable scatter of one tile.
+//   phase 0  all 16 key (and payload) loads of a thread are issued before anything waits on them
+//   phase 1  warp-synchronous stable ranking: match.any groups equal digits, the lowest lane of a
+//            group reserves the group's slots in the warp's digit counter
+//   phase 2  digit totals -> exclusive bases (inside the tile, and in the output segment)
+//   phase 3  keys and payloads are placed at their tile-sorted position in shared memory
+//   phase 4  the tile is written out in sorted order: each digit run is a contiguous stretch of the
+//            output, so neighbouring threads store neighbouring addresses
 template <bool kFirst, bool kHasIdx>
-__global__ void __launch_bounds__(kSortThreads, 4)
+__global__ void __launch_bounds__(kSortThreads, 3)
 tile_scatter_kernel(const uint32_t* __restrict__ keys_in, const uint8_t* __restrict__ labs_in,
                     const int32_t* __restrict__ idx_in, const uint8_t* __restrict__ gallery_labels,
                     uint32_t* __restrict__ keys_out, uint8_t* __restrict__ labs_out, int32_t* __restrict__ idx_out,
                     int64_t ldk, int64_t n, int shift, int tiles, const uint32_t* __restrict__ tile_offs) {
-  __shared__ uint32_t cnt[kWarps][kRadix];   // per-warp running digit counts, then bases
+  __shared__ uint32_t cnt[kWarps][kRadix];      // per-warp digit counts, then exclusive bases over warps
+  __shared__ uint32_t dig_base[kRadix];         // first tile-sorted position of each digit
+  __shared__ uint32_t out_off[kRadix];          // output position of a digit run minus dig_base
+  __shared__ uint32_t warp_tot[kWarps];
+  __shared__ uint32_t s_keys[kTile];
+  __shared__ uint8_t s_labs[kTile];
+  __shared__ int32_t s_idx[kHasIdx ? kTile : 1];
   const int q = blockIdx.y;
   const int t = blockIdx.x;
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const uint32_t lt_mask = (1u << lane) - 1u;
   for (int i = threadIdx.x; i < kWarps * kRadix; i += kSortThreads) (&cnt[0][0])[i] = 0;
-  __syncthreads();
 
   const int64_t seg_off = (int64_t)q * ldk;
   // warp-striped: warp w owns keys [w*512, w*512+512) of the tile, 16 rounds of 32 consecutive keys
   const int64_t warp_base = (int64_t)t * kTile + warp * (kItems * 32);
   uint32_t key[kItems];
-  uint16_t rank[kItems];
+  uint32_t lab4[kItems / 4];                    // four labels per register
+  int32_t idx[kHasIdx ? kItems : 1];
+#pragma unroll
+  for (int r = 0; r < kItems / 4; ++r) lab4[r] = 0u;
 #pragma unroll
   for (int r = 0; r < kItems; ++r) {
     const int64_t pos = warp_base + r * 32 + lane;
     const bool ok = pos < n;
     key[r] = ok ? __ldg(keys_in + seg_off + pos) : 0xFFFFFFFFu;
-    const uint32_t digit = ok ? ((key[r] >> shift) & 0xFFu) : 256u;
-    const uint32_t peers = __match_any_sync(0xffffffffu, digit);
-    const int leader = __ffs(peers) - 1;
-    uint32_t before = 0;
-    if (ok && lane == leader) {
-      before = cnt[warp][digit];
-      cnt[warp][digit] = before + __popc(peers);
+    const uint32_t l = ok ? (uint32_t)(kFirst ? __ldg(gallery_labels + pos) : __ldg(labs_in + seg_off + pos)) : 0u;
+    lab4[r >> 2] |= l << (8 * (r & 3));
+    if (kHasIdx) idx[r] = ok ? (kFirst ? (int32_t)pos : __ldg(idx_in + seg_off + pos)) : 0;
+  }
+  __syncthreads();
+
+  uint32_t rank2[kItems / 2];                   // two 16-bit ranks per register
+#pragma unroll
+  for (int r = 0; r < kItems / 2; ++r) rank2[r] = 0u;
+  // Lanes holding the same digit: eight ballots (one per digit bit) ANDed together -- the MATCH.ANY
+  // instruction computes the same mask but its latency/throughput made it the kernel's bottleneck
+  // (ncu: 59 % of stall samples on its consumers).  Lanes past the end of the segment vote as their own
+  // group (digit bit 8).
+#pragma unroll
+  for (int r = 0; r < kItems; ++r) {
+    const bool ok = warp_base + r * 32 + lane < n;
+    const uint32_t digit = (key[r] >> shift) & 0xFFu;
+    uint32_t peers = __ballot_sync(0xffffffffu, ok);
+    if (!ok) peers = ~peers;
+#pragma unroll
+    for (int b = 0; b < 8; ++b) {
+      const uint32_t vote = __ballot_sync(0xffffffffu, (digit >> b) & 1u);
+      peers &= ((digit >> b) & 1u) ? vote : ~vote;
     }
-    before = __shfl_sync(0xffffffffu, before, leader);
-    rank[r] = (uint16_t)(before + __popc(peers & lt_mask));
+    uint32_t before = 0;
+    if (ok) before = cnt[warp][digit];            // every lane of the group reads the same counter ...
+    __syncwarp();
+    if (ok && (peers & lt_mask) == 0u) cnt[warp][digit] = before + __popc(peers);   // ... its lowest lane bumps it
+    rank2[r >> 1] |= (before + __popc(peers & lt_mask)) << (16 * (r & 1));
     __syncwarp();
   }
   __syncthreads();
-  // digit bases: global offset of this tile's digit run + keys of the same digit in lower warps
   {
+    // thread d: exclusive prefix of digit d over the warps, and the digit's total
     const int d = threadIdx.x;
-    uint32_t run = tile_offs[((int64_t)q * tiles + t) * kRadix + d];
+    uint32_t run = 0;
 #pragma unroll
     for (int w = 0; w < kWarps; ++w) {
       const uint32_t c = cnt[w][d];
       cnt[w][d] = run;
       run += c;
     }
+    // exclusive scan of the 256 totals
+    uint32_t incl = run;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+      const uint32_t o = __shfl_up_sync(0xffffffffu, incl, off);
+      if (lane >= off) incl += o;
+    }
+    if (lane == 31) warp_tot[warp] = incl;
+    __syncthreads();
+    uint32_t base = 0;
+#pragma unroll
+    for (int w = 0; w < kWarps; ++w) base += (w < warp) ? warp_tot[w] : 0u;
+    const uint32_t excl = base + incl - run;
+    dig_base[d] = excl;
+    out_off[d] = tile_offs[((int64_t)q * tiles + t) * kRadix + d] - excl;
   }
   __syncthreads();
 #pragma unroll
   for (int r = 0; r < kItems; ++r) {
-    const int64_t pos = warp_base + r * 32 + lane;
-    if (pos < n) {
+    if (warp_base + r * 32 + lane < n) {
       const uint32_t digit = (key[r] >> shift) & 0xFFu;
-      const int64_t dst = seg_off + cnt[warp][digit] + rank[r];
-      keys_out[dst] = key[r];
-      labs_out[dst] = kFirst ? __ldg(gallery_labels + pos) : __ldg(labs_in + seg_off + pos);
-      if (kHasIdx) idx_out[dst] = kFirst ? (int32_t)pos : __ldg(idx_in + seg_off + pos);
+      const uint32_t p = dig_base[digit] + cnt[warp][digit] + ((rank2[r >> 1] >> (16 * (r & 1))) & 0xFFFFu);
+      s_keys[p] = key[r];
+      s_labs[p] = (uint8_t)(lab4[r >> 2] >> (8 * (r & 3)));
+      if (kHasIdx) s_idx[p] = idx[r];
+    }
+  }
+  __syncthreads();
+  const int64_t left = n - (int64_t)t * kTile;
+  const int count = left < kTile ? (int)left : kTile;
+#pragma unroll
+  for (int r = 0; r < kItems; ++r) {
+    const int p = r * kSortThreads + threadIdx.x;
+    if (p < count) {
+      const uint32_t k = s_keys[p];
+      const int64_t dst = seg_off + out_off[(k >> shift) & 0xFFu] + p;
+      keys_out[dst] = k;
+      labs_out[dst] = s_labs[p];
+      if (kHasIdx) idx_out[dst] = s_idx[p];
     }
   }
 }
