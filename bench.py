@@ -116,7 +116,7 @@ def workload_description(name, w, precision, world, gallery_sharded=False, n_glo
             "workload": f"{name}: {n_global}x{d} gallery sharded over {world} GPUs ({n} rows each) x {q} queries, "
                         f"C={w.n_classes}, top_n={w.topn}, {precision} similarity",
             "n_gallery": n_global, "depth": d, "n_queries": q, "n_classes": w.n_classes, "top_n": w.topn,
-            "precision": precision,
+            "precision": precision, "input_dtype": str(w.gallery.dtype).replace("torch.", ""),
             "l2_policy": f"inputs larger than L2 ({n * d * 4 / 1e6:.0f} MB gallery shard per GPU vs 126 MB L2); no explicit flush",
             "parallelism": f"gallery-sharded x{world}: NCCL all-reduce of thresholds/histograms + all-gather of "
                            "per-shard top-k lists, deterministic merge",
@@ -127,6 +127,7 @@ def workload_description(name, w, precision, world, gallery_sharded=False, n_glo
                     + (f"; {world} GPUs, each ranks its own {q} queries over the full gallery" if world > 1 else ""),
         "n_gallery": n, "depth": d, "n_queries_per_gpu": q, "n_classes": w.n_classes,
         "top_n": n if w.topn == 1.0 else w.topn, "precision": precision,
+        "input_dtype": str(w.gallery.dtype).replace("torch.", ""),
         "l2_policy": f"inputs larger than L2 ({n * d * 4 / 1e6:.0f} MB fp32 gallery + {q * n * 4 / 1e6:.0f} MB of keys per pass vs 126 MB L2); no explicit flush",
         "parallelism": "1 GPU" if world == 1 else f"query-sharded x{world} (no data-path collective)",
     }
@@ -235,6 +236,12 @@ def run_ours(args):
     lab = torch.from_numpy(w.labels.astype(np.uint8)).to(dev)
     ctx = _capi.context(local_rank)
     n_global = n
+    if args.input_dtype == "bf16":
+        if precision != "bf16":
+            raise SystemExit("--input-dtype bf16 needs a bf16-similarity workload (cfg3, cfg4shard)")
+        w.gallery = w.gallery.bfloat16()
+        w.queries = w.queries.bfloat16()
+        torch.cuda.empty_cache()
     if gallery_sharded:
         from debias_vision_lang_b200 import sharded
         comm = sharded.TorchDistComm()
@@ -309,8 +316,8 @@ def run_ours(args):
         e2e_ms_sharded = float(t.item())
         h2d_sharded = int(g_host.numel() * 4) * world
         del g_host
-    g_host = (w.gallery if not gallery_sharded else w.gallery[:1]).detach().cpu().pin_memory()
-    t_host = w.queries.detach().cpu().pin_memory()
+    g_host = (w.gallery if not gallery_sharded else w.gallery[:1]).detach().float().cpu().pin_memory()
+    t_host = w.queries.detach().float().cpu().pin_memory()
     l_host = torch.from_numpy(w.labels.astype(np.uint8)).pin_memory()
     g_np, t_np, l_np = g_host.numpy(), t_host.numpy(), l_host.numpy()
     if not gallery_sharded:
@@ -415,6 +422,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="cfg2", choices=["cfg1", "cfg2", "cfg3", "cfg5", "cfg4shard"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--input-dtype", default="fp32", choices=["fp32", "bf16"],
+                    help="dtype of the resident embeddings handed to the path (bf16 needs a bf16 workload: the "
+                         "library then reads them in place, without its conversion pass)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -113,8 +113,16 @@ int prepare_operands(Ctx* c, const void* gallery, int gdt, const void* queries, 
                      int precision, uint32_t flags, Operands* op, cudaStream_t st) {
   const int planes = (precision == DVL_PRECISION_FP32) ? 3 : 1;
   const int dp = (int)round_up(d, 8);
-  DVL_TRY(ensure(c, c->gal_planes, (size_t)planes * n * dp * 2));
-  DVL_TRY(ensure(c, c->qry_planes, (size_t)planes * q * dp * 2));
+  // bf16 embeddings in bf16 mode are already the operand TMA wants (K-major rows, 16-byte aligned
+  // pitch): use the caller's memory in place and skip the conversion pass
+  auto direct = [&](const void* ptr, int dtype, bool need_norm) {
+    return precision == DVL_PRECISION_BF16 && dtype == DVL_BF16 && !need_norm && d % 8 == 0 &&
+           (reinterpret_cast<uintptr_t>(ptr) & 15u) == 0;
+  };
+  const bool g_direct = direct(gallery, gdt, (flags & DVL_FLAG_NORMALIZE_GALLERY) != 0);
+  const bool q_direct = direct(queries, qdt, (flags & DVL_FLAG_NORMALIZE_QUERIES) != 0);
+  if (!g_direct) DVL_TRY(ensure(c, c->gal_planes, (size_t)planes * n * dp * 2));
+  if (!q_direct) DVL_TRY(ensure(c, c->qry_planes, (size_t)planes * q * dp * 2));
   float* gnorm = nullptr;
   float* qnorm = nullptr;
   if (flags & DVL_FLAG_NORMALIZE_GALLERY) {
@@ -126,10 +134,12 @@ int prepare_operands(Ctx* c, const void* gallery, int gdt, const void* queries, 
     qnorm = (float*)c->qry_inv_norm.ptr;
   }
   StageScope scope(c, DVL_STAGE_PREP, st);
-  DVL_TRY(launch_split_rows(c, gallery, gdt, n, d, dp, planes, (__nv_bfloat16*)c->gal_planes.ptr, gnorm, st));
-  DVL_TRY(launch_split_rows(c, queries, qdt, q, d, dp, planes, (__nv_bfloat16*)c->qry_planes.ptr, qnorm, st));
-  op->qry_planes = (const __nv_bfloat16*)c->qry_planes.ptr;
-  op->gal_planes = (const __nv_bfloat16*)c->gal_planes.ptr;
+  if (!g_direct)
+    DVL_TRY(launch_split_rows(c, gallery, gdt, n, d, dp, planes, (__nv_bfloat16*)c->gal_planes.ptr, gnorm, st));
+  if (!q_direct)
+    DVL_TRY(launch_split_rows(c, queries, qdt, q, d, dp, planes, (__nv_bfloat16*)c->qry_planes.ptr, qnorm, st));
+  op->qry_planes = q_direct ? (const __nv_bfloat16*)queries : (const __nv_bfloat16*)c->qry_planes.ptr;
+  op->gal_planes = g_direct ? (const __nv_bfloat16*)gallery : (const __nv_bfloat16*)c->gal_planes.ptr;
   op->planes = planes;
   op->dp = dp;
   op->qry_scale = qnorm;
@@ -320,6 +330,8 @@ int stream_topk(Ctx* c, const Operands& op, const uint8_t* labels, int64_t n, in
   sel.ldl = ldl;
   sel.avail = (int32_t*)c->topk_avail.ptr;
   sel.q_count = q;
+  sel.labels = labels;
+  sel.index_base = index_base;
 
   int64_t row = 0;
   int64_t chunk = plan.chunk0;

@@ -164,6 +164,8 @@ struct SelectArgs {
   int32_t* avail = nullptr;
   int q_offset = 0;
   int q_count = 0;
+  const uint8_t* labels = nullptr;   // local lists only
+  int64_t index_base = 0;
 };
 int launch_topk_reset(Ctx* c, uint32_t* cnt, float* tau, uint32_t* flags, int q, uint32_t cnt_value, bool reset_all,
                       cudaStream_t st);

@@ -78,9 +78,10 @@ struct KernelParams {
   int64_t index_base;          // global index of local row 0
 };
 
-__device__ __forceinline__ unsigned long long make_entry(float s, int64_t gidx, uint32_t label) {
-  return (static_cast<unsigned long long>(score_to_key(s)) << 32) | (static_cast<unsigned long long>(gidx) << 4) |
-         static_cast<unsigned long long>(label & 0xFu);
+// The label nibble is filled in by the final select pass (topk.cu): looking it up here would put a
+// dependent global load on the epilogue's slow path.
+__device__ __forceinline__ unsigned long long make_entry(float s, int64_t gidx) {
+  return (static_cast<unsigned long long>(score_to_key(s)) << 32) | (static_cast<unsigned long long>(gidx) << 4);
 }
 
 __global__ void __launch_bounds__(kNumThreads, 1)
@@ -198,13 +199,54 @@ sim_gemm_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
       mbar_wait(tfull_bar(as), aphase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + (uint32_t)(as * BN) + ((uint32_t)(quarter * 32) << 16);
+      const bool scaled = p.qry_scale != nullptr || p.gal_scale != nullptr;
+      if (p.mode == kGemmFilter) {
+        // ---- streaming top-k: one compare per similarity against tau.  Survivors (rare once tau has
+        // tightened) are appended to the query's list: ONE atomic per 32-column chunk reserves their
+        // slots, the values go through a 32-word shared-memory row so that the bit loop can index them.
+        uint32_t* mine = epi_scratch + (threadIdx.x - 64) * 33;
+        unsigned long long* list = p.cand + (int64_t)qrow * p.cap;
+#pragma unroll 1
+        for (int chunk = 0; chunk < BN / 32; ++chunk) {
+          uint32_t v[32];
+          tmem_ld_32x32(taddr + (uint32_t)(chunk * 32), v);
+          tmem_ld_wait();
+          const int64_t col0 = p.row0 + gb * BN + chunk * 32;
+          if (scaled) {                            // uniform branch, outside the element loop
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              float s = __uint_as_float(v[j]) * qs;
+              if (p.gal_scale != nullptr) s *= (col0 + j < p.n) ? __ldg(p.gal_scale + col0 + j) : 0.f;
+              v[j] = __float_as_uint(s);
+            }
+          }
+          uint32_t mask = 0;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) mask |= (__uint_as_float(v[j]) >= tau ? 1u : 0u) << j;
+          const int64_t left = p.n - col0;
+          if (left < 32) mask &= (left <= 0) ? 0u : ((1u << left) - 1u);
+          if (mask != 0u) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) mine[j] = v[j];
+            uint32_t slot = atomicAdd(p.cand_cnt + qrow, (uint32_t)__popc(mask));
+            while (mask != 0u) {
+              const int j = __ffs(mask) - 1;
+              mask &= mask - 1u;
+              const int64_t col = col0 + j;
+              if ((int64_t)slot < p.cap)
+                list[slot] = make_entry(__uint_as_float(mine[j]), p.index_base + col);
+              ++slot;
+            }
+          }
+        }
+      } else {
 #pragma unroll 1
       for (int chunk = 0; chunk < BN / 32; ++chunk) {
         uint32_t v[32];
         tmem_ld_32x32(taddr + (uint32_t)(chunk * 32), v);
         tmem_ld_wait();
         const int64_t col0 = p.row0 + gb * BN + chunk * 32;
-        if (p.qry_scale != nullptr || p.gal_scale != nullptr) {
+        if (scaled) {
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
             float s = __uint_as_float(v[j]) * qs;
@@ -227,48 +269,22 @@ sim_gemm_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
                              score_to_key(__uint_as_float(v[j + 2])), score_to_key(__uint_as_float(v[j + 3])));
             }
           }
-        } else if (p.mode == kGemmSeed) {
-          // first chunk: every row is a candidate, position = column (no atomics, 256 B per thread)
+        } else {
+          // SEED, first chunk: every row is a candidate, position = column (no atomics, 256 B per thread)
           if (row_ok && col0 < p.n) {
             unsigned long long* dst = p.cand + (int64_t)qrow * p.cap + (col0 - p.row0);
-            const uint4 l0 = __ldg(reinterpret_cast<const uint4*>(p.labels + col0));
-            const uint4 l1 = __ldg(reinterpret_cast<const uint4*>(p.labels + col0) + 1);
-            const uint32_t lw[8] = {l0.x, l0.y, l0.z, l0.w, l1.x, l1.y, l1.z, l1.w};
 #pragma unroll
             for (int j = 0; j < 32; j += 2) {
               // rows past the end of the gallery become NaN-keyed entries that are never ranked
-              const unsigned long long e0 = (col0 + j < p.n)
-                  ? make_entry(__uint_as_float(v[j]), p.index_base + col0 + j, (lw[j >> 2] >> (8 * (j & 3))) & 0xFFu)
-                  : ~0ull;
-              const unsigned long long e1 = (col0 + j + 1 < p.n)
-                  ? make_entry(__uint_as_float(v[j + 1]), p.index_base + col0 + j + 1,
-                               (lw[(j + 1) >> 2] >> (8 * ((j + 1) & 3))) & 0xFFu)
-                  : ~0ull;
+              const unsigned long long e0 =
+                  (col0 + j < p.n) ? make_entry(__uint_as_float(v[j]), p.index_base + col0 + j) : ~0ull;
+              const unsigned long long e1 =
+                  (col0 + j + 1 < p.n) ? make_entry(__uint_as_float(v[j + 1]), p.index_base + col0 + j + 1) : ~0ull;
               st_global_v4(dst + j, (uint32_t)e0, (uint32_t)(e0 >> 32), (uint32_t)e1, (uint32_t)(e1 >> 32));
             }
           }
-        } else {
-          // streaming top-k: one compare per similarity; survivors are rare once tau has tightened
-          uint32_t mask = 0;
-#pragma unroll
-          for (int j = 0; j < 32; ++j) mask |= (__uint_as_float(v[j]) >= tau ? 1u : 0u) << j;
-          const int64_t left = p.n - col0;
-          if (left < 32) mask &= (left <= 0) ? 0u : ((1u << left) - 1u);
-          if (mask != 0u) {
-            uint32_t* mine = epi_scratch + (threadIdx.x - 64) * 33;
-#pragma unroll
-            for (int j = 0; j < 32; ++j) mine[j] = v[j];
-            while (mask != 0u) {
-              const int j = __ffs(mask) - 1;
-              mask &= mask - 1u;
-              const int64_t col = col0 + j;
-              const uint32_t pos = atomicAdd(p.cand_cnt + qrow, 1u);
-              if ((int64_t)pos < p.cap)
-                p.cand[(int64_t)qrow * p.cap + pos] =
-                    make_entry(__uint_as_float(mine[j]), p.index_base + col, __ldg(p.labels + col));
-            }
-          }
         }
+      }
       }
       tc_fence_before();
       mbar_arrive(tempty_bar(as));
@@ -315,11 +331,11 @@ int launch_sim_gemm(Ctx* c, const GemmArgs& a, cudaStream_t st) {
   if (a.n <= 0 || a.q <= 0 || a.d <= 0) return set_error(c, DVL_ERR_INVALID, "empty similarity problem");
   if (a.row0 < 0 || a.row0 % BN != 0 || a.row1 <= a.row0 || a.row1 > a.n)
     return set_error(c, DVL_ERR_INVALID, "bad gallery row range [%lld, %lld)", (long long)a.row0, (long long)a.row1);
-  if (a.mode != kGemmStore && (a.cand == nullptr || a.cand_cnt == nullptr || a.labels == nullptr || a.cap < 1))
+  if (a.mode != kGemmStore && (a.cand == nullptr || a.cand_cnt == nullptr || a.cap < 1))
     return set_error(c, DVL_ERR_INVALID, "streaming top-k launch without candidate buffers");
   if (a.mode == kGemmFilter && a.tau == nullptr) return set_error(c, DVL_ERR_INVALID, "filter launch without thresholds");
-  if (a.mode == kGemmSeed && (a.row1 - a.row0 > a.cap || (reinterpret_cast<uintptr_t>(a.labels) & 15) != 0))
-    return set_error(c, DVL_ERR_INVALID, "seed chunk larger than the candidate capacity or unaligned labels");
+  if (a.mode == kGemmSeed && a.row1 - a.row0 > a.cap)
+    return set_error(c, DVL_ERR_INVALID, "seed chunk larger than the candidate capacity");
   if (a.index_base + a.n > (1ll << 28)) return set_error(c, DVL_ERR_UNSUPPORTED, "global gallery index needs more than 28 bits");
   if (a.n > 0x7FFFFF00ll) return set_error(c, DVL_ERR_UNSUPPORTED, "gallery shard larger than 2^31 rows");
   CUtensorMap map_q, map_g;

@@ -49,6 +49,8 @@ struct SelectParams {
   int64_t idx_cap;
   int32_t* avail;           // [q] ranked rows m_q
   int q_offset;             // queries handled: blockIdx.x + q_offset
+  const uint8_t* labels;    // local lists: labels of this shard, filled into the entries on the final pass
+  int64_t index_base;       //              (global index of local row 0); null when entries carry labels
 };
 
 __device__ __forceinline__ unsigned long long load_entry(const SelectParams& p, int q, int64_t i) {
@@ -79,25 +81,57 @@ __global__ void __launch_bounds__(kSelThreads) select_kernel(const SelectParams 
   // ---- the k-th smallest key ----
   uint32_t kth = 0xFFFFFFFFu;
   if (n > p.k) {
+    // short lists (the usual case) are cached once as 32-bit keys in the shared-memory list buffer,
+    // so the four radix passes do not go back to L2
+    uint32_t* sm_keys = reinterpret_cast<uint32_t*>(sm_list);
+    const bool cached = n <= 2 * (int64_t)p.sort_cap;
+    if (cached)
+      for (int64_t i = tid; i < n; i += kSelThreads) sm_keys[i] = (uint32_t)(load_entry(p, q, i) >> 32);
     if (tid == 0) { sh_prefix = 0u; sh_remaining = (uint32_t)p.k; }
     uint32_t known_mask = 0u;
     for (int shift = 24; shift >= 0; shift -= 8) {
       hist[tid] = 0u;
       __syncthreads();
       const uint32_t prefix = sh_prefix;
-      for (int64_t i = tid; i < n; i += kSelThreads) {
-        const uint32_t key = (uint32_t)(load_entry(p, q, i) >> 32);
-        if ((key & known_mask) == prefix) atomicAdd(&hist[(key >> shift) & 0xFFu], 1u);
+      if (cached) {
+        for (int i = tid; i < (int)n; i += kSelThreads) {
+          const uint32_t key = sm_keys[i];
+          if ((key & known_mask) == prefix) atomicAdd(&hist[(key >> shift) & 0xFFu], 1u);
+        }
+      } else {
+        for (int64_t i = tid; i < n; i += kSelThreads) {
+          const uint32_t key = (uint32_t)(load_entry(p, q, i) >> 32);
+          if ((key & known_mask) == prefix) atomicAdd(&hist[(key >> shift) & 0xFFu], 1u);
+        }
       }
       __syncthreads();
-      if (tid == 0) {
-        uint32_t remaining = sh_remaining, d = 0;
-        for (; d < 255u; ++d) {
-          if (hist[d] >= remaining) break;
-          remaining -= hist[d];
+      if (tid < 32) {
+        // warp 0 finds the digit whose cumulative count crosses `remaining`: 8 bins per lane
+        const uint32_t remaining = sh_remaining;
+        uint32_t local[8];
+        uint32_t sum = 0;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          local[j] = hist[tid * 8 + j];
+          sum += local[j];
         }
-        sh_prefix = prefix | (d << shift);
-        sh_remaining = remaining;
+        uint32_t incl = sum;
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+          const uint32_t o = __shfl_up_sync(0xffffffffu, incl, off);
+          if (tid >= off) incl += o;
+        }
+        uint32_t before = incl - sum;             // entries in lower bins
+        if (before < remaining && remaining <= incl) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            if (before < remaining && remaining <= before + local[j]) {
+              sh_prefix = prefix | ((uint32_t)(tid * 8 + j) << shift);
+              sh_remaining = remaining - before;
+            }
+            before += local[j];
+          }
+        }
       }
       known_mask |= 0xFFu << shift;
       __syncthreads();
@@ -171,7 +205,8 @@ __global__ void __launch_bounds__(kSelThreads) select_kernel(const SelectParams 
                                                          : p.cand + (int64_t)q * p.row_stride;
   uint8_t* labs = p.labs + (int64_t)q * p.ldl;
   for (uint32_t i = tid; i < m; i += kSelThreads) {
-    const unsigned long long e = sm_list[i];
+    unsigned long long e = sm_list[i];
+    if (p.labels != nullptr) e |= (unsigned long long)(p.labels[(int64_t)((e >> 4) & 0x0FFFFFFFull) - p.index_base] & 0xFu);
     sorted[i] = e;
     labs[i] = (uint8_t)(e & 0xFull);
     if (p.idx_out != nullptr && (int64_t)i < p.idx_cap)
@@ -253,6 +288,8 @@ int launch_select(Ctx* c, const SelectArgs& a, cudaStream_t st) {
   p.idx_cap = a.idx_cap;
   p.avail = a.avail;
   p.q_offset = a.q_offset;
+  p.labels = a.labels;
+  p.index_base = a.index_base;
   const size_t smem = (size_t)a.sort_cap * sizeof(unsigned long long);
   if (smem > 48 * 1024 && !c->select_attr_set) {
     DVL_CUDA(c, cudaFuncSetAttribute(select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 16384 * 8));
