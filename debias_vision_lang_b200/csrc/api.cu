@@ -692,8 +692,7 @@ DVL_API int dvl_shard_topk(dvl_ctx* c, const void* gallery, int gdt, const void*
   DVL_CUDA(c, cudaMemcpyAsync(out_class_counts, c->class_counts.ptr, sizeof(unsigned long long) * (dvl::kMaxClasses + 1),
                               cudaMemcpyDeviceToDevice, st));
   if (out_list_cap != nullptr) *out_list_cap = plan.sort_cap;
-  DVL_CUDA(c, cudaStreamSynchronize(st));
-  return DVL_OK;
+  return DVL_OK;    // stream-ordered: the outputs are consumed by collectives enqueued after this call
 }
 
 DVL_API int dvl_shard_trim(dvl_ctx* c, const float* tau_bound, int32_t q, int32_t* out_cnt, void* stream) {
@@ -785,8 +784,7 @@ DVL_API int dvl_merge_topk(dvl_ctx* c, const unsigned long long* gathered, int32
     dvl::StageScope scope(c, DVL_STAGE_METRICS, st);
     DVL_TRY(dvl::launch_metrics(c, m, st));
   }
-  DVL_CUDA(c, cudaStreamSynchronize(st));
-  return DVL_OK;
+  return DVL_OK;    // stream-ordered, no host synchronisation
 }
 
 DVL_API int dvl_mean(dvl_ctx* c, const double* per_query, int32_t q, double* out_mean4, void* stream) {

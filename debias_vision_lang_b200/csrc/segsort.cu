@@ -20,7 +20,7 @@ constexpr int kSortThreads = 256;
 constexpr int kWarps = kSortThreads / 32;
 constexpr int kItems = 16;                       // keys per thread
 constexpr int kTile = kSortThreads * kItems;     // 4096 keys per CTA
-constexpr int kRadix = 256;
+constexpr int kMaxBits = 8;
 
 // ---------------------------------------------------------------------------------------
 // float scores -> ranking keys (stage entry point dvl_rank_and_score)
@@ -35,13 +35,16 @@ __global__ void __launch_bounds__(256) scores_to_keys_kernel(const float* __rest
 
 // ---------------------------------------------------------------------------------------
 // pass step 1: digit histogram of one tile
+template <int BITS>
 __global__ void __launch_bounds__(kSortThreads) tile_hist_kernel(const uint32_t* __restrict__ keys, int64_t ldk,
                                                                  int64_t n, int shift, int tiles,
                                                                  uint32_t* __restrict__ tile_hist) {
-  __shared__ uint32_t hist[kRadix];
+  constexpr int RADIX = 1 << BITS;
+  constexpr uint32_t MASK = RADIX - 1;
+  __shared__ uint32_t hist[RADIX];
   const int q = blockIdx.y;
   const int t = blockIdx.x;
-  hist[threadIdx.x] = 0;
+  for (int i = threadIdx.x; i < RADIX; i += kSortThreads) hist[i] = 0;
   __syncthreads();
   const uint32_t* seg = keys + (int64_t)q * ldk;
   const int64_t base = (int64_t)t * kTile;
@@ -50,72 +53,94 @@ __global__ void __launch_bounds__(kSortThreads) tile_hist_kernel(const uint32_t*
 #pragma unroll
     for (int r = 0; r < kItems / 4; ++r) {
       const uint4 v = __ldg(reinterpret_cast<const uint4*>(seg + base) + r * kSortThreads + threadIdx.x);
-      atomicAdd(&hist[(v.x >> shift) & 0xFF], 1u);
-      atomicAdd(&hist[(v.y >> shift) & 0xFF], 1u);
-      atomicAdd(&hist[(v.z >> shift) & 0xFF], 1u);
-      atomicAdd(&hist[(v.w >> shift) & 0xFF], 1u);
+      atomicAdd(&hist[(v.x >> shift) & MASK], 1u);
+      atomicAdd(&hist[(v.y >> shift) & MASK], 1u);
+      atomicAdd(&hist[(v.z >> shift) & MASK], 1u);
+      atomicAdd(&hist[(v.w >> shift) & MASK], 1u);
     }
   } else {
-    for (int64_t i = base + threadIdx.x; i < n; i += kSortThreads) atomicAdd(&hist[(__ldg(seg + i) >> shift) & 0xFF], 1u);
+    for (int64_t i = base + threadIdx.x; i < n; i += kSortThreads) atomicAdd(&hist[(__ldg(seg + i) >> shift) & MASK], 1u);
   }
   __syncthreads();
-  tile_hist[((int64_t)q * tiles + t) * kRadix + threadIdx.x] = hist[threadIdx.x];
+  uint32_t* out = tile_hist + ((int64_t)q * tiles + t) * RADIX;
+  for (int i = threadIdx.x; i < RADIX; i += kSortThreads) out[i] = hist[i];
 }
 
 // pass step 2: per segment, exclusive scan in (digit major, tile minor) order, in place
-__global__ void __launch_bounds__(kRadix) seg_scan_kernel(uint32_t* __restrict__ tile_hist, int tiles) {
-  __shared__ uint32_t warp_tot[kRadix / 32];
+template <int BITS>
+__global__ void __launch_bounds__(kSortThreads) seg_scan_kernel(uint32_t* __restrict__ tile_hist, int tiles) {
+  constexpr int RADIX = 1 << BITS;
+  constexpr int SLABS = RADIX / kSortThreads;     // digits d = slab*256 + tid
+  __shared__ uint32_t warp_tot[kWarps];
+  __shared__ uint32_t carry;
   const int q = blockIdx.x;
-  const int d = threadIdx.x;
-  uint32_t* h = tile_hist + (int64_t)q * tiles * kRadix;
-  uint32_t total = 0;
-  for (int t = 0; t < tiles; ++t) total += h[t * kRadix + d];
-  // exclusive scan of the 256 digit totals
-  uint32_t incl = total;
-#pragma unroll
-  for (int off = 1; off < 32; off <<= 1) {
-    const uint32_t o = __shfl_up_sync(0xffffffffu, incl, off);
-    if ((d & 31) >= off) incl += o;
-  }
-  if ((d & 31) == 31) warp_tot[d >> 5] = incl;
+  const int tid = threadIdx.x;
+  uint32_t* h = tile_hist + (int64_t)q * tiles * RADIX;
+  if (tid == 0) carry = 0;
   __syncthreads();
-  uint32_t warp_base = 0;
-  for (int w = 0; w < (d >> 5); ++w) warp_base += warp_tot[w];
-  uint32_t run = warp_base + incl - total;
-  for (int t = 0; t < tiles; ++t) {
-    const uint32_t c = h[t * kRadix + d];
-    h[t * kRadix + d] = run;
-    run += c;
+  for (int slab = 0; slab < SLABS; ++slab) {
+    const int d = slab * kSortThreads + tid;
+    uint32_t total = 0;
+    for (int t = 0; t < tiles; ++t) total += h[t * RADIX + d];
+    uint32_t incl = total;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+      const uint32_t o = __shfl_up_sync(0xffffffffu, incl, off);
+      if ((tid & 31) >= off) incl += o;
+    }
+    if ((tid & 31) == 31) warp_tot[tid >> 5] = incl;
+    __syncthreads();
+    uint32_t base = carry;
+    for (int w = 0; w < (tid >> 5); ++w) base += warp_tot[w];
+    uint32_t run = base + incl - total;
+    for (int t = 0; t < tiles; ++t) {
+      const uint32_t c = h[t * RADIX + d];
+      h[t * RADIX + d] = run;
+      run += c;
+    }
+    __syncthreads();
+    if (tid == kSortThreads - 1) carry = base + incl;
+    __syncthreads();
   }
 }
 
 // pass step 3: stable scatter of one tile.
 //   phase 0  all 16 key (and payload) loads of a thread are issued before anything waits on them
-//   phase 1  warp-synchronous stable ranking: match.any groups equal digits, the lowest lane of a
-//            group reserves the group's slots in the warp's digit counter
+//   phase 1  warp-synchronous stable ranking: BITS ballots group the lanes holding equal digits, the
+//            lowest lane of a group reserves the group's slots in the warp's digit counter
 //   phase 2  digit totals -> exclusive bases (inside the tile, and in the output segment)
 //   phase 3  keys and payloads are placed at their tile-sorted position in shared memory
 //   phase 4  the tile is written out in sorted order: each digit run is a contiguous stretch of the
 //            output, so neighbouring threads store neighbouring addresses
-template <bool kFirst, bool kHasIdx>
+template <int BITS, bool kHasIdx>
+constexpr size_t scatter_smem_bytes() {
+  return (size_t)kWarps * (1 << BITS) * 2 + (size_t)(1 << BITS) * 2 + (size_t)(1 << BITS) * 4 + kTile * 4 + kTile +
+         (kHasIdx ? kTile * 4 : 0) + 64;
+}
+
+template <int BITS, bool kFirst, bool kHasIdx>
 __global__ void __launch_bounds__(kSortThreads, 3)
 tile_scatter_kernel(const uint32_t* __restrict__ keys_in, const uint8_t* __restrict__ labs_in,
                     const int32_t* __restrict__ idx_in, const uint8_t* __restrict__ gallery_labels,
                     uint32_t* __restrict__ keys_out, uint8_t* __restrict__ labs_out, int32_t* __restrict__ idx_out,
                     int64_t ldk, int64_t n, int shift, int tiles, const uint32_t* __restrict__ tile_offs) {
-  __shared__ uint32_t cnt[kWarps][kRadix];      // per-warp digit counts, then exclusive bases over warps
-  __shared__ uint32_t dig_base[kRadix];         // first tile-sorted position of each digit
-  __shared__ uint32_t out_off[kRadix];          // output position of a digit run minus dig_base
+  constexpr int RADIX = 1 << BITS;
+  constexpr uint32_t MASK = RADIX - 1;
+  constexpr int DPT = RADIX / kSortThreads;      // digits per thread in phase 2
+  extern __shared__ __align__(16) uint8_t smem_dyn[];
+  uint32_t* out_off = reinterpret_cast<uint32_t*>(smem_dyn);              // [RADIX] output position of a run - dig_base
+  uint32_t* s_keys = out_off + RADIX;                                     // [kTile]
+  int32_t* s_idx = reinterpret_cast<int32_t*>(s_keys + kTile);            // [kTile] if kHasIdx
+  uint16_t* cnt = reinterpret_cast<uint16_t*>(s_idx + (kHasIdx ? kTile : 0));   // [kWarps][RADIX]
+  uint16_t* dig_base = cnt + kWarps * RADIX;                              // [RADIX] first tile position of a digit
+  uint8_t* s_labs = reinterpret_cast<uint8_t*>(dig_base + RADIX);         // [kTile]
   __shared__ uint32_t warp_tot[kWarps];
-  __shared__ uint32_t s_keys[kTile];
-  __shared__ uint8_t s_labs[kTile];
-  __shared__ int32_t s_idx[kHasIdx ? kTile : 1];
   const int q = blockIdx.y;
   const int t = blockIdx.x;
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const uint32_t lt_mask = (1u << lane) - 1u;
-  for (int i = threadIdx.x; i < kWarps * kRadix; i += kSortThreads) (&cnt[0][0])[i] = 0;
+  for (int i = threadIdx.x; i < kWarps * RADIX / 2; i += kSortThreads) reinterpret_cast<uint32_t*>(cnt)[i] = 0;
 
   const int64_t seg_off = (int64_t)q * ldk;
   // warp-striped: warp w owns keys [w*512, w*512+512) of the tile, 16 rounds of 32 consecutive keys
@@ -139,41 +164,48 @@ tile_scatter_kernel(const uint32_t* __restrict__ keys_in, const uint8_t* __restr
   uint32_t rank2[kItems / 2];                   // two 16-bit ranks per register
 #pragma unroll
   for (int r = 0; r < kItems / 2; ++r) rank2[r] = 0u;
-  // Lanes holding the same digit: eight ballots (one per digit bit) ANDed together -- the MATCH.ANY
-  // instruction computes the same mask but its latency/throughput made it the kernel's bottleneck
-  // (ncu: 59 % of stall samples on its consumers).  Lanes past the end of the segment vote as their own
-  // group (digit bit 8).
+  uint16_t* my_cnt = cnt + warp * RADIX;
+  // Lanes holding the same digit: BITS ballots (one per digit bit) ANDed together -- the MATCH.ANY
+  // instruction computes the same mask but its latency made it the kernel's bottleneck (ncu: 59 % of
+  // stall samples on its consumers).  Lanes past the end of the segment form their own group.
 #pragma unroll
   for (int r = 0; r < kItems; ++r) {
     const bool ok = warp_base + r * 32 + lane < n;
-    const uint32_t digit = (key[r] >> shift) & 0xFFu;
+    const uint32_t digit = (key[r] >> shift) & MASK;
     uint32_t peers = __ballot_sync(0xffffffffu, ok);
     if (!ok) peers = ~peers;
 #pragma unroll
-    for (int b = 0; b < 8; ++b) {
+    for (int b = 0; b < BITS; ++b) {
       const uint32_t vote = __ballot_sync(0xffffffffu, (digit >> b) & 1u);
       peers &= ((digit >> b) & 1u) ? vote : ~vote;
     }
     uint32_t before = 0;
-    if (ok) before = cnt[warp][digit];            // every lane of the group reads the same counter ...
+    if (ok) before = my_cnt[digit];               // every lane of the group reads the same counter ...
     __syncwarp();
-    if (ok && (peers & lt_mask) == 0u) cnt[warp][digit] = before + __popc(peers);   // ... its lowest lane bumps it
+    if (ok && (peers & lt_mask) == 0u) my_cnt[digit] = (uint16_t)(before + __popc(peers));   // ... its lowest lane bumps it
     rank2[r >> 1] |= (before + __popc(peers & lt_mask)) << (16 * (r & 1));
     __syncwarp();
   }
   __syncthreads();
   {
-    // thread d: exclusive prefix of digit d over the warps, and the digit's total
-    const int d = threadIdx.x;
-    uint32_t run = 0;
+    // thread owns DPT consecutive digits: exclusive prefix over the warps, digit totals, then the
+    // exclusive scan of the totals across the block
+    uint32_t tot[DPT];
+    uint32_t sum = 0;
 #pragma unroll
-    for (int w = 0; w < kWarps; ++w) {
-      const uint32_t c = cnt[w][d];
-      cnt[w][d] = run;
-      run += c;
+    for (int j = 0; j < DPT; ++j) {
+      const int d = threadIdx.x * DPT + j;
+      uint32_t run = 0;
+#pragma unroll
+      for (int w = 0; w < kWarps; ++w) {
+        const uint32_t c = cnt[w * RADIX + d];
+        cnt[w * RADIX + d] = (uint16_t)run;
+        run += c;
+      }
+      tot[j] = run;
+      sum += run;
     }
-    // exclusive scan of the 256 totals
-    uint32_t incl = run;
+    uint32_t incl = sum;
 #pragma unroll
     for (int off = 1; off < 32; off <<= 1) {
       const uint32_t o = __shfl_up_sync(0xffffffffu, incl, off);
@@ -181,19 +213,24 @@ tile_scatter_kernel(const uint32_t* __restrict__ keys_in, const uint8_t* __restr
     }
     if (lane == 31) warp_tot[warp] = incl;
     __syncthreads();
-    uint32_t base = 0;
+    uint32_t run = incl - sum;
 #pragma unroll
-    for (int w = 0; w < kWarps; ++w) base += (w < warp) ? warp_tot[w] : 0u;
-    const uint32_t excl = base + incl - run;
-    dig_base[d] = excl;
-    out_off[d] = tile_offs[((int64_t)q * tiles + t) * kRadix + d] - excl;
+    for (int w = 0; w < kWarps; ++w) run += (w < warp) ? warp_tot[w] : 0u;
+    const uint32_t* offs = tile_offs + ((int64_t)q * tiles + t) * RADIX + threadIdx.x * DPT;
+#pragma unroll
+    for (int j = 0; j < DPT; ++j) {
+      const int d = threadIdx.x * DPT + j;
+      dig_base[d] = (uint16_t)run;
+      out_off[d] = offs[j] - run;
+      run += tot[j];
+    }
   }
   __syncthreads();
 #pragma unroll
   for (int r = 0; r < kItems; ++r) {
     if (warp_base + r * 32 + lane < n) {
-      const uint32_t digit = (key[r] >> shift) & 0xFFu;
-      const uint32_t p = dig_base[digit] + cnt[warp][digit] + ((rank2[r >> 1] >> (16 * (r & 1))) & 0xFFFFu);
+      const uint32_t digit = (key[r] >> shift) & MASK;
+      const uint32_t p = (uint32_t)dig_base[digit] + my_cnt[digit] + ((rank2[r >> 1] >> (16 * (r & 1))) & 0xFFFFu);
       s_keys[p] = key[r];
       s_labs[p] = (uint8_t)(lab4[r >> 2] >> (8 * (r & 3)));
       if (kHasIdx) s_idx[p] = idx[r];
@@ -207,12 +244,56 @@ tile_scatter_kernel(const uint32_t* __restrict__ keys_in, const uint8_t* __restr
     const int p = r * kSortThreads + threadIdx.x;
     if (p < count) {
       const uint32_t k = s_keys[p];
-      const int64_t dst = seg_off + out_off[(k >> shift) & 0xFFu] + p;
+      const int64_t dst = seg_off + (uint32_t)(out_off[(k >> shift) & MASK] + (uint32_t)p);
       keys_out[dst] = k;
       labs_out[dst] = s_labs[p];
       if (kHasIdx) idx_out[dst] = s_idx[p];
     }
   }
+}
+
+template <int BITS>
+int run_pass(Ctx* c, const SortArgs& a, int cur, bool first, int shift, int tiles, uint32_t* th, cudaStream_t st) {
+  constexpr int RADIX = 1 << BITS;
+  const bool has_idx = a.idxs[0] != nullptr;
+  for (int q0 = 0; q0 < a.q; q0 += 65535) {
+    const int qn = (a.q - q0) < 65535 ? (a.q - q0) : 65535;
+    const int64_t off = (int64_t)q0 * a.ldk;
+    uint32_t* th_q = th + (int64_t)q0 * tiles * RADIX;
+    dim3 grid((unsigned)tiles, (unsigned)qn);
+    {
+      StageScope scope(c, DVL_STAGE_SORT_HIST, st);
+      tile_hist_kernel<BITS><<<grid, kSortThreads, 0, st>>>(a.keys[cur] + off, a.ldk, a.n, shift, tiles, th_q);
+      DVL_LAUNCH_CHECK(c, "tile_hist_kernel");
+    }
+    {
+      StageScope scope(c, DVL_STAGE_SORT_SCAN, st);
+      seg_scan_kernel<BITS><<<(unsigned)qn, kSortThreads, 0, st>>>(th_q, tiles);
+      DVL_LAUNCH_CHECK(c, "seg_scan_kernel");
+    }
+    StageScope scope(c, DVL_STAGE_SORT_SCATTER, st);
+    const uint32_t* ki = a.keys[cur] + off;
+    const uint8_t* li = a.labs[cur] + off;
+    const int32_t* ii = has_idx ? a.idxs[cur] + off : nullptr;
+    uint32_t* ko = a.keys[cur ^ 1] + off;
+    uint8_t* lo = a.labs[cur ^ 1] + off;
+    int32_t* io = has_idx ? a.idxs[cur ^ 1] + off : nullptr;
+#define DVL_SCATTER(FIRST, IDX)                                                                                   \
+  do {                                                                                                            \
+    auto kern = tile_scatter_kernel<BITS, FIRST, IDX>;                                                            \
+    const size_t smem = scatter_smem_bytes<BITS, IDX>();                                                          \
+    DVL_CUDA(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));              \
+    kern<<<grid, kSortThreads, smem, st>>>(ki, li, ii, a.gallery_labels, ko, lo, io, a.ldk, a.n, shift, tiles, th_q); \
+  } while (0)
+    if (first) {
+      if (has_idx) DVL_SCATTER(true, true); else DVL_SCATTER(true, false);
+    } else {
+      if (has_idx) DVL_SCATTER(false, true); else DVL_SCATTER(false, false);
+    }
+#undef DVL_SCATTER
+    DVL_LAUNCH_CHECK(c, "tile_scatter_kernel");
+  }
+  return DVL_OK;
 }
 
 }  // namespace
@@ -233,55 +314,16 @@ int launch_scores_to_keys(Ctx* c, const float* scores, int64_t lds, uint32_t* ke
 
 int launch_segmented_sort(Ctx* c, const SortArgs& a, int* out_buf, cudaStream_t st) {
   const int tiles = (int)((a.n + kTile - 1) / kTile);
-  const bool has_idx = a.idxs[0] != nullptr;
   if (a.ldk % 4 != 0) return set_error(c, DVL_ERR_INVALID, "sort pitch must be a multiple of 4");
-  DVL_TRY(ensure(c, c->tile_hist, (size_t)a.q * tiles * kRadix * sizeof(uint32_t)));
+  DVL_TRY(ensure(c, c->tile_hist, (size_t)a.q * tiles * (1 << kMaxBits) * sizeof(uint32_t)));
   uint32_t* th = (uint32_t*)c->tile_hist.ptr;
-  int cur = 0;
-  for (int pass = 0; pass < 4; ++pass) {
-    const int shift = pass * 8;
-    for (int q0 = 0; q0 < a.q; q0 += 65535) {
-      const int qn = (a.q - q0) < 65535 ? (a.q - q0) : 65535;
-      const int64_t off = (int64_t)q0 * a.ldk;
-      uint32_t* th_q = th + (int64_t)q0 * tiles * kRadix;
-      dim3 grid((unsigned)tiles, (unsigned)qn);
-      {
-        StageScope scope(c, DVL_STAGE_SORT_HIST, st);
-        tile_hist_kernel<<<grid, kSortThreads, 0, st>>>(a.keys[cur] + off, a.ldk, a.n, shift, tiles, th_q);
-        DVL_LAUNCH_CHECK(c, "tile_hist_kernel");
-      }
-      {
-        StageScope scope(c, DVL_STAGE_SORT_SCAN, st);
-        seg_scan_kernel<<<(unsigned)qn, kRadix, 0, st>>>(th_q, tiles);
-        DVL_LAUNCH_CHECK(c, "seg_scan_kernel");
-      }
-      StageScope scope(c, DVL_STAGE_SORT_SCATTER, st);
-      const uint32_t* ki = a.keys[cur] + off;
-      const uint8_t* li = a.labs[cur] + off;
-      const int32_t* ii = has_idx ? a.idxs[cur] + off : nullptr;
-      uint32_t* ko = a.keys[cur ^ 1] + off;
-      uint8_t* lo = a.labs[cur ^ 1] + off;
-      int32_t* io = has_idx ? a.idxs[cur ^ 1] + off : nullptr;
-      if (pass == 0) {
-        if (has_idx)
-          tile_scatter_kernel<true, true><<<grid, kSortThreads, 0, st>>>(ki, li, ii, a.gallery_labels, ko, lo, io,
-                                                                         a.ldk, a.n, shift, tiles, th_q);
-        else
-          tile_scatter_kernel<true, false><<<grid, kSortThreads, 0, st>>>(ki, li, ii, a.gallery_labels, ko, lo, io,
-                                                                          a.ldk, a.n, shift, tiles, th_q);
-      } else {
-        if (has_idx)
-          tile_scatter_kernel<false, true><<<grid, kSortThreads, 0, st>>>(ki, li, ii, a.gallery_labels, ko, lo, io,
-                                                                          a.ldk, a.n, shift, tiles, th_q);
-        else
-          tile_scatter_kernel<false, false><<<grid, kSortThreads, 0, st>>>(ki, li, ii, a.gallery_labels, ko, lo, io,
-                                                                           a.ldk, a.n, shift, tiles, th_q);
-      }
-      DVL_LAUNCH_CHECK(c, "tile_scatter_kernel");
-    }
-    cur ^= 1;
-  }
-  *out_buf = cur;
+  // 32-bit keys in four LSD passes of 8 bits.  (11+11+10 bits in three passes was measured slower:
+  // 0.33 vs 0.23 ms per scatter pass on config 2 -- 12 ballots per key, two-key runs, 2048-bin scans.)
+  DVL_TRY(run_pass<8>(c, a, 0, true, 0, tiles, th, st));
+  DVL_TRY(run_pass<8>(c, a, 1, false, 8, tiles, th, st));
+  DVL_TRY(run_pass<8>(c, a, 0, false, 16, tiles, th, st));
+  DVL_TRY(run_pass<8>(c, a, 1, false, 24, tiles, th, st));
+  *out_buf = 0;
   return DVL_OK;
 }
 

@@ -135,8 +135,6 @@ def evaluate_sharded(ctx, comm, gallery_local: torch.Tensor, queries: torch.Tens
     tau = comm.all_reduce_max(tau)
     counts = comm.all_reduce_sum(counts)
     oflags = comm.all_reduce_max(oflags)
-    if int(counts[_capi.MAX_CLASSES].item()) != 0:
-        raise _capi.DvlError(-1, f"a label is >= n_classes ({n_classes})")
     # 2. what can still rank globally
     cnt = ctx.shard_trim(tau) if have_rows else torch.zeros((q,), dtype=torch.int32, device=dev)
     length = comm.all_reduce_max(cnt.max().reshape(1).to(torch.int64))
@@ -163,10 +161,17 @@ def evaluate_sharded(ctx, comm, gallery_local: torch.Tensor, queries: torch.Tens
     ranked_len = comm.all_gather(ranked_len_blk).reshape(-1)[:q].contiguous()
     merge_flags = comm.all_gather(flags_blk).reshape(-1)[:q]
     ranked_idx = comm.all_gather(idx_blk).reshape(-1, ranked_cap)[:q].contiguous() if ranked_cap else None
-    flagged = torch.nonzero((oflags != 0) | (merge_flags != 0)).reshape(-1)
-    n_flagged = int(flagged.numel())
-    # 5. exact re-rank of flagged queries (tie run longer than a candidate list)
-    if n_flagged:
+    flag_mask = (oflags != 0) | (merge_flags != 0)
+    status = torch.stack([flag_mask.any().to(torch.int64), counts[_capi.MAX_CLASSES]])
+    mean = ctx.mean(per_query)                # the path's second (and last) host synchronisation
+    any_flag, bad_label = (int(x) for x in status.tolist())
+    if bad_label:
+        raise _capi.DvlError(-1, f"a label is >= n_classes ({n_classes})")
+    n_flagged = 0
+    # 5. exact re-rank of flagged queries (tie run longer than a candidate list); rare
+    if any_flag:
+        flagged = torch.nonzero(flag_mask).reshape(-1)
+        n_flagged = int(flagged.numel())
         n_local = gallery_local.shape[0]
         rows_blk = shard_bounds(n_global, world, 0)[1]
         fq = queries[flagged].contiguous()
@@ -183,7 +188,7 @@ def evaluate_sharded(ctx, comm, gallery_local: torch.Tensor, queries: torch.Tens
         ranked_len[flagged] = rr["ranked_len"]
         if ranked_cap:
             ranked_idx[flagged] = rr["ranked_idx"]
-    mean = ctx.mean(per_query)
+        mean = ctx.mean(per_query)
     out = {"maxskew": {"eq_opp": mean[0], "dem_par": mean[1]}, "ndkl": {"eq_opp": mean[2], "dem_par": mean[3]},
            "per_query": per_query, "ranked_len": ranked_len, "n_flagged": n_flagged, "list_len": length}
     if ranked_cap:
