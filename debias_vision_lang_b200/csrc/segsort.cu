@@ -118,12 +118,12 @@ constexpr size_t scatter_smem_bytes() {
          (kHasIdx ? kTile * 4 : 0) + 64;
 }
 
-template <int BITS, bool kFirst, bool kHasIdx>
-__global__ void __launch_bounds__(kSortThreads, 3)
-tile_scatter_kernel(const uint32_t* __restrict__ keys_in, const uint8_t* __restrict__ labs_in,
-                    const int32_t* __restrict__ idx_in, const uint8_t* __restrict__ gallery_labels,
-                    uint32_t* __restrict__ keys_out, uint8_t* __restrict__ labs_out, int32_t* __restrict__ idx_out,
-                    int64_t ldk, int64_t n, int shift, int tiles, const uint32_t* __restrict__ tile_offs) {
+template <int BITS, bool kFirst, bool kHasIdx, bool kFull>
+__device__ __forceinline__ void
+tile_scatter_body(const uint32_t* __restrict__ keys_in, const uint8_t* __restrict__ labs_in,
+                  const int32_t* __restrict__ idx_in, const uint8_t* __restrict__ gallery_labels,
+                  uint32_t* __restrict__ keys_out, uint8_t* __restrict__ labs_out, int32_t* __restrict__ idx_out,
+                  int64_t ldk, int64_t n, int shift, int tiles, const uint32_t* __restrict__ tile_offs) {
   constexpr int RADIX = 1 << BITS;
   constexpr uint32_t MASK = RADIX - 1;
   constexpr int DPT = RADIX / kSortThreads;      // digits per thread in phase 2
@@ -143,7 +143,11 @@ tile_scatter_kernel(const uint32_t* __restrict__ keys_in, const uint8_t* __restr
   for (int i = threadIdx.x; i < kWarps * RADIX / 2; i += kSortThreads) reinterpret_cast<uint32_t*>(cnt)[i] = 0;
 
   const int64_t seg_off = (int64_t)q * ldk;
+  // keys of this tile that exist (a full tile needs no bounds checks at all: kFull)
+  const int64_t left = n - (int64_t)t * kTile;
+  const int count = (kFull || left >= kTile) ? kTile : (int)left;
   // warp-striped: warp w owns keys [w*512, w*512+512) of the tile, 16 rounds of 32 consecutive keys
+  const int local_base = warp * (kItems * 32) + lane;
   const int64_t warp_base = (int64_t)t * kTile + warp * (kItems * 32);
   uint32_t key[kItems];
   uint32_t lab4[kItems / 4];                    // four labels per register
@@ -153,7 +157,7 @@ tile_scatter_kernel(const uint32_t* __restrict__ keys_in, const uint8_t* __restr
 #pragma unroll
   for (int r = 0; r < kItems; ++r) {
     const int64_t pos = warp_base + r * 32 + lane;
-    const bool ok = pos < n;
+    const bool ok = kFull || (local_base + r * 32 < count);
     key[r] = ok ? __ldg(keys_in + seg_off + pos) : 0xFFFFFFFFu;
     const uint32_t l = ok ? (uint32_t)(kFirst ? __ldg(gallery_labels + pos) : __ldg(labs_in + seg_off + pos)) : 0u;
     lab4[r >> 2] |= l << (8 * (r & 3));
@@ -170,10 +174,13 @@ tile_scatter_kernel(const uint32_t* __restrict__ keys_in, const uint8_t* __restr
   // stall samples on its consumers).  Lanes past the end of the segment form their own group.
 #pragma unroll
   for (int r = 0; r < kItems; ++r) {
-    const bool ok = warp_base + r * 32 + lane < n;
+    const bool ok = kFull || (local_base + r * 32 < count);
     const uint32_t digit = (key[r] >> shift) & MASK;
-    uint32_t peers = __ballot_sync(0xffffffffu, ok);
-    if (!ok) peers = ~peers;
+    uint32_t peers = 0xffffffffu;
+    if (!kFull) {
+      peers = __ballot_sync(0xffffffffu, ok);
+      if (!ok) peers = ~peers;
+    }
 #pragma unroll
     for (int b = 0; b < BITS; ++b) {
       const uint32_t vote = __ballot_sync(0xffffffffu, (digit >> b) & 1u);
@@ -228,7 +235,7 @@ tile_scatter_kernel(const uint32_t* __restrict__ keys_in, const uint8_t* __restr
   __syncthreads();
 #pragma unroll
   for (int r = 0; r < kItems; ++r) {
-    if (warp_base + r * 32 + lane < n) {
+    if (kFull || (local_base + r * 32 < count)) {
       const uint32_t digit = (key[r] >> shift) & MASK;
       const uint32_t p = (uint32_t)dig_base[digit] + my_cnt[digit] + ((rank2[r >> 1] >> (16 * (r & 1))) & 0xFFFFu);
       s_keys[p] = key[r];
@@ -237,12 +244,10 @@ tile_scatter_kernel(const uint32_t* __restrict__ keys_in, const uint8_t* __restr
     }
   }
   __syncthreads();
-  const int64_t left = n - (int64_t)t * kTile;
-  const int count = left < kTile ? (int)left : kTile;
 #pragma unroll
   for (int r = 0; r < kItems; ++r) {
     const int p = r * kSortThreads + threadIdx.x;
-    if (p < count) {
+    if (kFull || p < count) {
       const uint32_t k = s_keys[p];
       const int64_t dst = seg_off + (uint32_t)(out_off[(k >> shift) & MASK] + (uint32_t)p);
       keys_out[dst] = k;
@@ -250,6 +255,20 @@ tile_scatter_kernel(const uint32_t* __restrict__ keys_in, const uint8_t* __restr
       if (kHasIdx) idx_out[dst] = s_idx[p];
     }
   }
+}
+
+template <int BITS, bool kFirst, bool kHasIdx>
+__global__ void __launch_bounds__(kSortThreads, 3)
+tile_scatter_kernel(const uint32_t* __restrict__ keys_in, const uint8_t* __restrict__ labs_in,
+                    const int32_t* __restrict__ idx_in, const uint8_t* __restrict__ gallery_labels,
+                    uint32_t* __restrict__ keys_out, uint8_t* __restrict__ labs_out, int32_t* __restrict__ idx_out,
+                    int64_t ldk, int64_t n, int shift, int tiles, const uint32_t* __restrict__ tile_offs) {
+  if ((int64_t)(blockIdx.x + 1) * kTile <= n)    // all tiles of a segment but (at most) the last
+    tile_scatter_body<BITS, kFirst, kHasIdx, true>(keys_in, labs_in, idx_in, gallery_labels, keys_out, labs_out,
+                                                   idx_out, ldk, n, shift, tiles, tile_offs);
+  else
+    tile_scatter_body<BITS, kFirst, kHasIdx, false>(keys_in, labs_in, idx_in, gallery_labels, keys_out, labs_out,
+                                                    idx_out, ldk, n, shift, tiles, tile_offs);
 }
 
 template <int BITS>
