@@ -34,6 +34,15 @@ METRIC = "gallery-query pairs/s scored+ranked (MaxSkew/NDKL)"
 UNIT = "pairs/s"
 
 
+def load_traffic(workload):
+    path = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    try:
+        with open(path) as f:
+            return json.load(f).get(workload)
+    except (OSError, ValueError):
+        return None
+
+
 def load_peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -378,6 +387,13 @@ def run_ours(args):
                 "ranking_stage": {"algorithmic_bytes": pairs_rank * 8.0, "ms": sort_ms,
                                   "achieved_gbs": pairs_rank * 8.0 / (sort_ms * 1e-3) / 1e9,
                                   "frac": pairs_rank * 8.0 / (sort_ms * 1e-3) / 1e9 / peaks["hbm_gbs"]}}
+
+    ncu = load_traffic(args.workload)
+    if ncu is not None and ncu["kernel"].split("<")[0].split(" ")[0] == roof["kernel"].split("<")[0]:
+        roof["traffic"] = ncu["traffic_bytes_per_launch"]
+        roof["traffic_source"] = ncu["source"] + " (ncu --set full, per launch: " + ncu["kernel"] + ")"
+        if "tensor_pipe_active_pct" in ncu:
+            roof["ncu_tensor_pipe_active_pct"] = ncu["tensor_pipe_active_pct"]
 
     # ---- CPU baseline beside it (rank 0, N = 1 only): bounded sample of the same workload ----
     cpu = None
