@@ -2,6 +2,7 @@
 // chain the kernels of prep.cu / gemm.cu / segsort.cu / metrics.cu on the caller's stream.
 #include <stdarg.h>
 #include <stdio.h>
+#include <math.h>
 #include <string.h>
 
 #include <new>
@@ -272,7 +273,11 @@ int finish(Ctx* c, const double* per_query, int q, int n_classes, double* out_me
 struct StreamPlan {
   int sort_cap;        // S: entries a query keeps between chunks (top_n + boundary ties)
   int64_t chunk0, chunk_max, cap, trigger;
+  int64_t pilot_step;  // > 1: optimistic threshold from every pilot_step-th row (large galleries)
+  int64_t pilot_rank;  // rank of the pilot sample's entry that becomes the threshold
 };
+
+constexpr int64_t kPilotRows = 65536;
 
 bool plan_stream(int64_t n, int q, int64_t top_n, uint32_t flags, StreamPlan* plan, bool shard = false) {
   if (top_n > 8192) return false;
@@ -295,6 +300,18 @@ bool plan_stream(int64_t n, int q, int64_t top_n, uint32_t flags, StreamPlan* pl
   plan->chunk0 = chunk0;
   plan->chunk_max = chunk_max;
   plan->cap = s + chunk_max;
+  plan->pilot_step = 1;
+  plan->pilot_rank = 0;
+  if (!(flags & DVL_FLAG_NO_PILOT) && n >= 4 * kPilotRows && top_n < n / 8) {
+    const int64_t step = n / kPilotRows;
+    const int64_t n_view = (n + step - 1) / step;
+    const double mu = (double)top_n * (double)n_view / (double)n;     // expected pilot rank of the top_n-th best
+    const int64_t rank = (int64_t)ceil(mu + 4.0 * sqrt(mu + 4.0) + 8.0);
+    if (rank + 1 < n_view && rank <= s / 2) {
+      plan->pilot_step = step;
+      plan->pilot_rank = rank;
+    }
+  }
   return true;
 }
 
@@ -333,40 +350,70 @@ int stream_topk(Ctx* c, const Operands& op, const uint8_t* labels, int64_t n, in
   sel.labels = labels;
   sel.index_base = index_base;
 
+  auto gemm_launch = [&](int mode, int64_t row0, int64_t row1, int64_t n_view, int64_t row_step) -> int {
+    StageScope scope(c, DVL_STAGE_GEMM, st);
+    GemmArgs g = gemm_args(op, n_view, d, q);
+    g.mode = mode;
+    g.row0 = row0;
+    g.row1 = row1;
+    g.tau = tau;
+    g.cand = cand;
+    g.cand_cnt = cnt;
+    g.cap = plan.cap;
+    g.labels = labels;
+    g.index_base = index_base;
+    g.gal_row_step = row_step;
+    g.gal_rows_total = n;
+    return launch_sim_gemm(c, g, st);
+  };
+  auto select_launch = [&](int64_t k, int64_t trigger, bool final_pass, bool pilot_pass) -> int {
+    StageScope scope(c, DVL_STAGE_SELECT, st);
+    sel.k = k;
+    sel.trigger = trigger;
+    sel.final_pass = final_pass;
+    sel.pilot_pass = pilot_pass;
+    sel.rows_total = final_pass ? n : 0;
+    sel.idx_out = final_pass ? idx_out : nullptr;
+    sel.idx_cap = final_pass ? idx_cap : 0;
+    return launch_select(c, sel, st);
+  };
+
+  if (plan.pilot_step > 1) {
+    // ---- optimistic threshold from a strided pilot sample (every pilot_step-th row, read in place
+    // through a strided TMA map).  The sample's r-th best score, r chosen 4 sigma above the rank the
+    // top_n-th best is expected at, is a threshold that keeps >= top_n rows with overwhelming
+    // probability; the final select VERIFIES it (fewer than top_n survivors -> the query is flagged and
+    // re-ranked exactly), so the result is exact either way.  The whole gallery then streams through ONE
+    // filter launch with ~2 top_n survivors per query instead of the ~6 top_n of the progressive scheme.
+    const int64_t n_view = (n + plan.pilot_step - 1) / plan.pilot_step;
+    const int64_t seed_rows = plan.chunk0 < n_view ? plan.chunk0 : n_view;
+    DVL_TRY(launch_topk_reset(c, cnt, tau, cflags, q, (uint32_t)seed_rows, true, st));
+    DVL_TRY(gemm_launch(kGemmSeed, 0, seed_rows, n_view, plan.pilot_step));
+    if (seed_rows < n_view) {
+      DVL_TRY(select_launch(plan.pilot_rank, plan.pilot_rank + 1, false, false));
+      DVL_TRY(gemm_launch(kGemmFilter, seed_rows, n_view, n_view, plan.pilot_step));
+    }
+    DVL_TRY(select_launch(plan.pilot_rank, 0, false, true));
+    DVL_TRY(gemm_launch(kGemmFilter, 0, n, n, 1));
+    return select_launch(top_n, 0, true, false);
+  }
+
+  // ---- progressive scheme: chunks of doubling size, the threshold tightens after every chunk ----
   int64_t row = 0;
   int64_t chunk = plan.chunk0;
   bool first = true;
   while (row < n) {
     const int64_t row1 = (row + chunk < n) ? row + chunk : n;
-    {
-      StageScope scope(c, DVL_STAGE_GEMM, st);
-      GemmArgs g = gemm_args(op, n, d, q);
-      g.mode = first ? kGemmSeed : kGemmFilter;
-      g.row0 = row;
-      g.row1 = row1;
-      g.tau = tau;
-      g.cand = cand;
-      g.cand_cnt = cnt;
-      g.cap = plan.cap;
-      g.labels = labels;
-      g.index_base = index_base;
-      if (first) DVL_TRY(launch_topk_reset(c, cnt, tau, cflags, q, (uint32_t)(row1 - row), true, st));
-      DVL_TRY(launch_sim_gemm(c, g, st));
-    }
+    if (first) DVL_TRY(launch_topk_reset(c, cnt, tau, cflags, q, (uint32_t)(row1 - row), true, st));
+    DVL_TRY(gemm_launch(first ? kGemmSeed : kGemmFilter, row, row1, n, 1));
     row = row1;
     first = false;
     if (row < n) {
-      StageScope scope(c, DVL_STAGE_SELECT, st);
-      sel.final_pass = false;
-      DVL_TRY(launch_select(c, sel, st));
+      DVL_TRY(select_launch(top_n, plan.trigger, false, false));
       chunk = (2 * chunk < plan.chunk_max) ? 2 * chunk : plan.chunk_max;
     }
   }
-  StageScope scope(c, DVL_STAGE_SELECT, st);
-  sel.final_pass = true;
-  sel.idx_out = idx_out;
-  sel.idx_cap = idx_cap;
-  return launch_select(c, sel, st);
+  return select_launch(top_n, 0, true, false);
 }
 
 struct DeviceGuard {
@@ -533,7 +580,10 @@ int rerank_flagged(Ctx* c, const void* gallery, int gdt, const void* queries, in
     DVL_TRY(ensure(c, c->fb_queries, (size_t)f * row_bytes));
     DVL_TRY(ensure(c, c->fb_per_query, (size_t)f * 4 * sizeof(double)));
     DVL_TRY(ensure(c, c->fb_len, (size_t)f * 4));
-    if (ranked_idx != nullptr) DVL_TRY(ensure(c, c->fb_idx, (size_t)f * ranked_cap * 4));
+    if (ranked_idx != nullptr) {
+      DVL_TRY(ensure(c, c->fb_idx, (size_t)f * ranked_cap * 4));
+      DVL_CUDA(c, cudaMemsetAsync(c->fb_idx.ptr, 0xFF, (size_t)f * ranked_cap * 4, st));   // -1 past the ranked rows
+    }
     DVL_TRY(ensure(c, c->keys[0], (size_t)f * ldk * 4));
     {
       StageScope scope(c, DVL_STAGE_COPY, st);

@@ -107,6 +107,8 @@ struct GemmArgs {
   int64_t cap = 0;
   const uint8_t* labels = nullptr;
   int64_t index_base = 0;
+  int64_t gal_row_step = 1;         // > 1: the kernel's rows are a strided sample of the gallery
+  int64_t gal_rows_total = 0;       //      (physical rows, needed for the plane stride)
   const __nv_bfloat16* qry_planes;  // [planes][q][dp]
   const __nv_bfloat16* gal_planes;  // [planes][n][dp]
   int planes;                       // 1 (bf16) or 3 (fp32 via bf16x3)
@@ -156,6 +158,9 @@ struct SelectArgs {
   int sort_cap = 0;
   int64_t trigger = 0;
   bool final_pass = false;
+  bool pilot_pass = false;          // only derive tau from the k-th best entry, then empty the list
+  int64_t rows_total = 0;           // final pass: rows this list was filtered from (verification of an
+                                    // optimistic threshold: fewer than min(k, rows_total) entries -> flag)
   unsigned long long* sorted_out = nullptr;
   uint8_t* labs = nullptr;
   int64_t ldl = 0;

@@ -302,7 +302,10 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
-int make_map(Ctx* c, CUtensorMap* map, const void* base, int64_t rows, int d, int dp, int planes, int box_rows) {
+// rows_view rows, `row_step` physical rows apart (row_step > 1: a strided sample of the matrix, no copy)
+int make_map(Ctx* c, CUtensorMap* map, const void* base, int64_t rows, int d, int dp, int planes, int box_rows,
+             int64_t rows_view = -1, int64_t row_step = 1) {
+  if (rows_view < 0) rows_view = rows;
   if (c->encode_tiled == nullptr) {
     void* fn = nullptr;
     cudaDriverEntryPointQueryResult qres;
@@ -312,8 +315,8 @@ int make_map(Ctx* c, CUtensorMap* map, const void* base, int64_t rows, int d, in
     c->encode_tiled = fn;
   }
   // logical depth d (not the pitch): columns >= d are zero-filled by TMA
-  cuuint64_t dims[3] = {(cuuint64_t)d, (cuuint64_t)rows, (cuuint64_t)planes};
-  cuuint64_t strides[2] = {(cuuint64_t)dp * 2ull, (cuuint64_t)rows * (cuuint64_t)dp * 2ull};
+  cuuint64_t dims[3] = {(cuuint64_t)d, (cuuint64_t)rows_view, (cuuint64_t)planes};
+  cuuint64_t strides[2] = {(cuuint64_t)dp * 2ull * (cuuint64_t)row_step, (cuuint64_t)rows * (cuuint64_t)dp * 2ull};
   cuuint32_t box[3] = {(cuuint32_t)BK, (cuuint32_t)box_rows, 1u};
   cuuint32_t estr[3] = {1u, 1u, 1u};
   CUresult r = ((EncodeTiledFn)c->encode_tiled)(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base),
@@ -340,7 +343,10 @@ int launch_sim_gemm(Ctx* c, const GemmArgs& a, cudaStream_t st) {
   if (a.n > 0x7FFFFF00ll) return set_error(c, DVL_ERR_UNSUPPORTED, "gallery shard larger than 2^31 rows");
   CUtensorMap map_q, map_g;
   DVL_TRY(make_map(c, &map_q, a.qry_planes, a.q, a.d, a.dp, a.planes, BM));
-  DVL_TRY(make_map(c, &map_g, a.gal_planes, a.n, a.d, a.dp, a.planes, BN));
+  // a.n = rows the kernel sees; when a.gal_row_step > 1 they are every gal_row_step-th row of a
+  // gallery of a.gal_rows_total rows
+  const int64_t total_rows = a.gal_row_step > 1 ? a.gal_rows_total : a.n;
+  DVL_TRY(make_map(c, &map_g, a.gal_planes, total_rows, a.d, a.dp, a.planes, BN, a.n, a.gal_row_step));
   KernelParams p;
   p.mode = a.mode;
   p.row0 = a.row0;

@@ -41,6 +41,8 @@ struct SelectParams {
   int sort_cap;             // S: entries that fit the shared-memory list
   int64_t trigger;          // skip (non-final) while the list is shorter than this
   int final_pass;
+  int pilot_pass;
+  int64_t rows_total;
   // final outputs
   unsigned long long* sorted_out;   // [q][sort_cap] or null (defaults to in place for segs == 1)
   uint8_t* labs;            // [q][ldl]
@@ -72,11 +74,23 @@ __global__ void __launch_bounds__(kSelThreads) select_kernel(const SelectParams 
   int64_t n;
   if (p.segs == 1) {
     n = p.cnt[q];
-    if (n > p.cap) n = p.cap;                          // cannot happen by construction (cap = S + chunk)
+    // More survivors than the list holds, or (final pass after an optimistic threshold) fewer than
+    // top_n of them: the list is not a superset of the ranked rows -> exact re-rank of this query.
+    const bool overflow = n > p.cap;
+    const bool starved = p.final_pass && p.rows_total > 0 && n < (p.k < p.rows_total ? p.k : p.rows_total);
+    if (overflow || starved) {
+      if (tid == 0) {
+        p.flags[q] = 1u;
+        p.cnt[q] = 0u;
+        if (p.tau != nullptr) p.tau[q] = __int_as_float(0x7f800000);
+        if (p.final_pass && p.avail != nullptr) p.avail[q] = 0;
+      }
+      return;
+    }
   } else {
     n = (int64_t)p.segs * p.seg_len;
   }
-  if (!p.final_pass && n < p.trigger) return;
+  if (!p.final_pass && !p.pilot_pass && n < p.trigger) return;
 
   // ---- the k-th smallest key ----
   uint32_t kth = 0xFFFFFFFFu;
@@ -137,6 +151,16 @@ __global__ void __launch_bounds__(kSelThreads) select_kernel(const SelectParams 
       __syncthreads();
     }
     kth = sh_prefix;
+  }
+
+  if (p.pilot_pass) {
+    // pilot sample: its k-th best score becomes the (optimistic) threshold of the main pass; the
+    // sample's own entries are dropped -- the main pass sees those rows again
+    if (tid == 0) {
+      p.cnt[q] = 0u;
+      p.tau[q] = (n > p.k && kth != kNanKey) ? key_to_score(kth) : __int_as_float(0xff800000);
+    }
+    return;
   }
 
   // ---- keep everything that still can rank: key <= kth (ties at the boundary included) ----
@@ -281,6 +305,8 @@ int launch_select(Ctx* c, const SelectArgs& a, cudaStream_t st) {
   p.sort_cap = a.sort_cap;
   p.trigger = a.trigger;
   p.final_pass = a.final_pass ? 1 : 0;
+  p.pilot_pass = a.pilot_pass ? 1 : 0;
+  p.rows_total = a.rows_total;
   p.sorted_out = a.sorted_out;
   p.labs = a.labs;
   p.ldl = a.ldl;

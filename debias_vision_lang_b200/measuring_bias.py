@@ -29,7 +29,7 @@ import torch
 from . import _capi
 
 __all__ = [
-    "normalized_discounted_KL", "compute_skew_metrics", "get_prompt_embeddings", "get_labels_img_embeddings",
+    "clip_logits", "normalized_discounted_KL", "compute_skew_metrics", "get_prompt_embeddings", "get_labels_img_embeddings",
     "eval_ranking", "gen_prompts", "measure_bias", "evaluate", "DEFAULT_OPTS", "PROMPT_TEMPLATES", "PROMPT_CONCEPTS",
 ]
 
@@ -246,6 +246,22 @@ def get_labels_img_embeddings(images_dl, model, device: torch.device, progress: 
         image_labels.append(lab.detach().cpu().numpy() if isinstance(lab, torch.Tensor) else np.asarray(lab))
     labels = np.concatenate([np.atleast_1d(x) for x in image_labels]) if image_labels else np.zeros(0, dtype=np.int64)
     return labels, torch.cat(image_embeddings, dim=0).to(device)
+
+
+def clip_logits(image_features: torch.Tensor, text_features: torch.Tensor, logit_scale: float = 1.0,
+                opts: Optional[dict] = None) -> Tuple[torch.Tensor, torch.Tensor]:
+    """The other similarity site of the reference, ``DebiasCLIP.forward`` (model/model.py:276-289):
+    both sides L2-normalised, cosine similarity times ``logit_scale`` -> (logits_per_image [N,Q],
+    logits_per_text [Q,N]).  Same tcgen05 GEMM, with both normalisations fused into its epilogue."""
+    dev = _device_of(image_features)
+    g = _as_device_matrix(image_features, dev)
+    t = _as_device_matrix(text_features, dev)
+    precision = _PRECISIONS[(opts or {}).get("precision", "fp32")]
+    with torch.cuda.device(dev):
+        sims = _capi.context(dev.index).similarity(g, t, precision,
+                                                   _capi.FLAG_NORMALIZE_GALLERY | _capi.FLAG_NORMALIZE_QUERIES)
+    logits_per_text = sims * float(logit_scale)
+    return logits_per_text.t(), logits_per_text
 
 
 def measure_bias(cliplike, img_preproc: Optional[Callable] = None, tokenizer: Optional[Callable] = None,

@@ -70,17 +70,9 @@ class TorchDistComm:
 
 
 class LocalComm:
-    """Single-process stand-in: `world` emulated ranks call in lock step from one thread; each
-    collective is executed when the last rank has contributed (used to emulate N shards on one
-    GPU, and by the unit tests)."""
+    """The collectives as plain tensor ops over a list of per-rank tensors: used by
+    ``evaluate_sharded_emulated`` to run all shards of a gallery from one process, stage by stage."""
 
-    def __init__(self, world: int):
-        self.world = world
-        self.rank = 0
-        self._pending: Dict[str, List[torch.Tensor]] = {}
-
-    # The emulation drives ranks phase by phase (see evaluate_sharded_emulated), so the
-    # collectives here operate on lists.
     @staticmethod
     def reduce_max(ts: Sequence[torch.Tensor]) -> torch.Tensor:
         return torch.stack(list(ts)).max(dim=0).values
@@ -200,7 +192,7 @@ def evaluate_sharded_emulated(contexts: Sequence, gallery: torch.Tensor, queries
                               n_classes: int, top_n: int, opts: Optional[dict] = None, ranked_cap: int = 0):
     """All `len(contexts)` ranks in ONE process on one GPU, stage by stage (no kernel ever waits on
     another rank): the same C-ABI stage calls as `evaluate_sharded`, with the collectives replaced
-    by tensor ops.  Used by the GPU tests and by bench.py --emulate-shards."""
+    by tensor ops.  Used by the GPU tests."""
     precision, flags = _flags_and_precision(opts)
     world = len(contexts)
     n, q = gallery.shape[0], queries.shape[0]

@@ -67,6 +67,9 @@ typedef enum dvl_precision { DVL_PRECISION_FP32 = 0, DVL_PRECISION_BF16 = 1 } dv
 #define DVL_FLAG_NORMALIZE_GALLERY 0x2u /* NOT what eval_ranking does: cosine mode */
 #define DVL_FLAG_FULL_SORT         0x4u /* force the materialise-and-sort ranking route even when
                                            top_n << N (the route top_n >= N always takes) */
+#define DVL_FLAG_NO_PILOT          0x10u /* streaming route: do not take an optimistic first threshold
+                                           from a pilot sample (large galleries); use the progressive
+                                           chunk-by-chunk scheme only */
 #define DVL_FLAG_STREAM_TOPK       0x8u /* force the streaming top-k route even on a small gallery
                                            (chunks of N/4 rows); needs top_n < N and top_n <= 8192 */
 

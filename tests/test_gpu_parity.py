@@ -259,3 +259,16 @@ def test_full_size_properties_cfg2(ctx):
     # NDKL of 4 sampled queries against the oracle on the CUDA path's own scores
     want, _ = spec.eval_scores_matrix(res["scores"][:4].cpu().numpy(), w.labels, n)
     assert np.abs(pq[:4] - want).max() <= TIGHT
+
+
+def test_clip_logits_both_sides_normalised():
+    """DebiasCLIP.forward's logits (model/model.py:276-289): both sides normalised, times logit_scale."""
+    torch.manual_seed(8)
+    img = torch.randn(700, 512, device="cuda") * 5
+    txt = torch.randn(9, 512, device="cuda") * 2
+    scale = 100.0
+    want = scale * (img / img.norm(dim=-1, keepdim=True)).double() @ (txt / txt.norm(dim=-1, keepdim=True)).double().T
+    per_image, per_text = dvl.clip_logits(img, txt, scale)
+    assert per_image.shape == (700, 9) and per_text.shape == (9, 700)
+    assert (per_image.double() - want).abs().max().item() <= scale * 1e-5
+    assert torch.equal(per_text, per_image.t())

@@ -137,3 +137,42 @@ def test_million_row_topk_properties(ctx):
         assert int((s[i][mask] > kth).sum()) == 0
     res2 = ctx.eval_ranking(w.gallery, w.queries, lab, 2, 1000, _capi.PRECISION_BF16, 0, want_per_query=True)
     assert torch.equal(res2["per_query"], res["per_query"])
+
+
+def test_pilot_threshold_route_is_exact(ctx):
+    """Galleries >= 262,144 rows take their first threshold from a strided pilot sample (optimistic, then
+    verified).  Same ranked lists and metrics as the full-sort route and as the progressive scheme."""
+    w = synthetic.clip_like(300_000, 64, 40, 7, seed=41, device="cuda")
+    lab = torch.from_numpy(w.labels.astype(np.uint8)).cuda()
+    runs = {}
+    for name, flags in (("pilot", 0), ("progressive", _capi.FLAG_NO_PILOT), ("full", _capi.FLAG_FULL_SORT)):
+        runs[name] = ctx.eval_ranking(w.gallery, w.queries, lab, 7, 500, _capi.PRECISION_FP32, flags,
+                                      want_per_query=True, ranked_cap=640)
+    for name in ("pilot", "progressive"):
+        assert torch.equal(runs[name]["ranked_len"], runs["full"]["ranked_len"]), name
+        assert torch.equal(runs[name]["ranked_idx"], runs["full"]["ranked_idx"]), name
+        assert torch.equal(runs[name]["per_query"], runs["full"]["per_query"]), name
+
+
+def test_pilot_threshold_starvation_is_caught_and_reranked(ctx):
+    """Adversarial for the pilot sample: the high scores sit exactly on the sampled rows (every 4th), so the
+    sample's threshold keeps fewer than top_n rows.  The final select must notice and the query must be
+    re-ranked exactly."""
+    n, d, q, k = 300_000, 32, 6, 1000
+    rng = np.random.RandomState(5)
+    g = (rng.randint(-20, 21, size=(n, d)) / 64.0).astype(np.float32)
+    t = np.zeros((q, d), dtype=np.float32)
+    t[:, 0] = 1.0
+    t[1:, 1:] = (rng.randint(-3, 4, size=(q - 1, d - 1)) / 64.0).astype(np.float32)
+    g[:, 0] = (rng.randint(0, 64, size=n) / 64.0)          # base scores 0..1 on the coordinate all queries weigh
+    g[::4, 0] += 8.0                                         # the pilot's rows (step = n // 65536 = 4) tower above
+    g[::4, 0] += (rng.randint(0, 4096, size=len(g[::4])) / 64.0)
+    labels = synthetic.make_labels(n, 2, 3)
+    lab = torch.from_numpy(labels.astype(np.uint8)).cuda()
+    gg, tt = torch.from_numpy(g).cuda(), torch.from_numpy(t).cuda()
+    pilot = ctx.eval_ranking(gg, tt, lab, 2, k, _capi.PRECISION_FP32, 0, want_per_query=True, ranked_cap=k + 64)
+    full = ctx.eval_ranking(gg, tt, lab, 2, k, _capi.PRECISION_FP32, _capi.FLAG_FULL_SORT, want_per_query=True,
+                            ranked_cap=k + 64)
+    assert torch.equal(pilot["ranked_len"], full["ranked_len"])
+    assert torch.equal(pilot["ranked_idx"], full["ranked_idx"])
+    assert torch.equal(pilot["per_query"], full["per_query"])
