@@ -9,6 +9,8 @@
 // Per pass:  tile digit histograms -> per-segment exclusive scan over (digit, tile) ->
 //            stable scatter (warp match/ballot ranking inside 4096-key tiles).
 // HBM-bound byte work: coalesced 16-byte key loads, one CTA per (tile, segment).
+#include <stdlib.h>
+
 #include "dvl_common.cuh"
 #include "dvl_internal.h"
 
@@ -104,6 +106,32 @@ __global__ void __launch_bounds__(kSortThreads) seg_scan_kernel(uint32_t* __rest
   }
 }
 
+// Lanes of the warp holding the same digit as this lane.
+//   kRank 0: BITS ballots.  Per bit: bit test -> predicate, VOTE, SEL (all-ones if my bit is set),
+//            one LOP3 accumulating the lanes that differ (vote ^ mine) -- four instructions; written in
+//            PTX because the compiler's own rendering of `bit ? vote : ~vote` took seven.
+//   kRank 1: one MATCH.ANY per key (kept for measurements: 47 instead of 72 instructions per key, but
+//            0.23 instead of 0.148 ms per pass on config 2 -- MATCH.ANY issues far below one per clock).
+template <int BITS, int kRank>
+__device__ __forceinline__ uint32_t digit_peers(uint32_t digit) {
+  if (kRank == 1) return __match_any_sync(0xffffffffu, digit);
+  uint32_t differ = 0u;
+#pragma unroll
+  for (int b = 0; b < BITS; ++b) {
+    uint32_t vote, mine;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .b32 t;\n\t"
+        "and.b32 t, %2, %3;\n\t"
+        "setp.ne.u32 p, t, 0;\n\t"
+        "vote.sync.ballot.b32 %0, p, 0xffffffff;\n\t"
+        "selp.b32 %1, 0xffffffff, 0, p;\n\t}"
+        : "=r"(vote), "=r"(mine)
+        : "r"(digit), "r"(1u << b));
+    differ |= vote ^ mine;
+  }
+  return ~differ;
+}
+
 // pass step 3: stable scatter of one tile.
 //   phase 0  all 16 key (and payload) loads of a thread are issued before anything waits on them
 //   phase 1  warp-synchronous stable ranking: BITS ballots group the lanes holding equal digits, the
@@ -114,16 +142,16 @@ __global__ void __launch_bounds__(kSortThreads) seg_scan_kernel(uint32_t* __rest
 //            output, so neighbouring threads store neighbouring addresses
 template <int BITS, bool kHasIdx>
 constexpr size_t scatter_smem_bytes() {
-  return (size_t)kWarps * (1 << BITS) * 2 + (size_t)(1 << BITS) * 2 + (size_t)(1 << BITS) * 4 + kTile * 4 + kTile +
+  return (size_t)kWarps * (1 << BITS) * 2 + (size_t)(1 << BITS) * 4 + kTile * 4 + kTile +
          (kHasIdx ? kTile * 4 : 0) + 64;
 }
 
-template <int BITS, bool kFirst, bool kHasIdx, bool kFull>
+template <int BITS, int SHIFT, int kRank, bool kFirst, bool kHasIdx, bool kFull>
 __device__ __forceinline__ void
 tile_scatter_body(const uint32_t* __restrict__ keys_in, const uint8_t* __restrict__ labs_in,
                   const int32_t* __restrict__ idx_in, const uint8_t* __restrict__ gallery_labels,
                   uint32_t* __restrict__ keys_out, uint8_t* __restrict__ labs_out, int32_t* __restrict__ idx_out,
-                  int64_t ldk, int64_t n, int shift, int tiles, const uint32_t* __restrict__ tile_offs) {
+                  int64_t ldk, int64_t n, int tiles, const uint32_t* __restrict__ tile_offs) {
   constexpr int RADIX = 1 << BITS;
   constexpr uint32_t MASK = RADIX - 1;
   constexpr int DPT = RADIX / kSortThreads;      // digits per thread in phase 2
@@ -132,8 +160,7 @@ tile_scatter_body(const uint32_t* __restrict__ keys_in, const uint8_t* __restric
   uint32_t* s_keys = out_off + RADIX;                                     // [kTile]
   int32_t* s_idx = reinterpret_cast<int32_t*>(s_keys + kTile);            // [kTile] if kHasIdx
   uint16_t* cnt = reinterpret_cast<uint16_t*>(s_idx + (kHasIdx ? kTile : 0));   // [kWarps][RADIX]
-  uint16_t* dig_base = cnt + kWarps * RADIX;                              // [RADIX] first tile position of a digit
-  uint8_t* s_labs = reinterpret_cast<uint8_t*>(dig_base + RADIX);         // [kTile]
+  uint8_t* s_labs = reinterpret_cast<uint8_t*>(cnt + kWarps * RADIX);     // [kTile]
   __shared__ uint32_t warp_tot[kWarps];
   const int q = blockIdx.y;
   const int t = blockIdx.x;
@@ -149,6 +176,8 @@ tile_scatter_body(const uint32_t* __restrict__ keys_in, const uint8_t* __restric
   // warp-striped: warp w owns keys [w*512, w*512+512) of the tile, 16 rounds of 32 consecutive keys
   const int local_base = warp * (kItems * 32) + lane;
   const int64_t warp_base = (int64_t)t * kTile + warp * (kItems * 32);
+  const uint32_t* kp = keys_in + seg_off + warp_base + lane;
+  const uint8_t* lp = (kFirst ? gallery_labels : labs_in + seg_off) + warp_base + lane;
   uint32_t key[kItems];
   uint32_t lab4[kItems / 4];                    // four labels per register
   int32_t idx[kHasIdx ? kItems : 1];
@@ -156,12 +185,11 @@ tile_scatter_body(const uint32_t* __restrict__ keys_in, const uint8_t* __restric
   for (int r = 0; r < kItems / 4; ++r) lab4[r] = 0u;
 #pragma unroll
   for (int r = 0; r < kItems; ++r) {
-    const int64_t pos = warp_base + r * 32 + lane;
     const bool ok = kFull || (local_base + r * 32 < count);
-    key[r] = ok ? __ldg(keys_in + seg_off + pos) : 0xFFFFFFFFu;
-    const uint32_t l = ok ? (uint32_t)(kFirst ? __ldg(gallery_labels + pos) : __ldg(labs_in + seg_off + pos)) : 0u;
+    key[r] = ok ? __ldg(kp + r * 32) : 0xFFFFFFFFu;
+    const uint32_t l = ok ? (uint32_t)__ldg(lp + r * 32) : 0u;
     lab4[r >> 2] |= l << (8 * (r & 3));
-    if (kHasIdx) idx[r] = ok ? (kFirst ? (int32_t)pos : __ldg(idx_in + seg_off + pos)) : 0;
+    if (kHasIdx) idx[r] = ok ? (kFirst ? (int32_t)(warp_base + r * 32 + lane) : __ldg(idx_in + seg_off + warp_base + r * 32 + lane)) : 0;
   }
   __syncthreads();
 
@@ -169,34 +197,48 @@ tile_scatter_body(const uint32_t* __restrict__ keys_in, const uint8_t* __restric
 #pragma unroll
   for (int r = 0; r < kItems / 2; ++r) rank2[r] = 0u;
   uint16_t* my_cnt = cnt + warp * RADIX;
-  // Lanes holding the same digit: BITS ballots (one per digit bit) ANDed together -- the MATCH.ANY
-  // instruction computes the same mask but its latency made it the kernel's bottleneck (ncu: 59 % of
-  // stall samples on its consumers).  Lanes past the end of the segment form their own group.
+  // Stable ranking inside the warp: the lanes holding the same digit form a group; every lane of the
+  // group reads the warp's counter of the digit, the lowest lane bumps it by the group size.
+  // Lanes past the end of the segment carry an extra digit bit, so they form their own group.
+  constexpr int kBatch = (kRank == 1) ? 8 : 1;  // MATCH.ANY has a long latency: issue a batch before use
 #pragma unroll
-  for (int r = 0; r < kItems; ++r) {
-    const bool ok = kFull || (local_base + r * 32 < count);
-    const uint32_t digit = (key[r] >> shift) & MASK;
-    uint32_t peers = 0xffffffffu;
-    if (!kFull) {
-      peers = __ballot_sync(0xffffffffu, ok);
-      if (!ok) peers = ~peers;
+  for (int r0 = 0; r0 < kItems; r0 += kBatch) {
+    uint32_t peers_b[kBatch];
+#pragma unroll
+    for (int j = 0; j < kBatch; ++j) {
+      const int r = r0 + j;
+      const bool ok = kFull || (local_base + r * 32 < count);
+      const uint32_t digit = (key[r] >> SHIFT) & MASK;
+      if (kRank == 1) {
+        peers_b[j] = digit_peers<BITS, 1>(kFull ? digit : (digit | (ok ? 0u : (uint32_t)RADIX)));
+      } else {
+        uint32_t peers = digit_peers<BITS, 0>(digit);
+        if (!kFull) {
+          const uint32_t live = __ballot_sync(0xffffffffu, ok);
+          peers &= ok ? live : ~live;
+        }
+        peers_b[j] = peers;
+      }
     }
 #pragma unroll
-    for (int b = 0; b < BITS; ++b) {
-      const uint32_t vote = __ballot_sync(0xffffffffu, (digit >> b) & 1u);
-      peers &= ((digit >> b) & 1u) ? vote : ~vote;
+    for (int j = 0; j < kBatch; ++j) {
+      const int r = r0 + j;
+      const bool ok = kFull || (local_base + r * 32 < count);
+      const uint32_t digit = (key[r] >> SHIFT) & MASK;
+      const uint32_t peers = peers_b[j];
+      uint32_t before = 0;
+      if (ok) before = my_cnt[digit];
+      __syncwarp();
+      if (ok && (peers & lt_mask) == 0u) my_cnt[digit] = (uint16_t)(before + __popc(peers));
+      rank2[r >> 1] |= (before + __popc(peers & lt_mask)) << (16 * (r & 1));
+      __syncwarp();
     }
-    uint32_t before = 0;
-    if (ok) before = my_cnt[digit];               // every lane of the group reads the same counter ...
-    __syncwarp();
-    if (ok && (peers & lt_mask) == 0u) my_cnt[digit] = (uint16_t)(before + __popc(peers));   // ... its lowest lane bumps it
-    rank2[r >> 1] |= (before + __popc(peers & lt_mask)) << (16 * (r & 1));
-    __syncwarp();
   }
   __syncthreads();
   {
     // thread owns DPT consecutive digits: exclusive prefix over the warps, digit totals, then the
-    // exclusive scan of the totals across the block
+    // exclusive scan of the totals across the block.  Afterwards cnt[w][d] = first tile position of
+    // warp w's keys with digit d, out_off[d] = output position of digit d's run minus its tile position.
     uint32_t tot[DPT];
     uint32_t sum = 0;
 #pragma unroll
@@ -205,9 +247,7 @@ tile_scatter_body(const uint32_t* __restrict__ keys_in, const uint8_t* __restric
       uint32_t run = 0;
 #pragma unroll
       for (int w = 0; w < kWarps; ++w) {
-        const uint32_t c = cnt[w * RADIX + d];
-        cnt[w * RADIX + d] = (uint16_t)run;
-        run += c;
+        run += cnt[w * RADIX + d];
       }
       tot[j] = run;
       sum += run;
@@ -227,8 +267,14 @@ tile_scatter_body(const uint32_t* __restrict__ keys_in, const uint8_t* __restric
 #pragma unroll
     for (int j = 0; j < DPT; ++j) {
       const int d = threadIdx.x * DPT + j;
-      dig_base[d] = (uint16_t)run;
-      out_off[d] = offs[j] - run;
+      out_off[d] = __ldg(offs + j) - run;
+      uint32_t pos = run;
+#pragma unroll
+      for (int w = 0; w < kWarps; ++w) {
+        const uint32_t c = cnt[w * RADIX + d];
+        cnt[w * RADIX + d] = (uint16_t)pos;
+        pos += c;
+      }
       run += tot[j];
     }
   }
@@ -236,43 +282,53 @@ tile_scatter_body(const uint32_t* __restrict__ keys_in, const uint8_t* __restric
 #pragma unroll
   for (int r = 0; r < kItems; ++r) {
     if (kFull || (local_base + r * 32 < count)) {
-      const uint32_t digit = (key[r] >> shift) & MASK;
-      const uint32_t p = (uint32_t)dig_base[digit] + my_cnt[digit] + ((rank2[r >> 1] >> (16 * (r & 1))) & 0xFFFFu);
+      const uint32_t digit = (key[r] >> SHIFT) & MASK;
+      const uint32_t p = (uint32_t)my_cnt[digit] + ((rank2[r >> 1] >> (16 * (r & 1))) & 0xFFFFu);
       s_keys[p] = key[r];
       s_labs[p] = (uint8_t)(lab4[r >> 2] >> (8 * (r & 3)));
       if (kHasIdx) s_idx[p] = idx[r];
     }
   }
   __syncthreads();
+  uint32_t* ko = keys_out + seg_off;
+  uint8_t* lo = labs_out + seg_off;
 #pragma unroll
   for (int r = 0; r < kItems; ++r) {
     const int p = r * kSortThreads + threadIdx.x;
     if (kFull || p < count) {
       const uint32_t k = s_keys[p];
-      const int64_t dst = seg_off + (uint32_t)(out_off[(k >> shift) & MASK] + (uint32_t)p);
-      keys_out[dst] = k;
-      labs_out[dst] = s_labs[p];
-      if (kHasIdx) idx_out[dst] = s_idx[p];
+      const uint32_t dst = out_off[(k >> SHIFT) & MASK] + (uint32_t)p;
+      ko[dst] = k;
+      lo[dst] = s_labs[p];
+      if (kHasIdx) idx_out[seg_off + dst] = s_idx[p];
     }
   }
 }
 
-template <int BITS, bool kFirst, bool kHasIdx>
+template <int BITS, int SHIFT, int kRank, bool kFirst, bool kHasIdx>
 __global__ void __launch_bounds__(kSortThreads, 3)
 tile_scatter_kernel(const uint32_t* __restrict__ keys_in, const uint8_t* __restrict__ labs_in,
                     const int32_t* __restrict__ idx_in, const uint8_t* __restrict__ gallery_labels,
                     uint32_t* __restrict__ keys_out, uint8_t* __restrict__ labs_out, int32_t* __restrict__ idx_out,
-                    int64_t ldk, int64_t n, int shift, int tiles, const uint32_t* __restrict__ tile_offs) {
+                    int64_t ldk, int64_t n, int tiles, const uint32_t* __restrict__ tile_offs) {
   if ((int64_t)(blockIdx.x + 1) * kTile <= n)    // all tiles of a segment but (at most) the last
-    tile_scatter_body<BITS, kFirst, kHasIdx, true>(keys_in, labs_in, idx_in, gallery_labels, keys_out, labs_out,
-                                                   idx_out, ldk, n, shift, tiles, tile_offs);
+    tile_scatter_body<BITS, SHIFT, kRank, kFirst, kHasIdx, true>(keys_in, labs_in, idx_in, gallery_labels, keys_out,
+                                                                 labs_out, idx_out, ldk, n, tiles, tile_offs);
   else
-    tile_scatter_body<BITS, kFirst, kHasIdx, false>(keys_in, labs_in, idx_in, gallery_labels, keys_out, labs_out,
-                                                    idx_out, ldk, n, shift, tiles, tile_offs);
+    tile_scatter_body<BITS, SHIFT, kRank, kFirst, kHasIdx, false>(keys_in, labs_in, idx_in, gallery_labels, keys_out,
+                                                                  labs_out, idx_out, ldk, n, tiles, tile_offs);
 }
 
-template <int BITS>
-int run_pass(Ctx* c, const SortArgs& a, int cur, bool first, int shift, int tiles, uint32_t* th, cudaStream_t st) {
+int sort_rank_mode() {
+  static const int mode = [] {
+    const char* e = getenv("DVL_SORT_RANK");
+    return (e != nullptr && e[0] == '1') ? 1 : 0;
+  }();
+  return mode;
+}
+
+template <int BITS, int SHIFT, int kRank, bool kFirst>
+int run_pass(Ctx* c, const SortArgs& a, int cur, int tiles, uint32_t* th, cudaStream_t st) {
   constexpr int RADIX = 1 << BITS;
   const bool has_idx = a.idxs[0] != nullptr;
   for (int q0 = 0; q0 < a.q; q0 += 65535) {
@@ -282,7 +338,7 @@ int run_pass(Ctx* c, const SortArgs& a, int cur, bool first, int shift, int tile
     dim3 grid((unsigned)tiles, (unsigned)qn);
     {
       StageScope scope(c, DVL_STAGE_SORT_HIST, st);
-      tile_hist_kernel<BITS><<<grid, kSortThreads, 0, st>>>(a.keys[cur] + off, a.ldk, a.n, shift, tiles, th_q);
+      tile_hist_kernel<BITS><<<grid, kSortThreads, 0, st>>>(a.keys[cur] + off, a.ldk, a.n, SHIFT, tiles, th_q);
       DVL_LAUNCH_CHECK(c, "tile_hist_kernel");
     }
     {
@@ -297,21 +353,29 @@ int run_pass(Ctx* c, const SortArgs& a, int cur, bool first, int shift, int tile
     uint32_t* ko = a.keys[cur ^ 1] + off;
     uint8_t* lo = a.labs[cur ^ 1] + off;
     int32_t* io = has_idx ? a.idxs[cur ^ 1] + off : nullptr;
-#define DVL_SCATTER(FIRST, IDX)                                                                                   \
+#define DVL_SCATTER(IDX)                                                                                          \
   do {                                                                                                            \
-    auto kern = tile_scatter_kernel<BITS, FIRST, IDX>;                                                            \
+    auto kern = tile_scatter_kernel<BITS, SHIFT, kRank, kFirst, IDX>;                                             \
     const size_t smem = scatter_smem_bytes<BITS, IDX>();                                                          \
     DVL_CUDA(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));              \
-    kern<<<grid, kSortThreads, smem, st>>>(ki, li, ii, a.gallery_labels, ko, lo, io, a.ldk, a.n, shift, tiles, th_q); \
+    kern<<<grid, kSortThreads, smem, st>>>(ki, li, ii, a.gallery_labels, ko, lo, io, a.ldk, a.n, tiles, th_q);    \
   } while (0)
-    if (first) {
-      if (has_idx) DVL_SCATTER(true, true); else DVL_SCATTER(true, false);
-    } else {
-      if (has_idx) DVL_SCATTER(false, true); else DVL_SCATTER(false, false);
-    }
+    if (has_idx) DVL_SCATTER(true); else DVL_SCATTER(false);
 #undef DVL_SCATTER
     DVL_LAUNCH_CHECK(c, "tile_scatter_kernel");
   }
+  return DVL_OK;
+}
+
+template <int kRank>
+int sort_passes(Ctx* c, const SortArgs& a, int tiles, uint32_t* th, cudaStream_t st) {
+  // 32-bit keys in four LSD passes of 8 bits.  (11+11+10 bits in three passes was measured slower:
+  // 0.33 vs 0.23 ms per scatter pass on config 2 -- two-key runs, 2048-bin scans and tile histograms
+  // half the size of the keys.)
+  DVL_TRY((run_pass<8, 0, kRank, true>(c, a, 0, tiles, th, st)));
+  DVL_TRY((run_pass<8, 8, kRank, false>(c, a, 1, tiles, th, st)));
+  DVL_TRY((run_pass<8, 16, kRank, false>(c, a, 0, tiles, th, st)));
+  DVL_TRY((run_pass<8, 24, kRank, false>(c, a, 1, tiles, th, st)));
   return DVL_OK;
 }
 
@@ -336,12 +400,10 @@ int launch_segmented_sort(Ctx* c, const SortArgs& a, int* out_buf, cudaStream_t 
   if (a.ldk % 4 != 0) return set_error(c, DVL_ERR_INVALID, "sort pitch must be a multiple of 4");
   DVL_TRY(ensure(c, c->tile_hist, (size_t)a.q * tiles * (1 << kMaxBits) * sizeof(uint32_t)));
   uint32_t* th = (uint32_t*)c->tile_hist.ptr;
-  // 32-bit keys in four LSD passes of 8 bits.  (11+11+10 bits in three passes was measured slower:
-  // 0.33 vs 0.23 ms per scatter pass on config 2 -- 12 ballots per key, two-key runs, 2048-bin scans.)
-  DVL_TRY(run_pass<8>(c, a, 0, true, 0, tiles, th, st));
-  DVL_TRY(run_pass<8>(c, a, 1, false, 8, tiles, th, st));
-  DVL_TRY(run_pass<8>(c, a, 0, false, 16, tiles, th, st));
-  DVL_TRY(run_pass<8>(c, a, 1, false, 24, tiles, th, st));
+  if (sort_rank_mode() == 1)
+    DVL_TRY(sort_passes<1>(c, a, tiles, th, st));
+  else
+    DVL_TRY(sort_passes<0>(c, a, tiles, th, st));
   *out_buf = 0;
   return DVL_OK;
 }
