@@ -633,6 +633,10 @@ DVL_API int dvl_eval_ranking(dvl_ctx* c, const void* gallery, int gdt, const voi
   dvl::StreamPlan plan;
   const bool stream_route = out_scores == nullptr && dvl::plan_stream(n, q, top_n, flags, &plan);
   if (stream_route) {
+    {   // the ranked lists hold up to sort_cap rows, which can exceed n on a small forced-stream gallery
+      dvl::StageScope scope(c, DVL_STAGE_PREP, st);
+      DVL_TRY(dvl::ensure_metric_tables(c, (int64_t)plan.sort_cap + 2, st));
+    }
     dvl::Operands op;
     DVL_TRY(dvl::prepare_operands(c, gallery, gdt, queries, qdt, n, d, q, precision, flags, &op, st));
     DVL_TRY(dvl::stream_topk(c, op, labels, n, 0, d, q, top_n, plan, out_ranked_idx, ranked_cap, st));

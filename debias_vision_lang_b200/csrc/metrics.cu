@@ -152,17 +152,29 @@ sub_counts_kernel(const uint8_t* __restrict__ labs, int64_t ldl, const int32_t* 
   const long long begin = (long long)sub * kSub;
   long long end = begin + kSub;
   if (end > m) end = m;
-  // the row pitch is a multiple of 256 and kSub of 4: 4-byte label loads are aligned
+  // the row pitch is a multiple of 256 and kSub of 16: 16-byte label loads are aligned and stay inside
+  // the row's padding; both loads of a lane (the whole slice of the warp) are in flight together
   const uint8_t* lab = labs + (int64_t)q * ldl;
+  uint32_t w[8];
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    const long long r0 = begin + 512 * h + 16 * lane;
+    uint4 v = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu);   // labels past the end match no class
+    if (r0 < end) v = __ldg(reinterpret_cast<const uint4*>(lab + r0));
+    w[4 * h] = v.x; w[4 * h + 1] = v.y; w[4 * h + 2] = v.z; w[4 * h + 3] = v.w;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const long long left = end - (r0 + 4 * k);
+      if (left < 4) w[4 * h + k] |= (left <= 0) ? 0xFFFFFFFFu : (0xFFFFFFFFu << (8 * (int)left));
+    }
+  }
   uint32_t cnt[C];
 #pragma unroll
-  for (int c = 0; c < C; ++c) cnt[c] = 0;
-  for (long long r0 = begin + 4 * lane; r0 < end; r0 += 128) {
-    uint32_t four = __ldg(reinterpret_cast<const uint32_t*>(lab + r0));
-    const int valid = (end - r0 >= 4) ? 4 : (int)(end - r0);
-    if (valid < 4) four |= 0xFFFFFFFFu << (8 * valid);      // labels past the end match no class
+  for (int c = 0; c < C; ++c) {
+    uint32_t acc = 0;
 #pragma unroll
-    for (int c = 0; c < C; ++c) cnt[c] += __popc(__vcmpeq4(four, 0x01010101u * c)) >> 3;
+    for (int k = 0; k < 8; ++k) acc += __popc(__vcmpeq4(w[k], 0x01010101u * c));
+    cnt[c] = acc >> 3;
   }
 #pragma unroll
   for (int c = 0; c < C; ++c) {
@@ -206,9 +218,18 @@ struct PartialParams {
   double* partial;                        // [q][subs][2]
 };
 
+// One warp per 1024-row sub-slice, eight rounds of 128 rows: a lane owns four consecutive ranked rows
+// (one 32-bit label load).  The class counts of a lane's rows are packed as 8-bit fields of 64-bit
+// words (classes 0-7, 8-15); ONE inclusive warp scan of those words gives every lane the number of
+// rows of each class in the lanes before it (a round holds 128 rows, a field at most 128), so the
+// own-class prefix count of a row -- the only thing NDKL needs from the ranking -- costs a field
+// extract instead of a ballot per class.  The running per-class base of the warp lives in shared
+// memory (it is indexed by the label).
 template <int C>
 __global__ void __launch_bounds__(32 * kWarpsPerCta) ndkl_partial_kernel(const PartialParams p) {
+  constexpr int W = (C + 7) / 8;
   __shared__ double ln_d[kMaxClasses];
+  __shared__ uint32_t s_base[kWarpsPerCta][kMaxClasses];
   if (threadIdx.x < kMaxClasses) {
     double v = 0.0;
     if (threadIdx.x < C) {
@@ -220,7 +241,8 @@ __global__ void __launch_bounds__(32 * kWarpsPerCta) ndkl_partial_kernel(const P
   }
   __syncthreads();
   const int q = blockIdx.y;
-  const int sub = blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5);
+  const int warp = threadIdx.x >> 5;
+  const int sub = blockIdx.x * kWarpsPerCta + warp;
   const int lane = threadIdx.x & 31;
   if (sub >= p.subs) return;
   const long long m = p.ranked_len[q];
@@ -231,28 +253,69 @@ __global__ void __launch_bounds__(32 * kWarpsPerCta) ndkl_partial_kernel(const P
   if (begin < end) {
     const uint8_t* lab = p.labs + (int64_t)q * p.ldl;
     const uint32_t* pref = p.sub_pref + ((int64_t)q * (p.subs + 1) + sub) * kMaxClasses;
-    uint32_t base[C];
-#pragma unroll
-    for (int c = 0; c < C; ++c) base[c] = pref[c];
+    uint32_t* base = s_base[warp];
+    if (lane < kMaxClasses) base[lane] = pref[lane];
+    __syncwarp();
     const double pwi_m = __ldg(p.pwi + m);
-    const uint32_t le_mask = (lane == 31) ? 0xffffffffu : ((2u << lane) - 1u);
-#pragma unroll 2
-    for (long long r0 = begin; r0 < end; r0 += 32) {
-      const long long r = r0 + lane;                 // 0-based rank; row j = r + 1
-      const bool ok = r < end;
-      const int l = ok ? (int)__ldg(lab + r) : 255;
-      uint32_t t = 0;                                // this row is the t-th of its class
+    for (long long r0 = begin; r0 < end; r0 += 128) {
+      const long long r = r0 + 4 * lane;             // 0-based rank of this lane's first row
+      const int valid = (end - r >= 4) ? 4 : (end > r ? (int)(end - r) : 0);
+      uint32_t four = 0;
+      double2 pa = make_double2(0.0, 0.0), pb = make_double2(0.0, 0.0);
+      if (valid > 0) {                               // the label pitch is padded to 256, the tables to len + 1024
+        four = __ldg(reinterpret_cast<const uint32_t*>(lab + r));
+        pa = __ldg(reinterpret_cast<const double2*>(p.pwi + r));
+        pb = __ldg(reinterpret_cast<const double2*>(p.pwi + r + 2));
+      }
+      unsigned long long own[W];
 #pragma unroll
-      for (int c = 0; c < C; ++c) {
-        const uint32_t mask = __ballot_sync(0xffffffffu, l == c);
-        if (l == c) t = base[c] + __popc(mask & le_mask);
-        base[c] += __popc(mask);
+      for (int w = 0; w < W; ++w) own[w] = 0ull;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const uint32_t l = (four >> (8 * k)) & (kMaxClasses - 1);   // labels >= C are rejected by the caller
+        if (k < valid) {
+          if (W == 1 || l < 8) own[0] += 1ull << (8 * (l & 7));
+          else own[W - 1] += 1ull << (8 * (l & 7));
+        }
       }
-      if (ok) {
-        const double tj = pwi_m - __ldg(p.pwi + r);  // PWI[m] - PWI[j-1]
-        acc_eq = fma(tj, __ldg(p.dxl + t), acc_eq);
-        acc_d = fma(tj, ln_d[l], acc_d);
+      unsigned long long incl[W];
+#pragma unroll
+      for (int w = 0; w < W; ++w) {
+        incl[w] = own[w];
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+          const unsigned long long o = __shfl_up_sync(0xffffffffu, incl[w], off);
+          if (lane >= off) incl[w] += o;
+        }
       }
+      unsigned long long run[W];                     // rows of each class before this lane's next row
+#pragma unroll
+      for (int w = 0; w < W; ++w) run[w] = incl[w] - own[w];
+      const double pw4[4] = {pa.x, pa.y, pb.x, pb.y};
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        if (k < valid) {
+          const uint32_t l = (four >> (8 * k)) & (kMaxClasses - 1);
+          const int sh = 8 * (l & 7);
+          const bool hi = (W > 1) && l >= 8;
+          const uint32_t before = (uint32_t)((hi ? run[W - 1] : run[0]) >> sh) & 0xFFu;
+          if (hi) run[W - 1] += 1ull << sh; else run[0] += 1ull << sh;
+          const uint32_t t = base[l] + before + 1u;  // this row is the t-th of its class
+          const double tj = pwi_m - pw4[k];          // PWI[m] - PWI[j-1], j = r + k + 1
+          acc_eq = fma(tj, __ldg(p.dxl + t), acc_eq);
+          acc_d = fma(tj, ln_d[l], acc_d);
+        }
+      }
+      __syncwarp();
+      {                                              // lane 31's inclusive scan = the round's class totals
+        unsigned long long tot = __shfl_sync(0xffffffffu, incl[0], 31);
+        if (W > 1) {
+          const unsigned long long tot_hi = __shfl_sync(0xffffffffu, incl[W - 1], 31);
+          if (lane >= 8) tot = tot_hi;
+        }
+        if (lane < C) base[lane] += (uint32_t)(tot >> (8 * (lane & 7))) & 0xFFu;
+      }
+      __syncwarp();
     }
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) {
@@ -302,15 +365,25 @@ struct FinalParams {
 };
 
 __global__ void __launch_bounds__(128) finalize_kernel(const FinalParams p) {
-  const int qi = blockIdx.x * blockDim.x + threadIdx.x;
+  // one warp per query: lanes sum the sub-slice partials in a fixed order (stride 32, then a
+  // butterfly), lane 0 finishes NDKL and computes MaxSkew
+  const int qi = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
   if (qi >= p.q) return;
   const long long m = p.ranked_len[qi];
   double s_eq = 0.0, s_dp = 0.0;
-  const double* part = p.partial + (int64_t)qi * p.subs * 2;
-  for (int s = 0; s < p.subs; ++s) {
-    s_eq += part[2 * s];
-    s_dp += part[2 * s + 1];
+  const double2* part = reinterpret_cast<const double2*>(p.partial) + (int64_t)qi * p.subs;
+  for (int s = lane; s < p.subs; s += 32) {
+    const double2 v = __ldg(part + s);
+    s_eq += v.x;
+    s_dp += v.y;
   }
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) {
+    s_eq += __shfl_xor_sync(0xffffffffu, s_eq, off);
+    s_dp += __shfl_xor_sync(0xffffffffu, s_dp, off);
+  }
+  if (lane != 0) return;
   int c_present = 0;
   for (int c = 0; c < p.n_classes; ++c) c_present += (p.class_counts[c] > 0);
   const double z = p.pw[p.top_n];
@@ -374,8 +447,10 @@ __global__ void __launch_bounds__(256) copy_ranked_kernel(const int32_t* __restr
 }  // namespace
 
 int ensure_metric_tables(Ctx* c, int64_t len, cudaStream_t st) {
-  if (len <= c->log_tab_len) return DVL_OK;
-  const int64_t want = len + len / 8 + 1024;
+  // ndkl_partial_kernel reads PWI in aligned groups of four: the tables keep 4 entries of slack and
+  // a length that is a multiple of 4 (the four tables sit back to back)
+  if (len + 4 <= c->log_tab_len) return DVL_OK;
+  const int64_t want = (len + len / 8 + 1024 + 3) / 4 * 4;
   const int64_t chunks = (want + kTabChunk - 1) / kTabChunk;
   DVL_TRY(ensure(c, c->log_tab, (size_t)want * 4 * sizeof(double)));
   DVL_TRY(ensure(c, c->tab_chunks, (size_t)chunks * 3 * sizeof(double)));
@@ -396,7 +471,7 @@ int launch_metrics(Ctx* c, const MetricArgs& a, cudaStream_t st) {
   if (a.n_classes < 1 || a.n_classes > kMaxClasses) return set_error(c, DVL_ERR_INVALID, "n_classes out of range");
   if (a.top_n < 1) return set_error(c, DVL_ERR_INVALID, "top_n must be >= 1");
   const int64_t tab_need = (a.n_avail > a.top_n ? a.n_avail : a.top_n) + 2;
-  if (tab_need > c->log_tab_len) return set_error(c, DVL_ERR_INVALID, "metric tables too short");
+  if (tab_need + 4 > c->log_tab_len) return set_error(c, DVL_ERR_INVALID, "metric tables too short");
   const int64_t tab = c->log_tab_len;
   const double* dxl = (const double*)c->log_tab.ptr;
   const double* pwi = dxl + tab;
@@ -450,7 +525,7 @@ int launch_metrics(Ctx* c, const MetricArgs& a, cudaStream_t st) {
   f.pw = pw;
   f.pwl = pwl;
   f.per_query = a.per_query;
-  finalize_kernel<<<(a.q + 127) / 128, 128, 0, st>>>(f);
+  finalize_kernel<<<(a.q + 3) / 4, 128, 0, st>>>(f);
   DVL_LAUNCH_CHECK(c, "finalize_kernel");
   return DVL_OK;
 }

@@ -306,7 +306,7 @@ tile_scatter_body(const uint32_t* __restrict__ keys_in, const uint8_t* __restric
 }
 
 template <int BITS, int SHIFT, int kRank, bool kFirst, bool kHasIdx>
-__global__ void __launch_bounds__(kSortThreads, 3)
+__global__ void __launch_bounds__(kSortThreads, kRank == 2 ? 4 : 3)
 tile_scatter_kernel(const uint32_t* __restrict__ keys_in, const uint8_t* __restrict__ labs_in,
                     const int32_t* __restrict__ idx_in, const uint8_t* __restrict__ gallery_labels,
                     uint32_t* __restrict__ keys_out, uint8_t* __restrict__ labs_out, int32_t* __restrict__ idx_out,
@@ -322,7 +322,7 @@ tile_scatter_kernel(const uint32_t* __restrict__ keys_in, const uint8_t* __restr
 int sort_rank_mode() {
   static const int mode = [] {
     const char* e = getenv("DVL_SORT_RANK");
-    return (e != nullptr && e[0] == '1') ? 1 : 0;
+    return (e != nullptr && e[0] >= '0' && e[0] <= '2') ? e[0] - '0' : 0;
   }();
   return mode;
 }
@@ -402,6 +402,8 @@ int launch_segmented_sort(Ctx* c, const SortArgs& a, int* out_buf, cudaStream_t 
   uint32_t* th = (uint32_t*)c->tile_hist.ptr;
   if (sort_rank_mode() == 1)
     DVL_TRY(sort_passes<1>(c, a, tiles, th, st));
+  else if (sort_rank_mode() == 2)
+    DVL_TRY(sort_passes<2>(c, a, tiles, th, st));
   else
     DVL_TRY(sort_passes<0>(c, a, tiles, th, st));
   *out_buf = 0;

@@ -109,7 +109,9 @@ def test_fused_normalisation_flags(ctx):
 
 
 @pytest.mark.parametrize("n,q,c,topn", [(10954, 16, 2, 1000), (10954, 8, 2, 10954), (30011, 6, 7, 30011),
-                                        (30011, 6, 9, 500), (4096, 5, 3, 1), (513, 3, 2, 600)])
+                                        (30011, 6, 9, 500), (4096, 5, 3, 1), (513, 3, 2, 600),
+                                        (20483, 4, 16, 20483), (9001, 3, 12, 1027), (1025, 2, 8, 1025),
+                                        (127, 2, 5, 127), (2049, 2, 13, 130)])
 def test_stage_isolation_random_scores(ctx, n, q, c, topn):
     """The CUDA similarities (random, un-tied data) fed back through the oracle's ranking+metrics must
     give the identical ranked index lists and metrics."""
