@@ -306,7 +306,7 @@ tile_scatter_body(const uint32_t* __restrict__ keys_in, const uint8_t* __restric
 }
 
 template <int BITS, int SHIFT, int kRank, bool kFirst, bool kHasIdx>
-__global__ void __launch_bounds__(kSortThreads, kRank == 2 ? 4 : 3)
+__global__ void __launch_bounds__(kSortThreads, 4)   // 64 registers: 32 of the SM's 64 warp slots
 tile_scatter_kernel(const uint32_t* __restrict__ keys_in, const uint8_t* __restrict__ labs_in,
                     const int32_t* __restrict__ idx_in, const uint8_t* __restrict__ gallery_labels,
                     uint32_t* __restrict__ keys_out, uint8_t* __restrict__ labs_out, int32_t* __restrict__ idx_out,
@@ -322,7 +322,7 @@ tile_scatter_kernel(const uint32_t* __restrict__ keys_in, const uint8_t* __restr
 int sort_rank_mode() {
   static const int mode = [] {
     const char* e = getenv("DVL_SORT_RANK");
-    return (e != nullptr && e[0] >= '0' && e[0] <= '2') ? e[0] - '0' : 0;
+    return (e != nullptr && e[0] == '1') ? 1 : 0;
   }();
   return mode;
 }
@@ -369,9 +369,13 @@ int run_pass(Ctx* c, const SortArgs& a, int cur, int tiles, uint32_t* th, cudaSt
 
 template <int kRank>
 int sort_passes(Ctx* c, const SortArgs& a, int tiles, uint32_t* th, cudaStream_t st) {
-  // 32-bit keys in four LSD passes of 8 bits.  (11+11+10 bits in three passes was measured slower:
-  // 0.33 vs 0.23 ms per scatter pass on config 2 -- two-key runs, 2048-bin scans and tile histograms
-  // half the size of the keys.)
+  // 32-bit keys in four LSD passes of 8 bits.  Measured alternatives (config 2):
+  //  * 11+11+10 bits in three passes: 0.33 vs 0.23 ms per scatter pass -- two-key runs, 2048-bin scans
+  //    and tile histograms half the size of the keys;
+  //  * one up-front digit histogram + decoupled look-back between the tiles of a pass instead of the
+  //    per-pass histogram and scan kernels: saves 0.11 ms of histogram/scan time but the look-back adds
+  //    0.09-0.19 ms to the scatter (a tile lives ~7 us; a published count takes ~1.5 us to become
+  //    visible behind the SM's own scatter stores), so it was not kept.
   DVL_TRY((run_pass<8, 0, kRank, true>(c, a, 0, tiles, th, st)));
   DVL_TRY((run_pass<8, 8, kRank, false>(c, a, 1, tiles, th, st)));
   DVL_TRY((run_pass<8, 16, kRank, false>(c, a, 0, tiles, th, st)));
@@ -402,8 +406,6 @@ int launch_segmented_sort(Ctx* c, const SortArgs& a, int* out_buf, cudaStream_t 
   uint32_t* th = (uint32_t*)c->tile_hist.ptr;
   if (sort_rank_mode() == 1)
     DVL_TRY(sort_passes<1>(c, a, tiles, th, st));
-  else if (sort_rank_mode() == 2)
-    DVL_TRY(sort_passes<2>(c, a, tiles, th, st));
   else
     DVL_TRY(sort_passes<0>(c, a, tiles, th, st));
   *out_buf = 0;
