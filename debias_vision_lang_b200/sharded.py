@@ -103,19 +103,47 @@ def _query_slice(q: int, world: int, rank: int) -> Tuple[int, int]:
     return lo, min(q, lo + block) - lo
 
 
+# Packed list length learnt by a (world, Q, top_n, shard size) configuration whose speculative length
+# was once too short (tie-heavy or label-sorted galleries): later calls start from it.
+_learnt_list_len: Dict[tuple, int] = {}
+
+
+def speculative_list_len(top_n: int, rows_per_shard: int, n_global: int) -> int:
+    """Rows of a shard expected among the global top_n (mu = top_n * shard / gallery) plus six
+    binomial sigmas and a margin, rounded up to 8 entries.  Only a starting point: the true maximum
+    travels with the results and a too-short guess is repaired by a second exchange."""
+    mu = top_n * min(1.0, rows_per_shard / max(1, n_global))
+    return int(-(-math.ceil(mu + 6.0 * math.sqrt(mu) + 32.0) // 8) * 8)
+
+
 def evaluate_sharded(ctx, comm, gallery_local: torch.Tensor, queries: torch.Tensor, labels_local_u8: torch.Tensor,
                      index_base: int, n_global: int, n_classes: int, top_n: int, opts: Optional[dict] = None,
                      ranked_cap: int = 0) -> Dict[str, object]:
     """One rank's part of the sharded evaluation.  Returns the same dict on every rank:
-    ``{"maxskew": {...}, "ndkl": {...}, "per_query": [Q,4] f64, "ranked_len": [Q] i32, "n_flagged": int}``."""
+    ``{"maxskew": {...}, "ndkl": {...}, "per_query": [Q,4] f64, "ranked_len": [Q] i32, "n_flagged": int}``.
+
+    Three collectives and ONE host synchronisation on the usual path: everything is enqueued behind the
+    local similarity GEMM, so launch and collective set-up latencies hide under it.
+
+    1. all-gather of the per-shard statistics (thresholds, overflow flags, label histogram -- one packed
+       buffer), reduced locally: tau = max over shards, histogram = sum;
+    2. all-gather of the trimmed candidate lists, packed to a *speculative* common length (the exact
+       one would need a host round trip in the middle of the pipeline);
+    3. all-gather of the per-query results of every rank's query slice, together with the list length
+       each rank really needed.
+    The host then reads the four means and a status word; only if a list was longer than the guess
+    (or a tie run overflowed a list) is there a second, exact round."""
     precision, flags = _flags_and_precision(opts)
     world, rank = comm.world, comm.rank
     q = queries.shape[0]
     if top_n < 1:
         raise ZeroDivisionError("top_n must be >= 1")
+    dev = queries.device
+    rows_per_shard = shard_bounds(n_global, world, 0)[1]
+    key = (world, q, int(top_n), rows_per_shard, n_global)
+    length = _learnt_list_len.get(key) or speculative_list_len(top_n, rows_per_shard, n_global)
 
     # 1. local streaming top-k (a rank may own no rows when the gallery is tiny)
-    dev = queries.device
     have_rows = gallery_local.shape[0] > 0
     if have_rows:
         tau, oflags, counts, _ = ctx.shard_topk(gallery_local, queries, labels_local_u8, index_base, n_classes,
@@ -124,41 +152,61 @@ def evaluate_sharded(ctx, comm, gallery_local: torch.Tensor, queries: torch.Tens
         tau = torch.full((q,), float("-inf"), dtype=torch.float32, device=dev)
         oflags = torch.zeros((q,), dtype=torch.int32, device=dev)
         counts = torch.zeros((_capi.MAX_CLASSES + 1,), dtype=torch.int64, device=dev)
-    tau = comm.all_reduce_max(tau)
-    counts = comm.all_reduce_sum(counts)
-    oflags = comm.all_reduce_max(oflags)
-    # 2. what can still rank globally
-    cnt = ctx.shard_trim(tau) if have_rows else torch.zeros((q,), dtype=torch.int32, device=dev)
-    length = comm.all_reduce_max(cnt.max().reshape(1).to(torch.int64))
-    length = max(1, int(length.item()))
-    # 3. exchange
-    packed = ctx.shard_pack(cnt, length) if have_rows else torch.full((q, length), -1, dtype=torch.int64, device=dev)
-    gathered = comm.all_gather(packed)                      # [world, Q, len]
-    # 4. merge this rank's slice of the queries
+    stats = comm.all_gather(torch.cat([tau.view(torch.int32), oflags.view(torch.int32), counts.view(torch.int32)]))
+    tau = stats[:, :q].view(torch.float32).max(dim=0).values.contiguous()   # no row below it can rank globally
+    oflags = stats[:, q:2 * q].max(dim=0).values
+    counts = stats[:, 2 * q:].contiguous().view(torch.int64).sum(dim=0)
+
     q0, qn = _query_slice(q, world, rank)
     block = -(-q // world)
-    per_query_blk = torch.zeros((block, 4), dtype=torch.float64, device=queries.device)
-    ranked_len_blk = torch.zeros((block,), dtype=torch.int32, device=queries.device)
-    flags_blk = torch.zeros((block,), dtype=torch.int32, device=queries.device)
-    idx_blk = torch.full((block, ranked_cap), -1, dtype=torch.int32, device=queries.device) if ranked_cap else None
-    if qn > 0:
-        res = ctx.merge_topk(gathered, q0, qn, n_global, counts[:_capi.MAX_CLASSES].contiguous(), n_classes, top_n,
-                             ranked_cap)
-        per_query_blk[:qn] = res["per_query"]
-        ranked_len_blk[:qn] = res["ranked_len"]
-        flags_blk[:qn] = res["flags"]
-        if ranked_cap:
-            idx_blk[:qn] = res["ranked_idx"]
-    per_query = comm.all_gather(per_query_blk).reshape(-1, 4)[:q].contiguous()
-    ranked_len = comm.all_gather(ranked_len_blk).reshape(-1)[:q].contiguous()
-    merge_flags = comm.all_gather(flags_blk).reshape(-1)[:q]
-    ranked_idx = comm.all_gather(idx_blk).reshape(-1, ranked_cap)[:q].contiguous() if ranked_cap else None
+
+    def exchange_and_merge(length: int):
+        # 2. what can still rank globally, packed to `length` entries per query
+        if have_rows:
+            cnt = ctx.shard_trim(tau)
+            need = cnt.max().to(torch.float64)
+            packed = ctx.shard_pack(cnt, length)
+        else:
+            need = torch.zeros((), dtype=torch.float64, device=dev)
+            packed = torch.full((q, length), -1, dtype=torch.int64, device=dev)
+        gathered = comm.all_gather(packed)                  # [world, Q, length]
+        # 3. merge this rank's slice of the queries; results + the length this rank needed in one buffer
+        results = torch.zeros((block + 1, 6), dtype=torch.float64, device=dev)
+        idx_blk = torch.full((block, ranked_cap), -1, dtype=torch.int32, device=dev) if ranked_cap else None
+        if qn > 0:
+            res = ctx.merge_topk(gathered, q0, qn, n_global, counts[:_capi.MAX_CLASSES].contiguous(), n_classes,
+                                 top_n, ranked_cap)
+            results[:qn, :4] = res["per_query"]
+            results[:qn, 4] = res["ranked_len"]
+            results[:qn, 5] = res["flags"]
+            if ranked_cap:
+                idx_blk[:qn] = res["ranked_idx"]
+        results[block, 0] = need
+        everything = comm.all_gather(results)               # [world, block + 1, 6]
+        per_query = everything[:, :block, :4].reshape(-1, 4)[:q].contiguous()
+        ranked_len = everything[:, :block, 4].reshape(-1)[:q].to(torch.int32)
+        merge_flags = everything[:, :block, 5].reshape(-1)[:q]
+        need_max = everything[:, block, 0].max()
+        ranked_idx = comm.all_gather(idx_blk).reshape(-1, ranked_cap)[:q].contiguous() if ranked_cap else None
+        return per_query, ranked_len, merge_flags, need_max, ranked_idx
+
+    per_query, ranked_len, merge_flags, need_max, ranked_idx = exchange_and_merge(length)
     flag_mask = (oflags != 0) | (merge_flags != 0)
-    status = torch.stack([flag_mask.any().to(torch.int64), counts[_capi.MAX_CLASSES]])
-    mean = ctx.mean(per_query)                # the path's second (and last) host synchronisation
-    any_flag, bad_label = (int(x) for x in status.tolist())
+    status = torch.stack([flag_mask.any().to(torch.float64), counts[_capi.MAX_CLASSES].to(torch.float64), need_max])
+    mean = ctx.mean(per_query)                # the path's host synchronisation
+    any_flag, bad_label, need_max = (int(x) for x in status.tolist())
     if bad_label:
         raise _capi.DvlError(-1, f"a label is >= n_classes ({n_classes})")
+    if need_max > length:
+        # a shard holds more of the global top_n than the guess allowed for (every rank sees the same
+        # need_max, so every rank takes this branch): exchange again with the exact length and remember it
+        length = int(-(-need_max // 8) * 8)
+        _learnt_list_len[key] = max(length, _learnt_list_len.get(key, 0))
+        per_query, ranked_len, merge_flags, _, ranked_idx = exchange_and_merge(length)
+        flag_mask = (oflags != 0) | (merge_flags != 0)
+        status = flag_mask.any().to(torch.float64).reshape(1)
+        mean = ctx.mean(per_query)
+        any_flag = int(status.tolist()[0])
     n_flagged = 0
     # 5. exact re-rank of flagged queries (tie run longer than a candidate list); rare
     if any_flag:

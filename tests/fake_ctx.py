@@ -62,7 +62,7 @@ class FakeCtx:
     def shard_pack(self, cnt, length):
         out = torch.full((len(self.lists), length), -1, dtype=torch.int64)
         for i, lst in enumerate(self.lists):
-            for j in range(int(cnt[i])):
+            for j in range(min(int(cnt[i]), length)):      # a too-short speculative length truncates
                 out[i, j] = _to_i64(lst[j][1])
         return out
 

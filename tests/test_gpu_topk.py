@@ -155,7 +155,7 @@ def test_pilot_threshold_route_is_exact(ctx):
 
 
 def test_pilot_threshold_starvation_is_caught_and_reranked(ctx):
-    """Adversarial for the pilot sample: the high scores sit exactly on the sampled rows (every 4th), so the
+    """Adversarial for the pilot sample: the high scores sit exactly on the sampled rows (every 18th), so the
     sample's threshold keeps fewer than top_n rows.  The final select must notice and the query must be
     re-ranked exactly."""
     n, d, q, k = 300_000, 32, 6, 1000
@@ -165,8 +165,9 @@ def test_pilot_threshold_starvation_is_caught_and_reranked(ctx):
     t[:, 0] = 1.0
     t[1:, 1:] = (rng.randint(-3, 4, size=(q - 1, d - 1)) / 64.0).astype(np.float32)
     g[:, 0] = (rng.randint(0, 64, size=n) / 64.0)          # base scores 0..1 on the coordinate all queries weigh
-    g[::4, 0] += 8.0                                         # the pilot's rows (step = n // 65536 = 4) tower above
-    g[::4, 0] += (rng.randint(0, 4096, size=len(g[::4])) / 64.0)
+    step = n // 16384                                        # the library's pilot stride (kPilotRows = 16384)
+    g[::step, 0] += 8.0                                      # the pilot's rows tower above
+    g[::step, 0] += (rng.randint(0, 4096, size=len(g[::step])) / 64.0)
     labels = synthetic.make_labels(n, 2, 3)
     lab = torch.from_numpy(labels.astype(np.uint8)).cuda()
     gg, tt = torch.from_numpy(g).cuda(), torch.from_numpy(t).cuda()

@@ -27,6 +27,8 @@ def _worker(rank, world, port, case, out_dir):
         w = synthetic.adversarial(case["n"], 32, case["q"], case["c"], seed=case["seed"], n_shards=world)
         lo, hi = sharded.shard_bounds(case["n"], world, rank)
         comm = sharded.TorchDistComm()
+        if "spec" in case:      # force the speculative list length to be too short: second, exact exchange
+            sharded.speculative_list_len = lambda *a, **k: case["spec"]
         res = sharded.evaluate_sharded(FakeCtx(list_cap=case["cap"]), comm, w.gallery[lo:hi].contiguous(), w.queries,
                                        torch.from_numpy(w.labels[lo:hi].astype(np.uint8)), lo, case["n"], case["c"],
                                        case["topn"], ranked_cap=case["topn"] + 8)
@@ -39,6 +41,7 @@ def _worker(rank, world, port, case, out_dir):
     (2, dict(n=1500, q=6, c=2, topn=40, seed=5, cap=4096)),
     (2, dict(n=700, q=5, c=3, topn=25, seed=6, cap=48)),       # small lists: tie-overflow -> flagged re-rank
     (3, dict(n=300, q=4, c=2, topn=10, seed=7, cap=4096)),      # 256-row blocks: rank 2 owns no rows
+    (2, dict(n=1500, q=6, c=2, topn=40, seed=8, cap=4096, spec=8)),   # guess too short -> re-exchange
 ])
 def test_sharded_protocol_gloo(tmp_path, world, case):
     port = 29500 + (os.getpid() % 2000)
@@ -61,6 +64,8 @@ def test_sharded_protocol_gloo(tmp_path, world, case):
         assert torch.equal(res["per_query"], outs[0]["per_query"])
     if case["cap"] < 100:
         assert outs[0]["n_flagged"] > 0
+    if "spec" in case:
+        assert all(o["list_len"] > case["spec"] for o in outs)
 
 
 def test_shard_bounds_cover_the_gallery():
