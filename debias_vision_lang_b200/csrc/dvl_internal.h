@@ -43,6 +43,13 @@ struct Ctx {
   // driver entry point for tensor-map encoding (resolved once, no -lcuda link dependency)
   void* encode_tiled = nullptr;
   bool gemm_attr_set = false;
+  // CUDA-graph replay of the full-sort route (api.cu run_full_sort)
+  uint64_t ws_generation = 0;              // bumped by every workspace (re)allocation
+  std::vector<uint8_t> warm_key, graph_key;
+  uint64_t warm_generation = 0, graph_generation = 0, graph_launches = 0;
+  cudaGraphExec_t graph_exec = nullptr;
+  cudaStream_t own_stream = nullptr;
+  cudaEvent_t fence_event = nullptr;
   // per-stage CUDA-event timing (dvl_set_profiling / dvl_get_profile)
   bool profiling = false;
   struct ProfRec { int stage; cudaEvent_t e0, e1; uint64_t launches; };

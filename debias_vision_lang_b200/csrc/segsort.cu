@@ -356,8 +356,8 @@ int run_pass(Ctx* c, const SortArgs& a, int cur, int tiles, uint32_t* th, cudaSt
 #define DVL_SCATTER(IDX)                                                                                          \
   do {                                                                                                            \
     auto kern = tile_scatter_kernel<BITS, SHIFT, kRank, kFirst, IDX>;                                             \
-    const size_t smem = scatter_smem_bytes<BITS, IDX>();                                                          \
-    DVL_CUDA(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));              \
+    constexpr size_t smem = scatter_smem_bytes<BITS, IDX>();                                                      \
+    static_assert(smem <= 48 * 1024, "above 48 KB the kernel needs cudaFuncAttributeMaxDynamicSharedMemorySize"); \
     kern<<<grid, kSortThreads, smem, st>>>(ki, li, ii, a.gallery_labels, ko, lo, io, a.ldk, a.n, tiles, th_q);    \
   } while (0)
     if (has_idx) DVL_SCATTER(true); else DVL_SCATTER(false);

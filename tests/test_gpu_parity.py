@@ -274,3 +274,45 @@ def test_clip_logits_both_sides_normalised():
     assert per_image.shape == (700, 9) and per_text.shape == (9, 700)
     assert (per_image.double() - want).abs().max().item() <= scale * 1e-5
     assert torch.equal(per_text, per_image.t())
+
+
+def test_graph_replay_matches_direct_launches(ctx):
+    """The full-sort route replays a captured CUDA graph from the third identical call on.  Replays must
+    see new contents of the same buffers, survive a differently shaped call in between (workspace
+    growth invalidates the graph) and keep per-stage profiling working."""
+    w = synthetic.clip_like(6000, 64, 9, 3, seed=77, device="cuda")
+    lab = torch.from_numpy(w.labels.astype(np.uint8)).cuda()
+    g, t = w.gallery.clone(), w.queries.clone()
+    out_pq = []
+    for _ in range(4):                                   # direct, capture, replay, replay
+        r = ctx.eval_ranking(g, t, lab, 3, 6000, _capi.PRECISION_FP32, want_per_query=True, ranked_cap=6000)
+        out_pq.append((r["per_query"].clone(), r["ranked_idx"].clone(), list(r["mean"])))
+    for pq, idx, mean in out_pq[1:]:
+        assert torch.equal(pq, out_pq[0][0]) and torch.equal(idx, out_pq[0][1]) and mean == out_pq[0][2]
+    want = spec.measure(w.labels, w.gallery.cpu(), w.queries.cpu(), 1.0)
+    assert np.abs(np.asarray(out_pq[0][2]) - np.asarray(_flat(want))).max() <= METRIC_TOL
+    # same buffers, new contents: a replay must not return the old answer
+    g.copy_(torch.flip(w.gallery, dims=[0]))
+    lab2 = torch.flip(lab, dims=[0]).contiguous()
+    lab.copy_(lab2)
+    r2 = ctx.eval_ranking(g, t, lab, 3, 6000, _capi.PRECISION_FP32, want_per_query=True, ranked_cap=6000)
+    want2 = spec.measure(w.labels[::-1].copy(), torch.flip(w.gallery, dims=[0]).cpu(), w.queries.cpu(), 1.0)
+    assert np.abs(np.asarray(r2["mean"]) - np.asarray(_flat(want2))).max() <= METRIC_TOL
+    # a larger call in between grows the workspace; the small call must still be right afterwards
+    big = synthetic.clip_like(20000, 64, 12, 3, seed=78, device="cuda")
+    ctx.eval_ranking(big.gallery, big.queries, torch.from_numpy(big.labels.astype(np.uint8)).cuda(), 3, 20000,
+                     _capi.PRECISION_FP32)
+    for _ in range(3):
+        r3 = ctx.eval_ranking(g, t, lab, 3, 6000, _capi.PRECISION_FP32, want_per_query=True, ranked_cap=6000)
+        assert torch.equal(r3["per_query"], r2["per_query"]) and torch.equal(r3["ranked_idx"], r2["ranked_idx"])
+    # profiling inside replays
+    ctx.get_profile()
+    ctx.set_profiling(True)
+    try:
+        for _ in range(4):
+            r4 = ctx.eval_ranking(g, t, lab, 3, 6000, _capi.PRECISION_FP32, want_per_query=True, ranked_cap=6000)
+            assert torch.equal(r4["per_query"], r2["per_query"])
+        prof = ctx.get_profile()
+    finally:
+        ctx.set_profiling(False)
+    assert prof["sort_scatter"][0] > 0 and prof["sort_scatter"][1] == 16 and prof["gemm"][1] == 4
