@@ -118,18 +118,89 @@ class EmbeddingGallery(IATDataset):
     """A gallery that already is embeddings: items are ``{"img": embedding, "iat_label": label}`` so
     it can flow through ``get_labels_img_embeddings`` with an identity ``encode_image``; the pair
     (``image_embeddings``, ``iat_labels``) fills the two attributes the reference reserves but never
-    implements (datasets.py:22-23)."""
+    implements (datasets.py:22-23).
 
-    def __init__(self, image_embeddings: torch.Tensor, iat_labels: np.ndarray, iat_type: str = "gender"):
+    ``save`` / ``load`` are the on-disk form of that pair -- the ``use_cache`` the reference reserves
+    (datasets.py:26) -- and the wire format that feeds gallery shards: a directory with
+
+    * ``embeddings.npy``  [N, D] row-major, float32 / float16, or uint16 holding bfloat16 bit patterns;
+    * ``labels.npy``      [N] uint8 class codes 0..C-1, in gallery (tie-break) order;
+    * ``meta.json``       format tag, N, D, dtype, iat_type, n_classes.
+
+    ``load(rank, world)`` memory-maps the files and reads only that rank's contiguous row block
+    (``sharded.shard_bounds``: 256-row aligned), so a 10 M-row gallery never passes through one host
+    buffer; ``index_base`` / ``n_global`` are what ``sharded.evaluate_sharded`` needs."""
+
+    FORMAT = "dvl-gallery/1"
+
+    def __init__(self, image_embeddings: torch.Tensor, iat_labels: np.ndarray, iat_type: str = "gender",
+                 index_base: int = 0, n_global: Optional[int] = None, n_classes: Optional[int] = None):
         super().__init__()
         assert len(image_embeddings) == len(iat_labels)
         self.image_embeddings = image_embeddings
         self.iat_labels = np.asarray(iat_labels)
         self.iat_type = iat_type
-        self.n_iat_classes = int(len(np.unique(self.iat_labels)))
+        self.n_iat_classes = int(n_classes) if n_classes is not None else int(len(np.unique(self.iat_labels)))
+        self.index_base = int(index_base)
+        self.n_global = int(n_global) if n_global is not None else len(self.iat_labels)
 
     def __getitem__(self, index: int):
         return {"img": self.image_embeddings[index], "iat_label": int(self.iat_labels[index])}
 
     def __len__(self):
         return len(self.iat_labels)
+
+    # ---- on-disk cache ----------------------------------------------------------------------
+    def save(self, path: str) -> str:
+        """Writes the whole (unsharded) gallery to directory ``path``; returns ``path``."""
+        import json
+        if self.index_base != 0 or self.n_global != len(self):
+            raise ValueError("only a whole gallery can be saved (this object is one shard of it)")
+        lab = np.asarray(self.iat_labels)
+        if lab.size and (lab.min() < 0 or lab.max() > 255):
+            raise ValueError("labels must be class codes 0..255")
+        emb = self.image_embeddings.detach().cpu().contiguous()
+        if emb.dtype == torch.bfloat16:
+            arr, dtype = emb.view(torch.int16).numpy().view(np.uint16), "bfloat16"
+        elif emb.dtype in (torch.float16, torch.float32):
+            arr, dtype = emb.numpy(), str(emb.dtype).replace("torch.", "")
+        else:
+            arr, dtype = emb.float().numpy(), "float32"
+        os.makedirs(path, exist_ok=True)
+        np.save(os.path.join(path, "embeddings.npy"), arr)
+        np.save(os.path.join(path, "labels.npy"), lab.astype(np.uint8))
+        meta = {"format": self.FORMAT, "n": int(arr.shape[0]), "d": int(arr.shape[1]), "dtype": dtype,
+                "iat_type": self.iat_type, "n_classes": int(self.n_iat_classes)}
+        with open(os.path.join(path, "meta.json"), "w") as f:      # written last: its presence marks a complete cache
+            json.dump(meta, f)
+        return path
+
+    @staticmethod
+    def is_cached(path: str) -> bool:
+        return os.path.isfile(os.path.join(path, "meta.json"))
+
+    @classmethod
+    def load(cls, path: str, rank: int = 0, world: int = 1, device: Optional[Union[str, torch.device]] = None
+             ) -> "EmbeddingGallery":
+        """Rows ``shard_bounds(N, world, rank)`` of the cached gallery, optionally moved to ``device``."""
+        import json
+        from .sharded import shard_bounds
+        with open(os.path.join(path, "meta.json")) as f:
+            meta = json.load(f)
+        if meta.get("format") != cls.FORMAT:
+            raise ValueError(f"{path}: not a {cls.FORMAT} gallery cache")
+        n = int(meta["n"])
+        lo, hi = shard_bounds(n, world, rank)
+        arr = np.load(os.path.join(path, "embeddings.npy"), mmap_mode="r")
+        lab = np.load(os.path.join(path, "labels.npy"), mmap_mode="r")
+        if arr.shape != (n, int(meta["d"])) or lab.shape != (n,):
+            raise ValueError(f"{path}: array shapes do not match meta.json")
+        block = np.array(arr[lo:hi])                  # a private, writable copy of this rank's rows
+        if meta["dtype"] == "bfloat16":
+            emb = torch.from_numpy(block.view(np.int16)).view(torch.bfloat16)
+        else:
+            emb = torch.from_numpy(block)
+        if device is not None:
+            emb = emb.to(device)
+        return cls(emb, np.array(lab[lo:hi]).astype(np.int64), meta.get("iat_type", "gender"),
+                   index_base=lo, n_global=n, n_classes=int(meta["n_classes"]))

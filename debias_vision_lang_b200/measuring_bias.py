@@ -53,6 +53,9 @@ PROMPT_CONCEPTS = (
 #   topn               overrides measure_bias's top-n (reference: whole gallery, 1.0)
 #   dataset            a ready dataset object instead of FairFace(mode="val", ...)
 #   batch_size / num_workers   DataLoader settings (reference: 256 / 6)
+#   use_cache          directory of an on-disk gallery cache (datasets.EmbeddingGallery.save/load; the
+#                      reference reserves ``use_cache`` but never implements it, datasets.py:26): read if
+#                      present -- the image encoder is then not run at all -- else written after encoding
 DEFAULT_OPTS: dict = dict()
 
 _PRECISIONS = {"fp32": _capi.PRECISION_FP32, "bf16": _capi.PRECISION_BF16}
@@ -269,13 +272,16 @@ def measure_bias(cliplike, img_preproc: Optional[Callable] = None, tokenizer: Op
     """Drop-in for ``debias_clip.measure_bias`` (measuring_bias.py:139-156).  Also accepts the README
     form ``measure_bias(model, attribute=...)`` (README.md:145)."""
     from torch.utils.data import DataLoader
-    from .datasets import FairFace
+    from .datasets import EmbeddingGallery, FairFace
 
     opts = dict(opts or {})
-    ds = opts.get("dataset")
-    if ds is None:
-        ds = FairFace(mode="val", iat_type=attribute, transforms=img_preproc)
-    dl = DataLoader(ds, batch_size=opts.get("batch_size", 256), num_workers=opts.get("num_workers", 6))
+
+    def dl():       # built only when the gallery is not served from the cache
+        ds = opts.get("dataset")
+        if ds is None:
+            ds = FairFace(mode="val", iat_type=attribute, transforms=img_preproc)
+        return DataLoader(ds, batch_size=opts.get("batch_size", 256), num_workers=opts.get("num_workers", 6))
+
     if tokenizer is None:
         try:
             import clip as _clip
@@ -285,7 +291,15 @@ def measure_bias(cliplike, img_preproc: Optional[Callable] = None, tokenizer: Op
 
     prompts: List[str] = gen_prompts()
     device = torch.device("cuda")          # hard-coded in the reference too (:148)
-    labels_list, image_embeddings = get_labels_img_embeddings(dl, cliplike, device, progress=opts.get("progress", False))
+    cache = opts.get("use_cache")
+    if cache and EmbeddingGallery.is_cached(cache):
+        cached = EmbeddingGallery.load(cache, device=device)
+        labels_list, image_embeddings = cached.iat_labels, cached.image_embeddings
+    else:
+        labels_list, image_embeddings = get_labels_img_embeddings(dl(), cliplike, device,
+                                                                  progress=opts.get("progress", False))
+        if cache:
+            EmbeddingGallery(image_embeddings, labels_list, attribute).save(cache)
     prompts_embeddings = get_prompt_embeddings(cliplike, tokenizer, device, prompts)
     both = evaluate(labels_list, image_embeddings, prompts_embeddings, opts.get("topn", 1.0), opts)
     return {"maxskew": dict(both["maxskew"]), "ndkl": dict(both["ndkl"])}

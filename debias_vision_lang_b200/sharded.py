@@ -32,7 +32,8 @@ import torch
 
 from . import _capi
 
-__all__ = ["shard_bounds", "TorchDistComm", "LocalComm", "evaluate_sharded", "measure_sharded"]
+__all__ = ["shard_bounds", "TorchDistComm", "LocalComm", "evaluate_sharded", "evaluate_query_sharded",
+           "measure_sharded", "speculative_list_len"]
 
 
 def shard_bounds(n: int, world: int, rank: int) -> Tuple[int, int]:
@@ -288,6 +289,41 @@ def evaluate_sharded_emulated(contexts: Sequence, gallery: torch.Tensor, queries
            "per_query": per_query, "ranked_len": ranked_len, "n_flagged": int(flagged.numel()), "list_len": length}
     if ranked_cap:
         out["ranked_idx"] = ranked_idx
+    return out
+
+
+def evaluate_query_sharded(ctx, comm, gallery: torch.Tensor, queries: torch.Tensor, labels_u8: torch.Tensor,
+                           n_classes: int, top_n: int, opts: Optional[dict] = None, ranked_cap: int = 0
+                           ) -> Dict[str, object]:
+    """The ``top_n >= N`` regime (the ``measure_bias`` default: the whole gallery is ranked) on several
+    GPUs: queries are independent and the gallery is small (FairFace: 55-222 MB), so every rank holds
+    the whole gallery and ranks a contiguous slice of the queries by the full-sort route.  No data-path
+    collective: one all-gather of the per-query results at the end, then the same fixed-tree mean as on
+    one GPU, so the numbers are bit-identical to the unsharded run.  Also the route for ``top_n`` beyond
+    the streaming top-k's 8192-entry lists."""
+    precision, flags = _flags_and_precision(opts)
+    world, rank = comm.world, comm.rank
+    q = queries.shape[0]
+    q0, qn = _query_slice(q, world, rank)
+    block = -(-q // world)
+    dev = queries.device
+    results = torch.zeros((block, 5), dtype=torch.float64, device=dev)
+    idx_blk = torch.full((block, ranked_cap), -1, dtype=torch.int32, device=dev) if ranked_cap else None
+    if qn > 0:
+        res = ctx.eval_ranking(gallery, queries[q0:q0 + qn].contiguous(), labels_u8, n_classes, top_n, precision,
+                               flags | _capi.FLAG_FULL_SORT, want_per_query=True, ranked_cap=ranked_cap)
+        results[:qn, :4] = res["per_query"]
+        results[:qn, 4] = res["ranked_len"]
+        if ranked_cap:
+            idx_blk[:qn] = res["ranked_idx"]
+    everything = comm.all_gather(results)
+    per_query = everything[:, :, :4].reshape(-1, 4)[:q].contiguous()
+    ranked_len = everything[:, :, 4].reshape(-1)[:q].to(torch.int32)
+    mean = ctx.mean(per_query)
+    out = {"maxskew": {"eq_opp": mean[0], "dem_par": mean[1]}, "ndkl": {"eq_opp": mean[2], "dem_par": mean[3]},
+           "per_query": per_query, "ranked_len": ranked_len, "n_flagged": 0}
+    if ranked_cap:
+        out["ranked_idx"] = comm.all_gather(idx_blk).reshape(-1, ranked_cap)[:q].contiguous()
     return out
 
 

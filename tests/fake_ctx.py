@@ -105,5 +105,10 @@ class FakeCtx:
         return dict(per_query=torch.from_numpy(pq), ranked_len=torch.tensor([len(o) for o in orders], dtype=torch.int32),
                     ranked_idx=ranked_idx, mean=pq.mean(axis=0).tolist())
 
+    def eval_ranking(self, gallery, queries, labels_u8, n_classes, top_n, precision=0, flags=0, want_per_query=False,
+                     ranked_cap=0, want_scores=False):
+        scores = self.similarity(gallery, queries)
+        return self.rank_and_score(scores, labels_u8, n_classes, top_n, ranked_cap)
+
     def mean(self, per_query):
         return [float(x) for x in (per_query.sum(dim=0) / per_query.shape[0]).tolist()]

@@ -233,6 +233,42 @@ def test_measure_bias_drop_in_with_stub_encoders():
     assert max(abs(a - b) for a, b in zip(_flat(got), _flat(want))) <= METRIC_TOL
 
 
+def test_measure_bias_gallery_cache(tmp_path):
+    """opts["use_cache"]: the first call encodes the gallery and writes the cache, the second is served
+    from it without touching the dataset or the image encoder, with the identical result."""
+    from debias_vision_lang_b200.datasets import EmbeddingGallery
+    w = synthetic.clip_like(2000, 32, 319, 7, seed=22)
+
+    class Stub(torch.nn.Module):
+        image_calls = 0
+
+        def encode_image(self, x):
+            Stub.image_calls += 1
+            return x
+
+        def encode_text(self, tok):
+            return w.queries.cuda()[tok]
+
+    tok = lambda prompts: torch.arange(len(prompts))
+    cache = str(tmp_path / "fairface_val_race")
+    first = dvl.measure_bias(Stub(), None, tok, attribute="race",
+                             opts={"dataset": EmbeddingGallery(w.gallery, w.labels, "race"), "num_workers": 0,
+                                   "use_cache": cache})
+    assert Stub.image_calls > 0 and EmbeddingGallery.is_cached(cache)
+    calls = Stub.image_calls
+
+    class NoDataset:
+        def __len__(self):
+            raise AssertionError("the dataset must not be touched when the cache is present")
+
+    second = dvl.measure_bias(Stub(), None, tok, attribute="race",
+                              opts={"dataset": NoDataset(), "num_workers": 0, "use_cache": cache})
+    assert Stub.image_calls == calls
+    assert _flat(first) == _flat(second)
+    want = spec.measure(w.labels, w.gallery, w.queries, 1.0)
+    assert max(abs(a - b) for a, b in zip(_flat(first), _flat(want))) <= METRIC_TOL
+
+
 def test_full_size_properties_cfg2(ctx):
     """BASELINE config 2 at full size (108,501 x 512 x 319, C=7, k=N): size-independent properties.
     dem_par MaxSkew@N is exactly 0 and eq_opp MaxSkew@N = ln(C*max_c n_c/N); every

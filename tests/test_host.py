@@ -109,3 +109,34 @@ def test_synthetic_workloads_are_deterministic_and_exact():
     assert torch.equal(s32.double(), s64)          # exactly representable, any summation order
     adv = synthetic.adversarial(512, 64, 16, 2, seed=6)
     assert float(adv.queries[0].abs().sum()) == 0.0
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float16, torch.bfloat16])
+def test_gallery_cache_round_trip_and_shards(tmp_path, dtype):
+    """EmbeddingGallery.save/load (the `use_cache` the reference reserves, datasets.py:26): bit-exact
+    round trip in every stored dtype, and rank shards that tile the gallery in order."""
+    from debias_vision_lang_b200.sharded import shard_bounds
+    w = synthetic.clip_like(1300, 24, 3, 7, seed=3)
+    emb = w.gallery.to(dtype)
+    path = str(tmp_path / "gallery")
+    assert not datasets.EmbeddingGallery.is_cached(path)
+    datasets.EmbeddingGallery(emb, w.labels, "race").save(path)
+    assert datasets.EmbeddingGallery.is_cached(path)
+    whole = datasets.EmbeddingGallery.load(path)
+    assert whole.image_embeddings.dtype == dtype and torch.equal(whole.image_embeddings, emb)
+    assert np.array_equal(whole.iat_labels, w.labels) and whole.n_iat_classes == 7 and whole.iat_type == "race"
+    assert whole.index_base == 0 and whole.n_global == 1300
+    rows, labs = [], []
+    for world in (3,):
+        for r in range(world):
+            part = datasets.EmbeddingGallery.load(path, rank=r, world=world)
+            lo, hi = shard_bounds(1300, world, r)
+            assert part.index_base == lo and len(part) == hi - lo and part.n_global == 1300
+            assert part.n_iat_classes == 7          # a shard may miss a class; the count is the gallery's
+            rows.append(part.image_embeddings)
+            labs.append(part.iat_labels)
+            with pytest.raises(ValueError):
+                part.save(str(tmp_path / "shard")) if len(part) != 1300 else (_ for _ in ()).throw(ValueError())
+    assert torch.equal(torch.cat(rows), emb) and np.array_equal(np.concatenate(labs), w.labels)
+    item = whole[5]
+    assert torch.equal(item["img"], emb[5]) and item["iat_label"] == int(w.labels[5])

@@ -27,6 +27,12 @@ def _worker(rank, world, port, case, out_dir):
         w = synthetic.adversarial(case["n"], 32, case["q"], case["c"], seed=case["seed"], n_shards=world)
         lo, hi = sharded.shard_bounds(case["n"], world, rank)
         comm = sharded.TorchDistComm()
+        if case.get("route") == "query":      # top_n = N: replicated gallery, query slices
+            res = sharded.evaluate_query_sharded(FakeCtx(), comm, w.gallery, w.queries,
+                                                 torch.from_numpy(w.labels.astype(np.uint8)), case["c"], case["topn"],
+                                                 ranked_cap=case["topn"] + 8)
+            torch.save({k: v for k, v in res.items()}, os.path.join(out_dir, f"rank{rank}.pt"))
+            return
         if "spec" in case:      # force the speculative list length to be too short: second, exact exchange
             sharded.speculative_list_len = lambda *a, **k: case["spec"]
         res = sharded.evaluate_sharded(FakeCtx(list_cap=case["cap"]), comm, w.gallery[lo:hi].contiguous(), w.queries,
@@ -42,6 +48,8 @@ def _worker(rank, world, port, case, out_dir):
     (2, dict(n=700, q=5, c=3, topn=25, seed=6, cap=48)),       # small lists: tie-overflow -> flagged re-rank
     (3, dict(n=300, q=4, c=2, topn=10, seed=7, cap=4096)),      # 256-row blocks: rank 2 owns no rows
     (2, dict(n=1500, q=6, c=2, topn=40, seed=8, cap=4096, spec=8)),   # guess too short -> re-exchange
+    (2, dict(n=400, q=5, c=3, topn=400, seed=9, cap=4096, route="query")),   # whole gallery ranked, query slices
+    (3, dict(n=300, q=2, c=2, topn=300, seed=10, cap=4096, route="query")),  # a rank without queries
 ])
 def test_sharded_protocol_gloo(tmp_path, world, case):
     port = 29500 + (os.getpid() % 2000)
