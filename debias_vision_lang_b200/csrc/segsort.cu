@@ -191,6 +191,13 @@ tile_scatter_body(const uint32_t* __restrict__ keys_in, const uint8_t* __restric
     lab4[r >> 2] |= l << (8 * (r & 3));
     if (kHasIdx) idx[r] = ok ? (kFirst ? (int32_t)(warp_base + r * 32 + lane) : __ldg(idx_in + seg_off + warp_base + r * 32 + lane)) : 0;
   }
+  // this tile's output offsets (used after the ranking): requested now, so their latency is hidden
+  uint32_t my_offs[DPT];
+  {
+    const uint32_t* offs = tile_offs + ((int64_t)q * tiles + t) * RADIX + threadIdx.x * DPT;
+#pragma unroll
+    for (int j = 0; j < DPT; ++j) my_offs[j] = __ldg(offs + j);
+  }
   __syncthreads();
 
   uint32_t rank2[kItems / 2];                   // two 16-bit ranks per register
@@ -263,11 +270,10 @@ tile_scatter_body(const uint32_t* __restrict__ keys_in, const uint8_t* __restric
     uint32_t run = incl - sum;
 #pragma unroll
     for (int w = 0; w < kWarps; ++w) run += (w < warp) ? warp_tot[w] : 0u;
-    const uint32_t* offs = tile_offs + ((int64_t)q * tiles + t) * RADIX + threadIdx.x * DPT;
 #pragma unroll
     for (int j = 0; j < DPT; ++j) {
       const int d = threadIdx.x * DPT + j;
-      out_off[d] = __ldg(offs + j) - run;
+      out_off[d] = my_offs[j] - run;
       uint32_t pos = run;
 #pragma unroll
       for (int w = 0; w < kWarps; ++w) {
@@ -375,7 +381,11 @@ int sort_passes(Ctx* c, const SortArgs& a, int tiles, uint32_t* th, cudaStream_t
   //  * one up-front digit histogram + decoupled look-back between the tiles of a pass instead of the
   //    per-pass histogram and scan kernels: saves 0.11 ms of histogram/scan time but the look-back adds
   //    0.09-0.19 ms to the scatter (a tile lives ~7 us; a published count takes ~1.5 us to become
-  //    visible behind the SM's own scatter stores), so it was not kept.
+  //    visible behind the SM's own scatter stores), so it was not kept;
+  //  * persistent CTAs that prefetch the next tile into a shared-memory staging buffer with
+  //    cp.async.bulk while the current one is ranked: 0.63 vs 0.52 ms for the four passes -- the kernel
+  //    is bound by shared-memory wavefronts (half of them bank conflicts of the digit-indexed counters
+  //    and the scattered tile placement), and staging adds 12 % more of them.
   DVL_TRY((run_pass<8, 0, kRank, true>(c, a, 0, tiles, th, st)));
   DVL_TRY((run_pass<8, 8, kRank, false>(c, a, 1, tiles, th, st)));
   DVL_TRY((run_pass<8, 16, kRank, false>(c, a, 0, tiles, th, st)));
