@@ -352,6 +352,14 @@ def run_ours(args):
         e2e_api = "sharded.evaluate_sharded after an H2D copy of the local gallery shard from pinned memory"
     e2e_value = pairs_per_step * args.steps / (e2e_ms * 1e-3)
 
+    # slowest rank per stage: the step waits for it at the first collective (power-capped GPUs differ)
+    stage_ms_max = None
+    if world > 1:
+        names = sorted(profile)
+        tv = torch.tensor([profile[k][0] / args.steps for k in names], dtype=torch.float64, device=dev)
+        dist.all_reduce(tv, op=dist.ReduceOp.MAX)
+        stage_ms_max = dict(zip(names, tv.tolist()))
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -416,7 +424,7 @@ def run_ours(args):
         "data": "synthetic (seeded CLIP-like embeddings and labels; no FairFace/CLIP weights offline)",
         "config": workload_description(args.workload, w, precision, world, gallery_sharded, n_global),
         "roofline": roof,
-        "stage_ms": stage_ms, "stage_launches": stage_launches,
+        "stage_ms": stage_ms, "stage_launches": stage_launches, "stage_ms_max_over_ranks": stage_ms_max,
         "cpu_baseline": cpu,
         "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_ms / args.steps,
                 "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 32 * world, "api": e2e_api},
