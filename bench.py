@@ -54,7 +54,9 @@ def load_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
+    """SM clock and clock-event (throttle) reasons sampled DURING the timed region: NVML polled every
+    2 ms from a background thread (the timed region of the small workloads lasts tens of milliseconds,
+    too short for `nvidia-smi -lms`), with `nvidia-smi` at 200 ms as the fallback."""
     FIELDS = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
               "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
               "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
@@ -63,8 +65,42 @@ class ClockSampler:
         self.gpu = gpu_index
         self.proc = None
         self.lines = []
+        self.nvml = None
+        self.samples = []          # (sm MHz, reasons bitmask)
+        self.stop_flag = threading.Event()
+        self.sm_max = None
+
+    def _nvml_handle(self):
+        import pynvml
+        pynvml.nvmlInit()
+        try:
+            props = torch.cuda.get_device_properties(self.gpu)
+            bus_id = f"{props.pci_domain_id:08X}:{props.pci_bus_id:02X}:{props.pci_device_id:02X}.0"
+            handle = pynvml.nvmlDeviceGetHandleByPciBusId(bus_id.encode())
+        except Exception:
+            handle = pynvml.nvmlDeviceGetHandleByIndex(self.gpu)
+        return pynvml, handle
+
+    def _poll(self, pynvml, handle):
+        while not self.stop_flag.is_set():
+            try:
+                sm = pynvml.nvmlDeviceGetClockInfo(handle, pynvml.NVML_CLOCK_SM)
+                reasons = pynvml.nvmlDeviceGetCurrentClocksEventReasons(handle)
+                self.samples.append((float(sm), int(reasons)))
+            except Exception:
+                pass
+            time.sleep(0.002)
 
     def start(self):
+        try:
+            pynvml, handle = self._nvml_handle()
+            self.sm_max = float(pynvml.nvmlDeviceGetMaxClockInfo(handle, pynvml.NVML_CLOCK_SM))
+            self.nvml = pynvml
+            self.t = threading.Thread(target=self._poll, args=(pynvml, handle), daemon=True)
+            self.t.start()
+            return
+        except Exception:
+            self.nvml = None
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "200",
@@ -79,6 +115,22 @@ class ClockSampler:
             self.lines.append(line.strip())
 
     def stop(self):
+        if self.nvml is not None:
+            self.stop_flag.set()
+            self.t.join(timeout=1.0)
+            if not self.samples:
+                return dict(sm_mhz=None, sm_max_mhz=self.sm_max, reasons=["no samples"])
+            p = self.nvml
+            names = {"hw_slowdown": p.nvmlClocksEventReasonHwSlowdown,
+                     "hw_thermal_slowdown": p.nvmlClocksEventReasonHwThermalSlowdown,
+                     "sw_thermal_slowdown": p.nvmlClocksEventReasonSwThermalSlowdown,
+                     "sw_power_cap": p.nvmlClocksEventReasonSwPowerCap}
+            seen = 0
+            for _, r in self.samples:
+                seen |= r
+            return dict(sm_mhz=float(np.median([x for x, _ in self.samples])), sm_max_mhz=self.sm_max,
+                        reasons=sorted(k for k, bit in names.items() if seen & bit), samples=len(self.samples),
+                        source="nvml, 2 ms poll during the timed region")
         if self.proc is None:
             return dict(sm_mhz=None, sm_max_mhz=None, reasons=["nvidia-smi unavailable"])
         time.sleep(0.25)
@@ -104,7 +156,7 @@ class ClockSampler:
         if not sm:
             return dict(sm_mhz=None, sm_max_mhz=None, reasons=["no samples"])
         return dict(sm_mhz=float(np.median(sm)), sm_max_mhz=float(max(smax)), reasons=sorted(reasons),
-                    samples=len(sm))
+                    samples=len(sm), source="nvidia-smi -lms 200")
 
 
 def make_workload(name: str, device: str, rank: int = 0):

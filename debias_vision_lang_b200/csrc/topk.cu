@@ -61,6 +61,66 @@ __device__ __forceinline__ unsigned long long load_entry(const SelectParams& p, 
   return p.cand[s * p.seg_stride + (int64_t)q * p.row_stride + (i - s * p.seg_len)];
 }
 
+// Bitonic sort of N = 256 * E u64 entries held E per thread (entry i = tid * E + j), ascending.
+// Exchanges inside a thread are register swaps, inside a warp 64-bit shuffles; only the strides that
+// cross warps (>= 32 * E) go through shared memory: 6 of the 55 stages at N = 1024 -- the other 49
+// need no barrier and touch no shared memory.  `buf` holds the entries on entry and on return.
+template <int E>
+__device__ __forceinline__ void bitonic_sort_regs(unsigned long long* buf, int tid) {
+  constexpr int N = kSelThreads * E;
+  const int lane = tid & 31;
+  unsigned long long v[E];
+#pragma unroll
+  for (int j = 0; j < E; ++j) v[j] = buf[tid * E + j];
+  for (int size = 2; size <= N; size <<= 1) {
+    for (int stride = size >> 1; stride >= E; stride >>= 1) {
+      const int tstride = stride / E;                       // partner thread = tid ^ tstride, same j
+      const bool lower = (tid & tstride) == 0;
+      const bool asc = ((tid * E) & size) == 0;             // size > stride >= E: the bit lies in the thread part
+      const bool keep_min = lower == asc;
+      if (tstride >= 32) {
+        __syncthreads();                                    // earlier readers of buf are done
+#pragma unroll
+        for (int j = 0; j < E; ++j) buf[j * kSelThreads + tid] = v[j];   // j-major: conflict-free
+        __syncthreads();
+#pragma unroll
+        for (int j = 0; j < E; ++j) {
+          const unsigned long long o = buf[j * kSelThreads + (tid ^ tstride)];
+          v[j] = keep_min ? (o < v[j] ? o : v[j]) : (o > v[j] ? o : v[j]);
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < E; ++j) {
+          const unsigned long long o = __shfl_xor_sync(0xffffffffu, v[j], tstride);
+          v[j] = keep_min ? (o < v[j] ? o : v[j]) : (o > v[j] ? o : v[j]);
+        }
+      }
+    }
+    // strides below E: both entries live in this thread
+#pragma unroll
+    for (int s = E / 2; s >= 1; s >>= 1) {
+      if (s <= (size >> 1)) {
+#pragma unroll
+        for (int j = 0; j < E; ++j) {
+          if ((j & s) == 0) {
+            const bool asc = ((tid * E + j) & size) == 0;
+            const unsigned long long a = v[j], b = v[j | s];
+            if ((a > b) == asc) {
+              v[j] = b;
+              v[j | s] = a;
+            }
+          }
+        }
+      }
+    }
+  }
+  (void)lane;
+  __syncthreads();
+#pragma unroll
+  for (int j = 0; j < E; ++j) buf[tid * E + j] = v[j];
+  __syncthreads();
+}
+
 __global__ void __launch_bounds__(kSelThreads) select_kernel(const SelectParams p) {
   extern __shared__ unsigned long long sm_list[];     // sort_cap entries
   __shared__ uint32_t hist[256];
@@ -198,21 +258,30 @@ __global__ void __launch_bounds__(kSelThreads) select_kernel(const SelectParams 
   // ---- final: sort, emit ----
   uint32_t pow2 = 1;
   while (pow2 < kept) pow2 <<= 1;
-  for (uint32_t i = kept + tid; i < pow2; i += kSelThreads) sm_list[i] = ~0ull;
-  __syncthreads();
-  for (uint32_t size = 2; size <= pow2; size <<= 1) {
-    for (uint32_t stride = size >> 1; stride > 0; stride >>= 1) {
-      for (uint32_t t = tid; t < (pow2 >> 1); t += kSelThreads) {
-        const uint32_t i = 2 * t - (t & (stride - 1));
-        const uint32_t j = i + stride;
-        const bool up = (i & size) == 0;
-        const unsigned long long a = sm_list[i], b = sm_list[j];
-        if ((a > b) == up) {
-          sm_list[i] = b;
-          sm_list[j] = a;
+  const uint32_t n_sort = pow2 <= 4u * kSelThreads ? 4u * kSelThreads : 8u * kSelThreads;
+  if (pow2 <= n_sort && (uint32_t)p.sort_cap >= n_sort) {
+    // up to 2048 entries (top_n <= ~1000 with its ties, the usual case): registers + warp shuffles
+    for (uint32_t i = kept + tid; i < n_sort; i += kSelThreads) sm_list[i] = ~0ull;
+    __syncthreads();
+    if (n_sort == 4u * kSelThreads) bitonic_sort_regs<4>(sm_list, tid);
+    else bitonic_sort_regs<8>(sm_list, tid);
+  } else {
+    for (uint32_t i = kept + tid; i < pow2; i += kSelThreads) sm_list[i] = ~0ull;
+    __syncthreads();
+    for (uint32_t size = 2; size <= pow2; size <<= 1) {
+      for (uint32_t stride = size >> 1; stride > 0; stride >>= 1) {
+        for (uint32_t t = tid; t < (pow2 >> 1); t += kSelThreads) {
+          const uint32_t i = 2 * t - (t & (stride - 1));
+          const uint32_t j = i + stride;
+          const bool up = (i & size) == 0;
+          const unsigned long long a = sm_list[i], b = sm_list[j];
+          if ((a > b) == up) {
+            sm_list[i] = b;
+            sm_list[j] = a;
+          }
         }
+        __syncthreads();
       }
-      __syncthreads();
     }
   }
   // rows with a NaN score are never ranked (selectn.py:133-134): they sort last
