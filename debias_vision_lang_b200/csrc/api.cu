@@ -111,43 +111,51 @@ struct Operands {
   const float* gal_scale;
 };
 
+// bf16 embeddings in bf16 mode are already the operand TMA wants (K-major rows, 16-byte aligned
+// pitch): the caller's memory is used in place and the conversion pass is skipped
+bool operand_direct(const void* ptr, int dtype, int d, int precision, bool need_norm) {
+  return precision == DVL_PRECISION_BF16 && dtype == DVL_BF16 && !need_norm && d % 8 == 0 &&
+         (reinterpret_cast<uintptr_t>(ptr) & 15u) == 0;
+}
+
+// one side of the similarity: bf16 planes (+ inverse row norms for the fused scale) in the context's
+// workspace, or the caller's rows in place
+int prepare_side(Ctx* c, const void* rows_ptr, int dtype, int64_t rows, int d, int precision, bool need_norm,
+                 DevBuf& planes_buf, DevBuf& norm_buf, const __nv_bfloat16** out_planes, const float** out_scale,
+                 cudaStream_t st) {
+  const int planes = (precision == DVL_PRECISION_FP32) ? 3 : 1;
+  const int dp = (int)round_up(d, 8);
+  const bool direct = operand_direct(rows_ptr, dtype, d, precision, need_norm);
+  if (!direct) DVL_TRY(ensure(c, planes_buf, (size_t)planes * rows * dp * 2));
+  float* norm = nullptr;
+  if (need_norm) {
+    DVL_TRY(ensure(c, norm_buf, (size_t)rows * 4));
+    norm = (float*)norm_buf.ptr;
+  }
+  if (!direct) {
+    StageScope scope(c, DVL_STAGE_PREP, st);
+    DVL_TRY(launch_split_rows(c, rows_ptr, dtype, rows, d, dp, planes, (__nv_bfloat16*)planes_buf.ptr, norm, st));
+  }
+  *out_planes = direct ? (const __nv_bfloat16*)rows_ptr : (const __nv_bfloat16*)planes_buf.ptr;
+  *out_scale = norm;
+  return DVL_OK;
+}
+
+// a1 for a query batch against an already prepared gallery (the exact re-rank of flagged queries)
+int prepare_queries(Ctx* c, const void* queries, int qdt, int d, int q, int precision, uint32_t flags, Operands* op,
+                    cudaStream_t st) {
+  return prepare_side(c, queries, qdt, q, d, precision, (flags & DVL_FLAG_NORMALIZE_QUERIES) != 0, c->qry_planes,
+                      c->qry_inv_norm, &op->qry_planes, &op->qry_scale, st);
+}
+
 // a1 + operand preparation: bf16 planes of gallery and queries, inverse norms for the fused scale
 int prepare_operands(Ctx* c, const void* gallery, int gdt, const void* queries, int qdt, int64_t n, int d, int q,
                      int precision, uint32_t flags, Operands* op, cudaStream_t st) {
-  const int planes = (precision == DVL_PRECISION_FP32) ? 3 : 1;
-  const int dp = (int)round_up(d, 8);
-  // bf16 embeddings in bf16 mode are already the operand TMA wants (K-major rows, 16-byte aligned
-  // pitch): use the caller's memory in place and skip the conversion pass
-  auto direct = [&](const void* ptr, int dtype, bool need_norm) {
-    return precision == DVL_PRECISION_BF16 && dtype == DVL_BF16 && !need_norm && d % 8 == 0 &&
-           (reinterpret_cast<uintptr_t>(ptr) & 15u) == 0;
-  };
-  const bool g_direct = direct(gallery, gdt, (flags & DVL_FLAG_NORMALIZE_GALLERY) != 0);
-  const bool q_direct = direct(queries, qdt, (flags & DVL_FLAG_NORMALIZE_QUERIES) != 0);
-  if (!g_direct) DVL_TRY(ensure(c, c->gal_planes, (size_t)planes * n * dp * 2));
-  if (!q_direct) DVL_TRY(ensure(c, c->qry_planes, (size_t)planes * q * dp * 2));
-  float* gnorm = nullptr;
-  float* qnorm = nullptr;
-  if (flags & DVL_FLAG_NORMALIZE_GALLERY) {
-    DVL_TRY(ensure(c, c->gal_inv_norm, (size_t)n * 4));
-    gnorm = (float*)c->gal_inv_norm.ptr;
-  }
-  if (flags & DVL_FLAG_NORMALIZE_QUERIES) {
-    DVL_TRY(ensure(c, c->qry_inv_norm, (size_t)q * 4));
-    qnorm = (float*)c->qry_inv_norm.ptr;
-  }
-  StageScope scope(c, DVL_STAGE_PREP, st);
-  if (!g_direct)
-    DVL_TRY(launch_split_rows(c, gallery, gdt, n, d, dp, planes, (__nv_bfloat16*)c->gal_planes.ptr, gnorm, st));
-  if (!q_direct)
-    DVL_TRY(launch_split_rows(c, queries, qdt, q, d, dp, planes, (__nv_bfloat16*)c->qry_planes.ptr, qnorm, st));
-  op->qry_planes = q_direct ? (const __nv_bfloat16*)queries : (const __nv_bfloat16*)c->qry_planes.ptr;
-  op->gal_planes = g_direct ? (const __nv_bfloat16*)gallery : (const __nv_bfloat16*)c->gal_planes.ptr;
-  op->planes = planes;
-  op->dp = dp;
-  op->qry_scale = qnorm;
-  op->gal_scale = gnorm;
-  return DVL_OK;
+  op->planes = (precision == DVL_PRECISION_FP32) ? 3 : 1;
+  op->dp = (int)round_up(d, 8);
+  DVL_TRY(prepare_side(c, gallery, gdt, n, d, precision, (flags & DVL_FLAG_NORMALIZE_GALLERY) != 0, c->gal_planes,
+                       c->gal_inv_norm, &op->gal_planes, &op->gal_scale, st));
+  return prepare_queries(c, queries, qdt, d, q, precision, flags, op, st);
 }
 
 GemmArgs gemm_args(const Operands& op, int64_t n, int d, int q) {
@@ -170,12 +178,9 @@ GemmArgs gemm_args(const Operands& op, int64_t n, int d, int q) {
   return g;
 }
 
-// similarity into ranking keys and/or fp32 scores (both pitched to whole 256-column tiles)
-int run_similarity(Ctx* c, const void* gallery, int gdt, const void* queries, int qdt, int64_t n, int d, int q,
-                   int precision, uint32_t flags, uint32_t* keys, int64_t ldk, float* scores, int64_t lds,
-                   cudaStream_t st) {
-  Operands op;
-  DVL_TRY(prepare_operands(c, gallery, gdt, queries, qdt, n, d, q, precision, flags, &op, st));
+// similarity of prepared operands into ranking keys and/or fp32 scores (both pitched to whole 256-column tiles)
+int run_similarity_prepared(Ctx* c, const Operands& op, int64_t n, int d, int q, uint32_t* keys, int64_t ldk,
+                            float* scores, int64_t lds, cudaStream_t st) {
   StageScope scope(c, DVL_STAGE_GEMM, st);
   GemmArgs g = gemm_args(op, n, d, q);
   g.keys = keys;
@@ -183,6 +188,14 @@ int run_similarity(Ctx* c, const void* gallery, int gdt, const void* queries, in
   g.scores = scores;
   g.lds = lds;
   return launch_sim_gemm(c, g, st);
+}
+
+int run_similarity(Ctx* c, const void* gallery, int gdt, const void* queries, int qdt, int64_t n, int d, int q,
+                   int precision, uint32_t flags, uint32_t* keys, int64_t ldk, float* scores, int64_t lds,
+                   cudaStream_t st) {
+  Operands op;
+  DVL_TRY(prepare_operands(c, gallery, gdt, queries, qdt, n, d, q, precision, flags, &op, st));
+  return run_similarity_prepared(c, op, n, d, q, keys, ldk, scores, lds, st);
 }
 
 // query-independent statistics: Counter(df.label) and the fp64 tables
@@ -690,7 +703,7 @@ namespace {
 
 // Re-ranks the queries the streaming route flagged (tie run longer than its list) by the full-sort
 // route and patches their rows of per_query / ranked_len / ranked_idx.  Rare by construction.
-int rerank_flagged(Ctx* c, const void* gallery, int gdt, const void* queries, int qdt, const uint8_t* labels,
+int rerank_flagged(Ctx* c, const Operands& gallery_op, const void* queries, int qdt, const uint8_t* labels,
                    int64_t n, int d, int q, int n_classes, int64_t top_n, int precision, uint32_t flags,
                    double* per_query, int32_t* ranked_len, int32_t* ranked_idx, int64_t ranked_cap,
                    cudaStream_t st) {
@@ -723,8 +736,11 @@ int rerank_flagged(Ctx* c, const void* gallery, int gdt, const void* queries, in
                                     (const char*)queries + (size_t)flagged[b0 + i] * row_bytes, row_bytes,
                                     cudaMemcpyDeviceToDevice, st));
     }
-    DVL_TRY(run_similarity(c, gallery, gdt, c->fb_queries.ptr, qdt, n, d, f, precision, flags,
-                           (uint32_t*)c->keys[0].ptr, ldk, nullptr, 0, st));
+    // the gallery planes of the streaming pass are still in the workspace: only the flagged queries
+    // are prepared again (the streaming pass is done with its own query planes)
+    Operands op = gallery_op;
+    DVL_TRY(prepare_queries(c, c->fb_queries.ptr, qdt, d, f, precision, flags, &op, st));
+    DVL_TRY(run_similarity_prepared(c, op, n, d, f, (uint32_t*)c->keys[0].ptr, ldk, nullptr, 0, st));
     DVL_TRY(rank_full(c, labels, n, n, f, n_classes, top_n, ldk, (double*)c->fb_per_query.ptr,
                       (int32_t*)c->fb_len.ptr, ranked_idx != nullptr ? (int32_t*)c->fb_idx.ptr : nullptr, ranked_cap,
                       st));
@@ -789,7 +805,7 @@ DVL_API int dvl_eval_ranking(dvl_ctx* c, const void* gallery, int gdt, const voi
       dvl::StageScope scope(c, DVL_STAGE_METRICS, st);
       DVL_TRY(dvl::launch_metrics(c, m, st));
     }
-    DVL_TRY(dvl::rerank_flagged(c, gallery, gdt, queries, qdt, labels, n, d, q, n_classes, top_n, precision, flags,
+    DVL_TRY(dvl::rerank_flagged(c, op, queries, qdt, labels, n, d, q, n_classes, top_n, precision, flags,
                                 per_query, ranked_len, out_ranked_idx, ranked_cap, st));
     return dvl::finish(c, per_query, q, n_classes, out_mean4, true, st);
   }

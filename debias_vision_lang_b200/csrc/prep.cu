@@ -23,11 +23,35 @@ __device__ __forceinline__ float load_as_float<__nv_bfloat16>(const __nv_bfloat1
 template <>
 __device__ __forceinline__ float load_as_float<__half>(const __half* p) { return __half2float(*p); }
 
-// One warp per row; lane handles 4 consecutive elements per step (coalesced 512 B / warp for fp32).
+// Four consecutive elements of a row as floats.  `vec`: the row starts are 16-byte (fp32) / 8-byte
+// (16-bit types) aligned and d is a multiple of 4, so the quad is one vector load; otherwise element
+// loads with a bound on d.  Columns >= d (the padding up to the plane pitch) read as zero.
+template <typename T>
+__device__ __forceinline__ void load_quad(const T* __restrict__ s, int c, int d, bool vec, float (&x)[4]) {
+  if (vec && c + 3 < d) {
+    if constexpr (sizeof(T) == 4) {
+      const float4 v = __ldcs(reinterpret_cast<const float4*>(s + c));
+      x[0] = v.x; x[1] = v.y; x[2] = v.z; x[3] = v.w;
+    } else {
+      const uint2 v = __ldcs(reinterpret_cast<const uint2*>(s + c));
+      const T* h = reinterpret_cast<const T*>(&v);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) x[j] = load_as_float<T>(h + j);
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) x[j] = (c + j < d) ? load_as_float<T>(s + c + j) : 0.f;
+  }
+}
+
+// One warp per row; a lane handles 4 consecutive elements per 128-element step (coalesced 512 B per
+// warp for fp32) and issues the loads of kUnroll steps before it touches any of them: at D = 512 a
+// whole row is in flight per warp.  HBM-bound: 4 B read + 2*PLANES B written per element.
 template <typename T, int PLANES>
 __global__ void __launch_bounds__(256) split_rows_kernel(const T* __restrict__ src, int64_t rows, int d, int dp,
                                                          __nv_bfloat16* __restrict__ dst,
-                                                         float* __restrict__ inv_norm) {
+                                                         float* __restrict__ inv_norm, int vec) {
+  constexpr int kUnroll = 4;
   const int lane = threadIdx.x & 31;
   const int64_t warps_total = (int64_t)gridDim.x * (blockDim.x >> 5);
   const int64_t plane_stride = rows * (int64_t)dp;
@@ -35,24 +59,29 @@ __global__ void __launch_bounds__(256) split_rows_kernel(const T* __restrict__ s
     const T* s = src + row * (int64_t)d;
     __nv_bfloat16* o = dst + row * (int64_t)dp;
     float ss = 0.f;
-    for (int c0 = lane * 4; c0 < dp; c0 += 128) {
-      float x[4];
+    for (int c0 = lane * 4; c0 < dp; c0 += 128 * kUnroll) {
+      float x[kUnroll][4];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) x[j] = (c0 + j < d) ? load_as_float<T>(s + c0 + j) : 0.f;
-      __align__(8) __nv_bfloat16 b[PLANES][4];
+      for (int u = 0; u < kUnroll; ++u) load_quad<T>(s, c0 + u * 128, d, vec != 0, x[u]);
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        ss = fmaf(x[j], x[j], ss);
-        float r = x[j];
+      for (int u = 0; u < kUnroll; ++u) {
+        const int c = c0 + u * 128;
+        if (c >= dp) break;
+        __align__(8) __nv_bfloat16 b[PLANES][4];
 #pragma unroll
-        for (int p = 0; p < PLANES; ++p) {
-          b[p][j] = __float2bfloat16_rn(r);
-          r = r - __bfloat162float(b[p][j]);   // exact: the residual of a round-to-8-bits fits fp32
+        for (int j = 0; j < 4; ++j) {
+          ss = fmaf(x[u][j], x[u][j], ss);
+          float r = x[u][j];
+#pragma unroll
+          for (int p = 0; p < PLANES; ++p) {
+            b[p][j] = __float2bfloat16_rn(r);
+            r = r - __bfloat162float(b[p][j]);   // exact: the residual of a round-to-8-bits fits fp32
+          }
         }
-      }
 #pragma unroll
-      for (int p = 0; p < PLANES; ++p)
-        *reinterpret_cast<uint2*>(o + p * plane_stride + c0) = *reinterpret_cast<const uint2*>(b[p]);
+        for (int p = 0; p < PLANES; ++p)
+          *reinterpret_cast<uint2*>(o + p * plane_stride + c) = *reinterpret_cast<const uint2*>(b[p]);
+      }
     }
     if (inv_norm != nullptr) {
 #pragma unroll
@@ -70,10 +99,12 @@ static int launch_split_t(Ctx* c, const T* src, int64_t rows, int d, int dp, int
   int64_t cap = (int64_t)c->num_sms * 16;
   if (blocks > cap) blocks = cap;
   if (blocks < 1) blocks = 1;
+  // whole-quad vector loads need every row start aligned to the quad: d % 4 == 0 and an aligned base
+  const int vec = (d % 4 == 0 && (reinterpret_cast<uintptr_t>(src) % (4 * sizeof(T))) == 0) ? 1 : 0;
   if (planes == 1)
-    split_rows_kernel<T, 1><<<(unsigned)blocks, 256, 0, st>>>(src, rows, d, dp, dst, inv_norm);
+    split_rows_kernel<T, 1><<<(unsigned)blocks, 256, 0, st>>>(src, rows, d, dp, dst, inv_norm, vec);
   else
-    split_rows_kernel<T, 3><<<(unsigned)blocks, 256, 0, st>>>(src, rows, d, dp, dst, inv_norm);
+    split_rows_kernel<T, 3><<<(unsigned)blocks, 256, 0, st>>>(src, rows, d, dp, dst, inv_norm, vec);
   DVL_LAUNCH_CHECK(c, "split_rows_kernel");
   return DVL_OK;
 }
