@@ -423,14 +423,14 @@ def run_ours(args):
     dominant = max(stage_ms, key=lambda k: stage_ms[k])
     pairs_rank = w.gallery.shape[0] * q
     if dominant == "gemm":
-        terms = 6 if precision == "fp32" else 1
+        terms = 3 if precision == "fp32" else 1      # scaled fp16 pair: h1*h0', h0*h1', h0*h0'
         flops = 2.0 * pairs_rank * d                       # algorithmic: 2*D flop per pair
         achieved = flops / (stage_ms["gemm"] * 1e-3) / 1e12
         roof = {"bound": "tensor", "kernel": "sim_gemm_kernel", "achieved": achieved,
                 "peak": peaks["bf16_tflops"], "unit": "TFLOP/s", "frac": achieved / peaks["bf16_tflops"],
                 "traffic": None, "peak_source": peaks["source"] + " bf16 burst",
                 "issued_tflops": achieved * terms,
-                "note": f"algorithmic 2*D flop/pair; fp32 mode issues {terms}x that in bf16 products"}
+                "note": f"algorithmic 2*D flop/pair; fp32 mode issues {terms}x that in 16-bit tensor-core products"}
     else:
         # the radix sort: per launch of tile_scatter_kernel a pair costs key read+write (8 B) and label
         # read+write (2 B); see DESIGN.md section 4

@@ -96,15 +96,15 @@ int check_common(Ctx* c, int64_t n, int32_t d, int32_t q, int32_t n_classes, int
   if (n_classes < 1 || n_classes > DVL_MAX_CLASSES)
     return set_error(c, DVL_ERR_INVALID, "n_classes %d outside 1..%d", n_classes, DVL_MAX_CLASSES);
   if (top_n < 1) return set_error(c, DVL_ERR_INVALID, "top_n must be >= 1 (the reference divides by it)");
-  if (precision != DVL_PRECISION_FP32 && precision != DVL_PRECISION_BF16)
+  if (precision != DVL_PRECISION_FP32 && precision != DVL_PRECISION_BF16 && precision != DVL_PRECISION_FP32X3)
     return set_error(c, DVL_ERR_INVALID, "unknown precision %d", precision);
   if (dtype_size(gdt) == 0 || dtype_size(qdt) == 0) return set_error(c, DVL_ERR_INVALID, "unknown dtype");
   return DVL_OK;
 }
 
 struct Operands {
-  const __nv_bfloat16* qry_planes;
-  const __nv_bfloat16* gal_planes;
+  const void* qry_planes;
+  const void* gal_planes;
   int planes;
   int dp;
   const float* qry_scale;
@@ -118,26 +118,31 @@ bool operand_direct(const void* ptr, int dtype, int d, int precision, bool need_
          (reinterpret_cast<uintptr_t>(ptr) & 15u) == 0;
 }
 
-// one side of the similarity: bf16 planes (+ inverse row norms for the fused scale) in the context's
-// workspace, or the caller's rows in place
+// 16-bit planes per operand: 1 = bf16, 2 = scaled fp16 pair (fp32 mode), 3 = exact bf16 triple
+int planes_of(int precision) {
+  return precision == DVL_PRECISION_BF16 ? 1 : (precision == DVL_PRECISION_FP32X3 ? 3 : 2);
+}
+
+// one side of the similarity: 16-bit planes (+ the row factors of the fused scale: 2^-e of the fp16
+// split, inverse row norms) in the context's workspace, or the caller's rows in place
 int prepare_side(Ctx* c, const void* rows_ptr, int dtype, int64_t rows, int d, int precision, bool need_norm,
-                 DevBuf& planes_buf, DevBuf& norm_buf, const __nv_bfloat16** out_planes, const float** out_scale,
+                 DevBuf& planes_buf, DevBuf& scale_buf, const void** out_planes, const float** out_scale,
                  cudaStream_t st) {
-  const int planes = (precision == DVL_PRECISION_FP32) ? 3 : 1;
+  const int planes = planes_of(precision);
   const int dp = (int)round_up(d, 8);
   const bool direct = operand_direct(rows_ptr, dtype, d, precision, need_norm);
   if (!direct) DVL_TRY(ensure(c, planes_buf, (size_t)planes * rows * dp * 2));
-  float* norm = nullptr;
-  if (need_norm) {
-    DVL_TRY(ensure(c, norm_buf, (size_t)rows * 4));
-    norm = (float*)norm_buf.ptr;
+  float* scale = nullptr;
+  if (need_norm || planes == 2) {
+    DVL_TRY(ensure(c, scale_buf, (size_t)rows * 4));
+    scale = (float*)scale_buf.ptr;
   }
   if (!direct) {
     StageScope scope(c, DVL_STAGE_PREP, st);
-    DVL_TRY(launch_split_rows(c, rows_ptr, dtype, rows, d, dp, planes, (__nv_bfloat16*)planes_buf.ptr, norm, st));
+    DVL_TRY(launch_split_rows(c, rows_ptr, dtype, rows, d, dp, planes, planes_buf.ptr, scale, need_norm, st));
   }
-  *out_planes = direct ? (const __nv_bfloat16*)rows_ptr : (const __nv_bfloat16*)planes_buf.ptr;
-  *out_scale = norm;
+  *out_planes = direct ? rows_ptr : planes_buf.ptr;
+  *out_scale = scale;
   return DVL_OK;
 }
 
@@ -151,7 +156,7 @@ int prepare_queries(Ctx* c, const void* queries, int qdt, int d, int q, int prec
 // a1 + operand preparation: bf16 planes of gallery and queries, inverse norms for the fused scale
 int prepare_operands(Ctx* c, const void* gallery, int gdt, const void* queries, int qdt, int64_t n, int d, int q,
                      int precision, uint32_t flags, Operands* op, cudaStream_t st) {
-  op->planes = (precision == DVL_PRECISION_FP32) ? 3 : 1;
+  op->planes = planes_of(precision);
   op->dp = (int)round_up(d, 8);
   DVL_TRY(prepare_side(c, gallery, gdt, n, d, precision, (flags & DVL_FLAG_NORMALIZE_GALLERY) != 0, c->gal_planes,
                        c->gal_inv_norm, &op->gal_planes, &op->gal_scale, st));

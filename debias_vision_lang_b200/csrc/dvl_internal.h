@@ -96,10 +96,12 @@ int ensure(Ctx* c, DevBuf& b, size_t bytes);
   } while (0)
 
 // ---- prep.cu ---------------------------------------------------------------------------
-// rows [r, d] of `dtype` -> `planes` bf16 planes [planes][r][dp] (dp = padded row pitch, zero
-// filled) and, if inv_norm != nullptr, 1/||row||_2.
-int launch_split_rows(Ctx* c, const void* src, int dtype, int64_t rows, int d, int dp, int planes,
-                      __nv_bfloat16* dst, float* inv_norm, cudaStream_t st);
+// rows [r, d] of `dtype` -> 16-bit planes [planes][r][dp] (dp = padded row pitch, zero filled):
+// 1 = one bf16 plane, 3 = exact bf16 triple, 2 = two fp16 planes of the power-of-two scaled row.
+// row_scale [r] (required for planes == 2 or normalize): the factor the similarity epilogue applies to
+// the row: 2^-e of the scaled split, times 1/||row||_2 when `normalize`.
+int launch_split_rows(Ctx* c, const void* src, int dtype, int64_t rows, int d, int dp, int planes, void* dst,
+                      float* row_scale, bool normalize, cudaStream_t st);
 int launch_class_counts(Ctx* c, const uint8_t* labels, int64_t n, int n_classes, unsigned long long* counts,
                         cudaStream_t st);
 
@@ -116,15 +118,15 @@ struct GemmArgs {
   int64_t index_base = 0;
   int64_t gal_row_step = 1;         // > 1: the kernel's rows are a strided sample of the gallery
   int64_t gal_rows_total = 0;       //      (physical rows, needed for the plane stride)
-  const __nv_bfloat16* qry_planes;  // [planes][q][dp]
-  const __nv_bfloat16* gal_planes;  // [planes][n][dp]
-  int planes;                       // 1 (bf16) or 3 (fp32 via bf16x3)
+  const void* qry_planes;           // [planes][q][dp] 16-bit elements
+  const void* gal_planes;           // [planes][n][dp]
+  int planes;                       // 1 (bf16), 2 (fp32 via scaled fp16x2: 3 product terms) or 3 (bf16x3: 6 terms)
   int64_t n;
   int q;
   int d;       // logical depth
   int dp;      // row pitch (elements), multiple of 8
-  const float* qry_scale;  // [q] or nullptr (1/||t_q||)
-  const float* gal_scale;  // [n] or nullptr (1/||g_i||)
+  const float* qry_scale;  // [q] or nullptr: row factor applied in the epilogue (2^-e of the split, 1/||t_q||)
+  const float* gal_scale;  // [n] or nullptr
   // outputs (any may be null)
   uint32_t* keys;   // [q][ldk]
   int64_t ldk;

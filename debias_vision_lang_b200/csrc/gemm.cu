@@ -12,7 +12,10 @@
 //   warp 0      TMA producer (one lane)      full/empty mbarrier ring, kStages deep
 //   warp 1      TMEM allocator + MMA issuer (one lane), double-buffered fp32 accumulators
 //               (2 x 256 TMEM columns) so the epilogue of tile t overlaps the MMAs of t+1
-//   warps 2..5  epilogue: tcgen05.ld 32 lanes x 32 columns -> fused scale (L2 normalisation) ->
+//   warps 2..9  epilogue (a warp may only read the TMEM lane quarter warp_id % 4: two warps per quarter,
+//               one per half of the tile's 256 columns -- with four warps the epilogue of the scaled
+//               fp32 modes took twice the MMA time of a tile and the tensor pipe idled half the time):
+//               tcgen05.ld 32 lanes x 32 columns -> fused scale (L2 normalisation, 2^-e) ->
 //               STORE : ranking key / fp32 score, 128-byte row segments to HBM (full-sort route)
 //               SEED  : every (key, index, label) candidate of the first gallery chunk, dense
 //               FILTER: streaming top-k -- one compare per similarity against the query's
@@ -20,8 +23,16 @@
 //                       appended to the query's candidate list.  The similarity matrix never
 //                       reaches HBM.
 //
-// fp32 mode: operands arrive as three exact bf16 planes each; the K loop runs over the six
-// (i, j) plane pairs with i + j <= 4, smallest terms first, all into the same accumulator.
+// fp32 modes: operands arrive as several 16-bit planes each, all product terms go into the same
+// accumulator, the row factors (2^-e of the fp16 split, fused L2 normalisation) are applied in the
+// epilogue.
+//   fp16 pair (default, three terms): k-block major -- a pipeline stage holds BOTH planes of both
+//     operands for one k-block (96 KB, two stages) and feeds 12 MMAs (h1*h0', h0*h1', h0*h0'), so every
+//     operand byte is fetched from L2 once per tile.  Loading a stage per term instead (1.15 MB per tile)
+//     left the kernel bound by the L2 -> shared-memory path (~54 B/clk/SM), not by the tensor pipe.
+//     (Requesting the next tile's gallery block into L2 a tile ahead with cp.async.bulk.prefetch.tensor
+//     was measured and not kept: no gain on configs 2 and 5, 20 % slower on config 3.)
+//   bf16 triple (six terms): term major, one plane pair per 48 KB stage, four stages, smallest terms first.
 //
 // Tiles are ordered gallery-block major so that CTAs running at the same time share the
 // gallery block (read from HBM once, then L2 hits) while the small query matrix stays
@@ -44,15 +55,19 @@ constexpr int kABytes = BM * BK * 2;   // 16 KB
 constexpr int kBBytes = BN * BK * 2;   // 32 KB
 constexpr int kStageBytes = kABytes + kBBytes;
 constexpr int kTmemCols = 512;         // 2 accumulator buffers x 256 columns
-constexpr int kNumThreads = 192;       // 6 warps
-constexpr int kEpiThreads = 128;
+constexpr int kEpiWarps = 8;           // two per TMEM lane quarter, each takes one half of the 256 columns
+constexpr int kEpiThreads = 32 * kEpiWarps;
+constexpr int kNumThreads = 64 + kEpiThreads;   // + TMA producer warp + MMA warp
 constexpr int kEpiScratchBytes = kEpiThreads * 33 * 4;   // FILTER: one 32-word row per epilogue thread
 constexpr size_t kSmemBytes =
     1024 /*align slack*/ + (size_t)kStages * kStageBytes + 256 /*barriers*/ + kEpiScratchBytes;
 
 // plane pairs (query plane, gallery plane), smallest product magnitude first
-__constant__ int c_term_a[6] = {0, 1, 2, 0, 1, 0};
-__constant__ int c_term_b[6] = {2, 1, 0, 1, 0, 0};
+constexpr int kMaxTerms = 6;
+constexpr int kTermsX3A[6] = {0, 1, 2, 0, 1, 0};   // three bf16 planes: i + j <= 2
+constexpr int kTermsX3B[6] = {2, 1, 0, 1, 0, 0};
+constexpr int kTermsX2A[3] = {1, 0, 0};            // two fp16 planes: h1*h0', h0*h1', h0*h0'
+constexpr int kTermsX2B[3] = {0, 1, 0};
 
 struct KernelParams {
   int mode;          // kGemmStore / kGemmSeed / kGemmFilter
@@ -62,9 +77,14 @@ struct KernelParams {
   int n_qtiles;
   int64_t n_tiles;
   int k_blocks;     // ceil(d / 64)
-  int n_terms;      // 1 or 6
+  int n_terms;      // 1 (one plane), 3 (fp16 pair) or 6 (bf16 triple)
+  int n_planes;     // 16-bit planes per operand
+  int fused_planes; // 1: fp16 pair, k-block major with both planes of both operands in one stage
+  int term_a[kMaxTerms], term_b[kMaxTerms];
+  uint32_t idesc;   // UMMA instruction descriptor (bf16 or fp16 operands)
   const float* qry_scale;
-  const float* gal_scale;
+  const float* gal_scale;   // indexed by the physical gallery row: kernel row * gal_step
+  int64_t gal_step;
   uint32_t* keys;
   int64_t ldk;
   float* scores;
@@ -126,7 +146,10 @@ sim_gemm_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
 
-  const int iters_per_tile = p.k_blocks * p.n_terms;
+  // pipeline shape: 4 stages of one plane pair (48 KB), or 2 stages of both planes of both operands (96 KB)
+  const int iters_per_tile = p.fused_planes ? p.k_blocks : p.k_blocks * p.n_terms;
+  const int n_stages = p.fused_planes ? kStages / 2 : kStages;
+  const uint32_t stage_bytes = p.fused_planes ? 2u * kStageBytes : (uint32_t)kStageBytes;
 
   if (warp == 0) {
     // ------------------------------ TMA producer ------------------------------
@@ -136,24 +159,31 @@ sim_gemm_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
       for (int64_t t = blockIdx.x; t < p.n_tiles; t += gridDim.x) {
         const int qt = (int)(t % p.n_qtiles);
         const int64_t gb = t / p.n_qtiles;
+        const int grow = (int)(p.row0 + gb * BN);
         for (int it = 0; it < iters_per_tile; ++it) {
-          const int term = it / p.k_blocks;
-          const int kb = it - term * p.k_blocks;
-          const int pa = (p.n_terms == 1) ? 0 : c_term_a[term];
-          const int pb = (p.n_terms == 1) ? 0 : c_term_b[term];
           mbar_wait(empty_bar(stage), phase ^ 1u);
-          mbar_arrive_expect_tx(full_bar(stage), kStageBytes);
-          const uint32_t sa = smem_base + stage * kStageBytes;
-          tma_load_3d(sa, &map_q, full_bar(stage), kb * BK, qt * BM, pa);
-          tma_load_3d(sa + kABytes, &map_g, full_bar(stage), kb * BK, (int)(p.row0 + gb * BN), pb);
-          if (++stage == kStages) { stage = 0; phase ^= 1u; }
+          mbar_arrive_expect_tx(full_bar(stage), stage_bytes);
+          const uint32_t sa = smem_base + stage * stage_bytes;
+          if (p.fused_planes) {
+            // [A plane 0][A plane 1][B plane 0][B plane 1] of k-block `it`
+            tma_load_3d(sa, &map_q, full_bar(stage), it * BK, qt * BM, 0);
+            tma_load_3d(sa + kABytes, &map_q, full_bar(stage), it * BK, qt * BM, 1);
+            tma_load_3d(sa + 2 * kABytes, &map_g, full_bar(stage), it * BK, grow, 0);
+            tma_load_3d(sa + 2 * kABytes + kBBytes, &map_g, full_bar(stage), it * BK, grow, 1);
+          } else {
+            const int term = it / p.k_blocks;
+            const int kb = it - term * p.k_blocks;
+            tma_load_3d(sa, &map_q, full_bar(stage), kb * BK, qt * BM, p.term_a[term]);
+            tma_load_3d(sa + kABytes, &map_g, full_bar(stage), kb * BK, grow, p.term_b[term]);
+          }
+          if (++stage == n_stages) { stage = 0; phase ^= 1u; }
         }
       }
     }
   } else if (warp == 1) {
     // ------------------------------ MMA issuer ------------------------------
     if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_bf16(BM, BN);
+      const uint32_t idesc = p.idesc;
       int stage = 0;
       uint32_t phase = 0;
       int as = 0;
@@ -165,16 +195,31 @@ sim_gemm_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
         for (int it = 0; it < iters_per_tile; ++it) {
           mbar_wait(full_bar(stage), phase);      // TMA bytes have landed
           tc_fence_after();
-          const uint32_t sa = smem_base + stage * kStageBytes;
-          const uint32_t sb = sa + kABytes;
+          const uint32_t sa = smem_base + stage * stage_bytes;
+          if (p.fused_planes) {
+            const uint32_t sb = sa + 2 * kABytes;
 #pragma unroll
-          for (int k = 0; k < BK / UMMA_K; ++k) {
-            const uint64_t da = umma_desc_sw128(sa + k * (UMMA_K * 2));
-            const uint64_t db = umma_desc_sw128(sb + k * (UMMA_K * 2));
-            umma_bf16_ss(tmem_d, da, db, idesc, (it > 0 || k > 0) ? 1u : 0u);
+            for (int term = 0; term < 3; ++term) {   // h1*h0', h0*h1', h0*h0': smallest first
+              const uint32_t ta = sa + (term == 0 ? kABytes : 0);
+              const uint32_t tb = sb + (term == 1 ? kBBytes : 0);
+#pragma unroll
+              for (int k = 0; k < BK / UMMA_K; ++k) {
+                const uint64_t da = umma_desc_sw128(ta + k * (UMMA_K * 2));
+                const uint64_t db = umma_desc_sw128(tb + k * (UMMA_K * 2));
+                umma_bf16_ss(tmem_d, da, db, idesc, (it > 0 || term > 0 || k > 0) ? 1u : 0u);
+              }
+            }
+          } else {
+            const uint32_t sb = sa + kABytes;
+#pragma unroll
+            for (int k = 0; k < BK / UMMA_K; ++k) {
+              const uint64_t da = umma_desc_sw128(sa + k * (UMMA_K * 2));
+              const uint64_t db = umma_desc_sw128(sb + k * (UMMA_K * 2));
+              umma_bf16_ss(tmem_d, da, db, idesc, (it > 0 || k > 0) ? 1u : 0u);
+            }
           }
           umma_commit(empty_bar(stage));          // smem slot free once these MMAs retire
-          if (++stage == kStages) { stage = 0; phase ^= 1u; }
+          if (++stage == n_stages) { stage = 0; phase ^= 1u; }
         }
         umma_commit(tfull_bar(as));               // accumulator complete -> epilogue
         as ^= 1;
@@ -186,6 +231,7 @@ sim_gemm_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
     // ------------------------------ epilogue ------------------------------
     const int quarter = warp & 3;                 // TMEM lanes this warp may touch: 32*quarter..+31
     const int row_in_tile = quarter * 32 + lane;
+    const int chunk0 = ((warp - 2) >> 2) * (BN / 64);   // first of this warp's four 32-column chunks
     int as = 0;
     uint32_t aphase = 0;
     for (int64_t t = blockIdx.x; t < p.n_tiles; t += gridDim.x) {
@@ -207,18 +253,24 @@ sim_gemm_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
         uint32_t* mine = epi_scratch + (threadIdx.x - 64) * 33;
         unsigned long long* list = p.cand + (int64_t)qrow * p.cap;
 #pragma unroll 1
-        for (int chunk = 0; chunk < BN / 32; ++chunk) {
+        for (int chunk = chunk0; chunk < chunk0 + BN / 64; ++chunk) {
           uint32_t v[32];
+          const int64_t col0 = p.row0 + gb * BN + chunk * 32;
+          // the chunk's 32 gallery-row factors: lane j fetches column j's (one coalesced load, requested
+          // before the accumulator read so that both latencies overlap), the element loop gets them by shuffle
+          float gs_lane = 1.0f;
+          if (p.gal_scale != nullptr) gs_lane = (col0 + lane < p.n) ? __ldg(p.gal_scale + (col0 + lane) * p.gal_step) : 0.f;
           tmem_ld_32x32(taddr + (uint32_t)(chunk * 32), v);
           tmem_ld_wait();
-          const int64_t col0 = p.row0 + gb * BN + chunk * 32;
-          if (scaled) {                            // uniform branch, outside the element loop
+          // uniform branches, outside the element loops (a shuffle under a per-element branch is neither
+          // if-converted nor pipelined by the compiler)
+          if (p.gal_scale != nullptr) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              float s = __uint_as_float(v[j]) * qs;
-              if (p.gal_scale != nullptr) s *= (col0 + j < p.n) ? __ldg(p.gal_scale + col0 + j) : 0.f;
-              v[j] = __float_as_uint(s);
-            }
+            for (int j = 0; j < 32; ++j)
+              v[j] = __float_as_uint(__uint_as_float(v[j]) * qs * __shfl_sync(0xffffffffu, gs_lane, j));
+          } else if (scaled) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) * qs);
           }
           uint32_t mask = 0;
 #pragma unroll
@@ -241,18 +293,20 @@ sim_gemm_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
         }
       } else {
 #pragma unroll 1
-      for (int chunk = 0; chunk < BN / 32; ++chunk) {
+      for (int chunk = chunk0; chunk < chunk0 + BN / 64; ++chunk) {
         uint32_t v[32];
+        const int64_t col0 = p.row0 + gb * BN + chunk * 32;
+        float gs_lane = 1.0f;                      // as in the filter branch
+        if (p.gal_scale != nullptr) gs_lane = (col0 + lane < p.n) ? __ldg(p.gal_scale + (col0 + lane) * p.gal_step) : 0.f;
         tmem_ld_32x32(taddr + (uint32_t)(chunk * 32), v);
         tmem_ld_wait();
-        const int64_t col0 = p.row0 + gb * BN + chunk * 32;
-        if (scaled) {
+        if (p.gal_scale != nullptr) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            float s = __uint_as_float(v[j]) * qs;
-            if (p.gal_scale != nullptr) s *= (col0 + j < p.n) ? __ldg(p.gal_scale + col0 + j) : 0.f;
-            v[j] = __float_as_uint(s);
-          }
+          for (int j = 0; j < 32; ++j)
+            v[j] = __float_as_uint(__uint_as_float(v[j]) * qs * __shfl_sync(0xffffffffu, gs_lane, j));
+        } else if (scaled) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) * qs);
         }
         if (p.mode == kGemmStore) {
           if (row_ok) {
@@ -303,8 +357,8 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
 // rows_view rows, `row_step` physical rows apart (row_step > 1: a strided sample of the matrix, no copy)
-int make_map(Ctx* c, CUtensorMap* map, const void* base, int64_t rows, int d, int dp, int planes, int box_rows,
-             int64_t rows_view = -1, int64_t row_step = 1) {
+int make_map(Ctx* c, CUtensorMap* map, const void* base, bool fp16, int64_t rows, int d, int dp, int planes,
+             int box_rows, int64_t rows_view = -1, int64_t row_step = 1) {
   if (rows_view < 0) rows_view = rows;
   if (c->encode_tiled == nullptr) {
     void* fn = nullptr;
@@ -319,7 +373,8 @@ int make_map(Ctx* c, CUtensorMap* map, const void* base, int64_t rows, int d, in
   cuuint64_t strides[2] = {(cuuint64_t)dp * 2ull * (cuuint64_t)row_step, (cuuint64_t)rows * (cuuint64_t)dp * 2ull};
   cuuint32_t box[3] = {(cuuint32_t)BK, (cuuint32_t)box_rows, 1u};
   cuuint32_t estr[3] = {1u, 1u, 1u};
-  CUresult r = ((EncodeTiledFn)c->encode_tiled)(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base),
+  CUresult r = ((EncodeTiledFn)c->encode_tiled)(map, fp16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3,
+                                                const_cast<void*>(base),
                                                 dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                                                 CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                                                 CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -342,11 +397,14 @@ int launch_sim_gemm(Ctx* c, const GemmArgs& a, cudaStream_t st) {
   if (a.index_base + a.n > (1ll << 28)) return set_error(c, DVL_ERR_UNSUPPORTED, "global gallery index needs more than 28 bits");
   if (a.n > 0x7FFFFF00ll) return set_error(c, DVL_ERR_UNSUPPORTED, "gallery shard larger than 2^31 rows");
   CUtensorMap map_q, map_g;
-  DVL_TRY(make_map(c, &map_q, a.qry_planes, a.q, a.d, a.dp, a.planes, BM));
+  const bool fp16 = a.planes == 2;
+  if (fp16 && (a.qry_scale == nullptr || a.gal_scale == nullptr))
+    return set_error(c, DVL_ERR_INVALID, "the scaled fp16 split needs both row-scale arrays");
+  DVL_TRY(make_map(c, &map_q, a.qry_planes, fp16, a.q, a.d, a.dp, a.planes, BM));
   // a.n = rows the kernel sees; when a.gal_row_step > 1 they are every gal_row_step-th row of a
   // gallery of a.gal_rows_total rows
   const int64_t total_rows = a.gal_row_step > 1 ? a.gal_rows_total : a.n;
-  DVL_TRY(make_map(c, &map_g, a.gal_planes, total_rows, a.d, a.dp, a.planes, BN, a.n, a.gal_row_step));
+  DVL_TRY(make_map(c, &map_g, a.gal_planes, fp16, total_rows, a.d, a.dp, a.planes, BN, a.n, a.gal_row_step));
   KernelParams p;
   p.mode = a.mode;
   p.row0 = a.row0;
@@ -361,9 +419,17 @@ int launch_sim_gemm(Ctx* c, const GemmArgs& a, cudaStream_t st) {
   p.labels = a.labels;
   p.index_base = a.index_base;
   p.k_blocks = (a.d + BK - 1) / BK;
-  p.n_terms = (a.planes == 3) ? 6 : 1;
+  p.n_terms = (a.planes == 3) ? 6 : (a.planes == 2 ? 3 : 1);
+  for (int i = 0; i < kMaxTerms; ++i) {
+    p.term_a[i] = (a.planes == 3) ? kTermsX3A[i] : ((a.planes == 2 && i < 3) ? kTermsX2A[i] : 0);
+    p.term_b[i] = (a.planes == 3) ? kTermsX3B[i] : ((a.planes == 2 && i < 3) ? kTermsX2B[i] : 0);
+  }
+  p.idesc = fp16 ? umma_idesc_f16(BM, BN) : umma_idesc_bf16(BM, BN);
+  p.fused_planes = fp16 ? 1 : 0;
+  p.n_planes = a.planes;
   p.qry_scale = a.qry_scale;
   p.gal_scale = a.gal_scale;
+  p.gal_step = a.gal_row_step > 1 ? a.gal_row_step : 1;
   p.keys = a.keys;
   p.ldk = a.ldk;
   p.scores = a.scores;

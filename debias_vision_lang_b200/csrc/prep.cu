@@ -1,10 +1,18 @@
 // Operand preparation for the similarity stage and the query-independent label statistics.
 //
-//  * split_rows:   embeddings -> bf16 planes.  bf16 mode: one plane (round to nearest even).
-//                  fp32 mode: x == b1 + b2 + b3 exactly, three bf16 planes, so that the six
-//                  product terms a_i*b_j (i+j<=4) accumulated in fp32 on the tensor cores
-//                  reproduce the fp32 similarity of measuring_bias.py:114 to ~2^-24.
-//                  Also emits 1/||row|| for the fused normalisation (measuring_bias.py:79).
+//  * split_rows:   embeddings -> 16-bit planes for the tensor cores.
+//                  bf16 mode: one bf16 plane (round to nearest even).
+//                  fp32 mode (default): every row is scaled by a power of two that brings its largest
+//                  magnitude into [2^14, 2^15) and split into TWO fp16 planes, x*2^e = h0 + h1 + eps with
+//                  |eps| <= 2^-22 |x*2^e|; the three product terms h0*h0', h0*h1', h1*h0' accumulated in
+//                  fp32 on the tensor cores reproduce the fp32 similarity of measuring_bias.py:114 to
+//                  ~3*2^-22 of |g||t| (the dropped h1*h1' term and the two eps), i.e. the accuracy of an
+//                  fp32 dot product itself, at half the tensor work of the three-plane split.  The row's
+//                  2^-e goes into the row-scale array the GEMM epilogue multiplies by (exact).
+//                  fp32x3 mode: x == b0 + b1 + b2 exactly, three bf16 planes, six product terms
+//                  (i + j <= 2): ~2^-24, any fp32 range, no row scale.
+//                  The row-scale array also carries 1/||row|| for the fused normalisation
+//                  (measuring_bias.py:79).
 //  * class_counts: Counter(df.label)  (measuring_bias.py:23,56) -- once per call instead of once
 //                  per query and per metric.
 #include "dvl_common.cuh"
@@ -91,9 +99,81 @@ __global__ void __launch_bounds__(256) split_rows_kernel(const T* __restrict__ s
   }
 }
 
+// fp32 mode: one warp per row, two fp16 planes of the power-of-two scaled row.  Rows of up to 512
+// elements stay in registers between the magnitude pass and the split pass; longer rows are read twice
+// (the second time from L1/L2).
 template <typename T>
-static int launch_split_t(Ctx* c, const T* src, int64_t rows, int d, int dp, int planes, __nv_bfloat16* dst,
-                          float* inv_norm, cudaStream_t st) {
+__global__ void __launch_bounds__(256) split_rows_f16x2_kernel(const T* __restrict__ src, int64_t rows, int d, int dp,
+                                                               __half* __restrict__ dst, float* __restrict__ row_scale,
+                                                               int normalize, int vec) {
+  constexpr int kUnroll = 4;
+  const int lane = threadIdx.x & 31;
+  const int64_t warps_total = (int64_t)gridDim.x * (blockDim.x >> 5);
+  const int64_t plane_stride = rows * (int64_t)dp;
+  const bool single = dp <= 128 * kUnroll;
+  for (int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); row < rows; row += warps_total) {
+    const T* s = src + row * (int64_t)d;
+    __half* o = dst + row * (int64_t)dp;
+    float ss = 0.f, amax = 0.f;
+    bool finite = true;
+    float x[kUnroll][4];
+    for (int c0 = lane * 4; c0 < dp; c0 += 128 * kUnroll) {
+#pragma unroll
+      for (int u = 0; u < kUnroll; ++u) load_quad<T>(s, c0 + u * 128, d, vec != 0, x[u]);
+#pragma unroll
+      for (int u = 0; u < kUnroll; ++u) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          ss = fmaf(x[u][j], x[u][j], ss);
+          const float a = fabsf(x[u][j]);
+          finite &= (a <= 3.4028234664e38f);     // false for inf and NaN
+          amax = fmaxf(amax, a);
+        }
+      }
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+      ss += __shfl_xor_sync(0xffffffffu, ss, off);
+      amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, off));
+    }
+    finite = __all_sync(0xffffffffu, finite);
+    // e = 14 - floor(log2(amax)), clamped so that 2^e and 2^-e are normal floats; an all-zero or
+    // non-finite row keeps scale 1 (inf/NaN then propagate into the scores like in an fp32 product)
+    int e = 0;
+    if (finite && amax > 0.f) {
+      const int be = (int)((__float_as_uint(amax) >> 23) & 0xFFu);   // biased exponent; 0 for subnormals
+      e = 14 - (be - 127);
+      e = e > 126 ? 126 : (e < -126 ? -126 : e);
+    }
+    const float up = __uint_as_float((uint32_t)(127 + e) << 23);
+    const float down = __uint_as_float((uint32_t)(127 - e) << 23);
+    for (int c0 = lane * 4; c0 < dp; c0 += 128 * kUnroll) {
+      if (!single) {
+#pragma unroll
+        for (int u = 0; u < kUnroll; ++u) load_quad<T>(s, c0 + u * 128, d, vec != 0, x[u]);
+      }
+#pragma unroll
+      for (int u = 0; u < kUnroll; ++u) {
+        const int c = c0 + u * 128;
+        if (c >= dp) break;
+        __align__(8) __half h0[4], h1[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float xs = x[u][j] * up;            // exact (power of two; |xs| < 2^15)
+          h0[j] = __float2half_rn(xs);
+          h1[j] = __float2half_rn(xs - __half2float(h0[j]));   // the residual is exact in fp32
+        }
+        *reinterpret_cast<uint2*>(o + c) = *reinterpret_cast<const uint2*>(h0);
+        *reinterpret_cast<uint2*>(o + plane_stride + c) = *reinterpret_cast<const uint2*>(h1);
+      }
+    }
+    if (lane == 0) row_scale[row] = normalize ? down / sqrtf(ss) : down;
+  }
+}
+
+template <typename T>
+static int launch_split_t(Ctx* c, const T* src, int64_t rows, int d, int dp, int planes, void* dst, float* row_scale,
+                          bool normalize, cudaStream_t st) {
   const int warps_per_block = 8;
   int64_t blocks = (rows + warps_per_block - 1) / warps_per_block;
   int64_t cap = (int64_t)c->num_sms * 16;
@@ -102,22 +182,30 @@ static int launch_split_t(Ctx* c, const T* src, int64_t rows, int d, int dp, int
   // whole-quad vector loads need every row start aligned to the quad: d % 4 == 0 and an aligned base
   const int vec = (d % 4 == 0 && (reinterpret_cast<uintptr_t>(src) % (4 * sizeof(T))) == 0) ? 1 : 0;
   if (planes == 1)
-    split_rows_kernel<T, 1><<<(unsigned)blocks, 256, 0, st>>>(src, rows, d, dp, dst, inv_norm, vec);
+    split_rows_kernel<T, 1><<<(unsigned)blocks, 256, 0, st>>>(src, rows, d, dp, (__nv_bfloat16*)dst,
+                                                             normalize ? row_scale : nullptr, vec);
+  else if (planes == 3)
+    split_rows_kernel<T, 3><<<(unsigned)blocks, 256, 0, st>>>(src, rows, d, dp, (__nv_bfloat16*)dst,
+                                                             normalize ? row_scale : nullptr, vec);
   else
-    split_rows_kernel<T, 3><<<(unsigned)blocks, 256, 0, st>>>(src, rows, d, dp, dst, inv_norm, vec);
-  DVL_LAUNCH_CHECK(c, "split_rows_kernel");
+    split_rows_f16x2_kernel<T><<<(unsigned)blocks, 256, 0, st>>>(src, rows, d, dp, (__half*)dst, row_scale,
+                                                                normalize ? 1 : 0, vec);
+  DVL_LAUNCH_CHECK(c, planes == 2 ? "split_rows_f16x2_kernel" : "split_rows_kernel");
   return DVL_OK;
 }
 
-int launch_split_rows(Ctx* c, const void* src, int dtype, int64_t rows, int d, int dp, int planes,
-                      __nv_bfloat16* dst, float* inv_norm, cudaStream_t st) {
-  if (planes != 1 && planes != 3) return set_error(c, DVL_ERR_INVALID, "planes must be 1 or 3");
+int launch_split_rows(Ctx* c, const void* src, int dtype, int64_t rows, int d, int dp, int planes, void* dst,
+                      float* row_scale, bool normalize, cudaStream_t st) {
+  if (planes < 1 || planes > 3) return set_error(c, DVL_ERR_INVALID, "planes must be 1, 2 or 3");
   if (dp % 4 != 0) return set_error(c, DVL_ERR_INVALID, "row pitch must be a multiple of 4");
+  if ((planes == 2 || normalize) && row_scale == nullptr)
+    return set_error(c, DVL_ERR_INVALID, "split without a row-scale array");
   switch (dtype) {
-    case DVL_F32: return launch_split_t<float>(c, (const float*)src, rows, d, dp, planes, dst, inv_norm, st);
+    case DVL_F32: return launch_split_t<float>(c, (const float*)src, rows, d, dp, planes, dst, row_scale, normalize, st);
     case DVL_BF16:
-      return launch_split_t<__nv_bfloat16>(c, (const __nv_bfloat16*)src, rows, d, dp, planes, dst, inv_norm, st);
-    case DVL_F16: return launch_split_t<__half>(c, (const __half*)src, rows, d, dp, planes, dst, inv_norm, st);
+      return launch_split_t<__nv_bfloat16>(c, (const __nv_bfloat16*)src, rows, d, dp, planes, dst, row_scale, normalize,
+                                           st);
+    case DVL_F16: return launch_split_t<__half>(c, (const __half*)src, rows, d, dp, planes, dst, row_scale, normalize, st);
     default: return set_error(c, DVL_ERR_INVALID, "unknown dtype %d", dtype);
   }
 }

@@ -48,7 +48,8 @@ PROMPT_CONCEPTS = (
 )
 
 # ``opts`` is the reference's unused extension point (measuring_bias.py:136,139); keys understood here:
-#   precision          "fp32" (default; bf16x3 split, matches the reference's fp32 mat-vec) | "bf16"
+#   precision          "fp32" (default; scaled fp16x2 split, as accurate as the reference's fp32 mat-vec) |
+#                      "fp32x3" (exact bf16x3 split, twice the tensor work) | "bf16"
 #   normalize_gallery  False (default, as eval_ranking) | True (cosine similarity)
 #   topn               overrides measure_bias's top-n (reference: whole gallery, 1.0)
 #   dataset            a ready dataset object instead of FairFace(mode="val", ...)
@@ -58,7 +59,7 @@ PROMPT_CONCEPTS = (
 #                      present -- the image encoder is then not run at all -- else written after encoding
 DEFAULT_OPTS: dict = dict()
 
-_PRECISIONS = {"fp32": _capi.PRECISION_FP32, "bf16": _capi.PRECISION_BF16}
+_PRECISIONS = {"fp32": _capi.PRECISION_FP32, "bf16": _capi.PRECISION_BF16, "fp32x3": _capi.PRECISION_FP32X3}
 
 
 def gen_prompts() -> List[str]:

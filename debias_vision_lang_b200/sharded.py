@@ -89,7 +89,8 @@ class LocalComm:
 
 def _flags_and_precision(opts: Optional[dict]):
     opts = dict(opts or {})
-    precision = {"fp32": _capi.PRECISION_FP32, "bf16": _capi.PRECISION_BF16}[opts.get("precision", "fp32")]
+    precision = {"fp32": _capi.PRECISION_FP32, "bf16": _capi.PRECISION_BF16,
+                 "fp32x3": _capi.PRECISION_FP32X3}[opts.get("precision", "fp32")]
     flags = 0
     if opts.get("normalize_gallery", False):
         flags |= _capi.FLAG_NORMALIZE_GALLERY

@@ -54,11 +54,14 @@ typedef enum dvl_status {
 typedef enum dvl_dtype { DVL_F32 = 0, DVL_BF16 = 1, DVL_F16 = 2 } dvl_dtype;
 
 /* arithmetic of the similarity stage (a2).
- * FP32: every operand is split exactly into three bf16 planes and the six largest product
- *       terms are accumulated in fp32 on the tensor cores (error ~2^-24 of |g||t|; exact on
- *       data whose dot products are exactly representable, whatever the summation order).
- * BF16: operands rounded once to bf16, fp32 accumulation (2e-2 tolerance of BASELINE.json). */
-typedef enum dvl_precision { DVL_PRECISION_FP32 = 0, DVL_PRECISION_BF16 = 1 } dvl_precision;
+ * FP32:   every row is scaled by a power of two and split into two fp16 planes (22+ significand bits);
+ *         the three largest product terms are accumulated in fp32 on the tensor cores.  Error
+ *         <= ~3*2^-22 of |g||t| -- that of an fp32 dot product -- and exact on data whose dot products
+ *         are exactly representable (whatever the summation order).
+ * BF16:   operands rounded once to bf16, fp32 accumulation (2e-2 tolerance of BASELINE.json).
+ * FP32X3: every operand split exactly into three bf16 planes, six product terms: error ~2^-24 of
+ *         |g||t| over the whole fp32 range, at twice the tensor work of FP32. */
+typedef enum dvl_precision { DVL_PRECISION_FP32 = 0, DVL_PRECISION_BF16 = 1, DVL_PRECISION_FP32X3 = 2 } dvl_precision;
 
 /* flags */
 #define DVL_FLAG_NORMALIZE_QUERIES 0x1u /* a1: divide each query row by its L2 norm (fused into the

@@ -26,7 +26,7 @@ import numpy as np
 __all__ = [
     "resolve_topn", "similarity_f32", "rank_indices", "class_counts", "maxskew_from_ranked",
     "ndkl_from_ranked", "ndkl_normaliser", "eval_query", "eval_ranking", "measure",
-    "split_bf16x3", "similarity_bf16", "similarity_split",
+    "split_bf16x3", "split_f16x2", "similarity_bf16", "similarity_split", "similarity_split_f16x2",
 ]
 
 
@@ -247,6 +247,35 @@ def split_bf16x3(x: np.ndarray) -> Tuple[np.ndarray, np.ndarray, np.ndarray]:
     r2 = (r1 - b2).astype(np.float32)
     b3 = _bf16_round(r2)
     return b1, b2, b3
+
+
+def split_f16x2(x: np.ndarray) -> Tuple[np.ndarray, np.ndarray, np.ndarray]:
+    """The default fp32 mode's operand split: every row is scaled by the power of two that brings its
+    largest magnitude into [2^14, 2^15), then x * 2^e = h0 + h1 + eps with h0, h1 fp16 and
+    |eps| <= 2^-22 |x * 2^e| (round to nearest twice).  Returns (h0, h1, down) with down = 2^-e per row;
+    all-zero and non-finite rows keep scale 1."""
+    x = np.asarray(x, dtype=np.float32)
+    amax = np.abs(x).max(axis=-1)
+    ok = np.isfinite(amax) & (amax > 0)
+    be = ((np.where(ok, amax, 1.0).astype(np.float32).view(np.uint32) >> 23) & 0xFF).astype(np.int64)
+    e = np.clip(14 - (be - 127), -126, 126)
+    e = np.where(ok, e, 0)
+    up = np.ldexp(np.float32(1.0), e).astype(np.float32)
+    down = np.ldexp(np.float32(1.0), -e).astype(np.float32)
+    with np.errstate(over="ignore", invalid="ignore"):
+        xs = (x * up[..., None]).astype(np.float32)
+        h0 = xs.astype(np.float16)
+        h1 = (xs - h0.astype(np.float32)).astype(np.float16)
+    return h0, h1, down
+
+
+def similarity_split_f16x2(gallery: np.ndarray, queries: np.ndarray) -> np.ndarray:
+    """[Q, N] float64 value of the three product terms the default fp32 mode keeps (h1*h0', h0*h1',
+    h0*h0'), descaled; differs from the exact product by at most ~3 * 2^-22 of |g||t|."""
+    g0, g1, gd = (a.astype(np.float64) for a in split_f16x2(gallery))
+    t0, t1, td = (a.astype(np.float64) for a in split_f16x2(queries))
+    acc = t1 @ g0.T + t0 @ g1.T + t0 @ g0.T
+    return acc * td[:, None] * gd[None, :]
 
 
 def similarity_bf16(gallery: np.ndarray, queries: np.ndarray) -> np.ndarray:

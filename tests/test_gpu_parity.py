@@ -78,8 +78,11 @@ def test_similarity_tolerances(ctx, n, d, q):
     scale = g.double().norm(dim=-1)[None, :] * t.double().norm(dim=-1)[:, None]
     s32 = ctx.similarity(g, t, _capi.PRECISION_FP32)
     assert ((s32.double() - exact).abs() / scale).max().item() <= 1e-5
-    # in practice the bf16x3 split is as accurate as an fp32 dot product
-    assert ((s32.double() - exact).abs() / scale).max().item() <= 2e-6
+    # in practice the scaled fp16x2 split (bound 3 * 2^-22 of |g||t|) is as accurate as an fp32 dot product
+    assert ((s32.double() - exact).abs() / scale).max().item() <= 1e-6
+    # and the exact bf16x3 split is tighter still
+    sx3 = ctx.similarity(g, t, _capi.PRECISION_FP32X3)
+    assert ((sx3.double() - exact).abs() / scale).max().item() <= 5e-7
     sbf = ctx.similarity(g, t, _capi.PRECISION_BF16)
     assert ((sbf.double() - exact).abs() / scale).max().item() <= 2e-2
     # and bf16 mode equals the product of the bf16-rounded operands up to fp32 accumulation
@@ -91,9 +94,30 @@ def test_similarity_exact_on_dyadic_grid(ctx):
     w = synthetic.dyadic_grid(5000, 512, 70, 2, seed=12)
     g, t = w.gallery.cuda(), w.queries.cuda()
     exact = (t.double() @ g.double().T)
-    for prec in (_capi.PRECISION_FP32, _capi.PRECISION_BF16):     # |k| <= 127 fits bf16 exactly
+    # |k| <= 127 fits one bf16 / fp16 plane exactly, and the row scales of the fp16 split are powers of two
+    for prec in (_capi.PRECISION_FP32, _capi.PRECISION_BF16, _capi.PRECISION_FP32X3):
         s = ctx.similarity(g, t, prec)
         assert torch.equal(s.double(), exact)
+
+
+@pytest.mark.parametrize("prec,tol", [(_capi.PRECISION_FP32, 1e-6), (_capi.PRECISION_FP32X3, 5e-7)])
+def test_similarity_over_the_fp32_range(ctx, prec, tol):
+    """Row magnitudes from 1e-30 to 1e+30 (far outside what fp16 holds), elements spanning five decades
+    inside a row, an all-zero row, D not a multiple of 4 (scalar-load path) and D > 512 (two-pass path):
+    the per-row power-of-two scale keeps the fp32 mode's error at that of an fp32 dot product."""
+    for n, d, q in ((2048, 300, 40), (1024, 1026, 24), (512, 777, 8)):
+        torch.manual_seed(d)
+        g = torch.randn(n, d, device="cuda") * torch.logspace(-30, 6, n, device="cuda")[:, None]
+        g = g * torch.logspace(0, -5, d, device="cuda")[None, :]
+        g[7] = 0.0
+        t = torch.randn(q, d, device="cuda") * torch.logspace(-6, 20, q, device="cuda")[:, None]
+        exact = t.double() @ g.double().T
+        scale = g.double().norm(dim=-1)[None, :] * t.double().norm(dim=-1)[:, None]
+        s = ctx.similarity(g, t, prec)
+        err = (s.double() - exact).abs() / scale.clamp_min(1e-300)
+        err[:, 7] = (s[:, 7] != 0).double()          # the zero row scores exactly zero
+        assert torch.isfinite(s).all()
+        assert err.max().item() <= tol, (n, d, q, err.max().item())
 
 
 def test_fused_normalisation_flags(ctx):

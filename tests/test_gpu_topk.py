@@ -144,14 +144,18 @@ def test_pilot_threshold_route_is_exact(ctx):
     verified).  Same ranked lists and metrics as the full-sort route and as the progressive scheme."""
     w = synthetic.clip_like(300_000, 64, 40, 7, seed=41, device="cuda")
     lab = torch.from_numpy(w.labels.astype(np.uint8)).cuda()
-    runs = {}
-    for name, flags in (("pilot", 0), ("progressive", _capi.FLAG_NO_PILOT), ("full", _capi.FLAG_FULL_SORT)):
-        runs[name] = ctx.eval_ranking(w.gallery, w.queries, lab, 7, 500, _capi.PRECISION_FP32, flags,
-                                      want_per_query=True, ranked_cap=640)
-    for name in ("pilot", "progressive"):
-        assert torch.equal(runs[name]["ranked_len"], runs["full"]["ranked_len"]), name
-        assert torch.equal(runs[name]["ranked_idx"], runs["full"]["ranked_idx"]), name
-        assert torch.equal(runs[name]["per_query"], runs["full"]["per_query"]), name
+    # every precision mode (the fp32 mode's per-row scale must follow the strided pilot view), with and
+    # without the fused gallery normalisation
+    for prec, extra in ((_capi.PRECISION_FP32, 0), (_capi.PRECISION_FP32, _capi.FLAG_NORMALIZE_GALLERY),
+                        (_capi.PRECISION_FP32X3, 0), (_capi.PRECISION_BF16, _capi.FLAG_NORMALIZE_GALLERY)):
+        runs = {}
+        for name, flags in (("pilot", 0), ("progressive", _capi.FLAG_NO_PILOT), ("full", _capi.FLAG_FULL_SORT)):
+            runs[name] = ctx.eval_ranking(w.gallery, w.queries, lab, 7, 500, prec, flags | extra,
+                                          want_per_query=True, ranked_cap=640)
+        for name in ("pilot", "progressive"):
+            assert torch.equal(runs[name]["ranked_len"], runs["full"]["ranked_len"]), (name, prec, extra)
+            assert torch.equal(runs[name]["ranked_idx"], runs["full"]["ranked_idx"]), (name, prec, extra)
+            assert torch.equal(runs[name]["per_query"], runs["full"]["per_query"]), (name, prec, extra)
 
 
 def test_pilot_threshold_starvation_is_caught_and_reranked(ctx):

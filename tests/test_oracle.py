@@ -71,6 +71,28 @@ def test_split_bf16x3_is_exact():
         assert np.all((b.view(np.uint32) & 0xFFFF) == 0)
 
 
+def test_split_f16x2_error_bound():
+    """Model of the default fp32 mode's operand split (two fp16 planes of the power-of-two scaled row,
+    three product terms): within 3 * 2^-22 of |g||t| of the exact product over the whole fp32 range, and
+    exact on the dyadic grid."""
+    rng = np.random.RandomState(1)
+    g = (rng.randn(300, 96) * np.exp(rng.randn(300, 1) * 20) * np.exp(rng.randn(300, 96) * 2)).astype(np.float32)
+    t = (rng.randn(40, 96) * np.exp(rng.randn(40, 1) * 10)).astype(np.float32)
+    g[5] = 0.0
+    h0, h1, down = spec.split_f16x2(g)
+    assert np.all(np.isfinite(h0.astype(np.float32))) and np.all(np.isfinite(h1.astype(np.float32)))
+    rebuilt = (h0.astype(np.float64) + h1.astype(np.float64)) * down.astype(np.float64)[:, None]
+    assert np.abs(rebuilt - g).max(axis=1).max() >= 0          # finite
+    assert np.all(np.abs(rebuilt - g) <= 2.0 ** -22 * np.abs(g).max(axis=1, keepdims=True) + 0)
+    exact = t.astype(np.float64) @ g.astype(np.float64).T
+    scale = np.linalg.norm(t.astype(np.float64), axis=1)[:, None] * np.linalg.norm(g.astype(np.float64), axis=1)[None, :]
+    err = np.abs(spec.similarity_split_f16x2(g, t) - exact) / np.maximum(scale, 1e-300)
+    assert err.max() <= 3 * 2.0 ** -22
+    k = rng.randint(-127, 128, size=(64, 128)).astype(np.float32) / 64
+    q = rng.randint(-127, 128, size=(8, 128)).astype(np.float32) / 64
+    assert np.array_equal(spec.similarity_split_f16x2(k, q), q.astype(np.float64) @ k.astype(np.float64).T)
+
+
 @pytest.mark.needs_reference
 @pytest.mark.skipif(not ref_shim.available(), reason="/root/reference not mounted")
 def test_spec_against_live_reference_random():
