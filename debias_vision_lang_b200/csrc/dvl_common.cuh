@@ -151,6 +151,19 @@ __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&v)[32])
       : "memory");
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// The same wait when other instructions were issued between the load and the wait (software-pipelined
+// epilogue): the 32 destination registers are passed as in/out operands, so the compiler treats the wait
+// as the point where they are defined and cannot read (or copy) them earlier, while the load is in flight.
+__device__ __forceinline__ void tmem_ld_wait_regs(uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.wait::ld.sync.aligned;"
+      : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), "+r"(v[7]), "+r"(v[8]),
+        "+r"(v[9]), "+r"(v[10]), "+r"(v[11]), "+r"(v[12]), "+r"(v[13]), "+r"(v[14]), "+r"(v[15]), "+r"(v[16]),
+        "+r"(v[17]), "+r"(v[18]), "+r"(v[19]), "+r"(v[20]), "+r"(v[21]), "+r"(v[22]), "+r"(v[23]), "+r"(v[24]),
+        "+r"(v[25]), "+r"(v[26]), "+r"(v[27]), "+r"(v[28]), "+r"(v[29]), "+r"(v[30]), "+r"(v[31])
+      :
+      : "memory");
+}
 
 // UMMA shared-memory matrix descriptor, K-major operand in the 128-byte-swizzle canonical
 // layout TMA produces for a {64 bf16, rows} box: 8-row x 128 B atoms, 1024 B apart.

@@ -38,6 +38,7 @@
 // gallery block (read from HBM once, then L2 hits) while the small query matrix stays
 // L2-resident.
 #include <stdarg.h>
+#include <stdlib.h>
 
 #include "dvl_common.cuh"
 #include "dvl_internal.h"
@@ -252,16 +253,21 @@ sim_gemm_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
         // slots, the values go through a 32-word shared-memory row so that the bit loop can index them.
         uint32_t* mine = epi_scratch + (threadIdx.x - 64) * 33;
         unsigned long long* list = p.cand + (int64_t)qrow * p.cap;
-#pragma unroll 1
-        for (int chunk = chunk0; chunk < chunk0 + BN / 64; ++chunk) {
-          uint32_t v[32];
+        // software pipeline over the warp's four 32-column chunks: the accumulator read of chunk c+1 is
+        // in flight while chunk c is processed
+        uint32_t vbuf[2][32];
+        tmem_ld_32x32(taddr + (uint32_t)(chunk0 * 32), vbuf[0]);
+#pragma unroll
+        for (int ci = 0; ci < BN / 64; ++ci) {
+          const int chunk = chunk0 + ci;
+          uint32_t (&v)[32] = vbuf[ci & 1];
           const int64_t col0 = p.row0 + gb * BN + chunk * 32;
-          // the chunk's 32 gallery-row factors: lane j fetches column j's (one coalesced load, requested
-          // before the accumulator read so that both latencies overlap), the element loop gets them by shuffle
+          // the chunk's 32 gallery-row factors: lane j fetches column j's (one coalesced load), the element
+          // loop gets them by shuffle
           float gs_lane = 1.0f;
           if (p.gal_scale != nullptr) gs_lane = (col0 + lane < p.n) ? __ldg(p.gal_scale + (col0 + lane) * p.gal_step) : 0.f;
-          tmem_ld_32x32(taddr + (uint32_t)(chunk * 32), v);
-          tmem_ld_wait();
+          tmem_ld_wait_regs(v);
+          if (ci + 1 < BN / 64) tmem_ld_32x32(taddr + (uint32_t)((chunk + 1) * 32), vbuf[(ci + 1) & 1]);
           // uniform branches, outside the element loops (a shuffle under a per-element branch is neither
           // if-converted nor pipelined by the compiler)
           if (p.gal_scale != nullptr) {
@@ -292,14 +298,17 @@ sim_gemm_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
           }
         }
       } else {
-#pragma unroll 1
-      for (int chunk = chunk0; chunk < chunk0 + BN / 64; ++chunk) {
-        uint32_t v[32];
+      uint32_t vbuf[2][32];                        // software pipeline as in the filter branch
+      tmem_ld_32x32(taddr + (uint32_t)(chunk0 * 32), vbuf[0]);
+#pragma unroll
+      for (int ci = 0; ci < BN / 64; ++ci) {
+        const int chunk = chunk0 + ci;
+        uint32_t (&v)[32] = vbuf[ci & 1];
         const int64_t col0 = p.row0 + gb * BN + chunk * 32;
-        float gs_lane = 1.0f;                      // as in the filter branch
+        float gs_lane = 1.0f;
         if (p.gal_scale != nullptr) gs_lane = (col0 + lane < p.n) ? __ldg(p.gal_scale + (col0 + lane) * p.gal_step) : 0.f;
-        tmem_ld_32x32(taddr + (uint32_t)(chunk * 32), v);
-        tmem_ld_wait();
+        tmem_ld_wait_regs(v);
+        if (ci + 1 < BN / 64) tmem_ld_32x32(taddr + (uint32_t)((chunk + 1) * 32), vbuf[(ci + 1) & 1]);
         if (p.gal_scale != nullptr) {
 #pragma unroll
           for (int j = 0; j < 32; ++j)
@@ -309,19 +318,33 @@ sim_gemm_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
           for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) * qs);
         }
         if (p.mode == kGemmStore) {
-          if (row_ok) {
-            if (p.scores != nullptr) {
-              float* dst = p.scores + (int64_t)qrow * p.lds + col0;
+          // A thread owns one query ROW of the chunk, but a row's 32 columns are only 128 bytes of output:
+          // stored from the registers, every store instruction of the warp touches 32 different lines with
+          // 16 bytes each.  The chunk is transposed through the warp's 32 x 33-word scratch instead, and each
+          // instruction writes one row's 128 contiguous bytes (8x fewer L2 write transactions; time-neutral
+          // on config 2, where key conversion + stores together are 37 of the GEMM's 140 us).
+          uint32_t* tile = epi_scratch + (warp - 2) * (32 * 33);
+          const int qrow0 = qt * BM + quarter * 32;             // first query row of this warp
+          const int rows_ok = (p.q - qrow0 < 32) ? (p.q - qrow0) : 32;   // <= 0: nothing to store
+          if (p.scores != nullptr) {
 #pragma unroll
-              for (int j = 0; j < 32; j += 4) st_global_v4(dst + j, v[j], v[j + 1], v[j + 2], v[j + 3]);
-            }
-            if (p.keys != nullptr) {
-              uint32_t* dst = p.keys + (int64_t)qrow * p.ldk + col0;
+            for (int j = 0; j < 32; ++j) tile[lane * 33 + j] = v[j];
+            __syncwarp();
+            float* dst = p.scores + (int64_t)qrow0 * p.lds + col0 + lane;
+#pragma unroll 8
+            for (int r = 0; r < 32; ++r)
+              if (r < rows_ok) dst[(int64_t)r * p.lds] = __uint_as_float(tile[r * 33 + lane]);
+            __syncwarp();
+          }
+          if (p.keys != nullptr) {
 #pragma unroll
-              for (int j = 0; j < 32; j += 4)
-                st_global_v4(dst + j, score_to_key(__uint_as_float(v[j])), score_to_key(__uint_as_float(v[j + 1])),
-                             score_to_key(__uint_as_float(v[j + 2])), score_to_key(__uint_as_float(v[j + 3])));
-            }
+            for (int j = 0; j < 32; ++j) tile[lane * 33 + j] = score_to_key(__uint_as_float(v[j]));
+            __syncwarp();
+            uint32_t* dst = p.keys + (int64_t)qrow0 * p.ldk + col0 + lane;
+#pragma unroll 8
+            for (int r = 0; r < 32; ++r)
+              if (r < rows_ok) dst[(int64_t)r * p.ldk] = tile[r * 33 + lane];
+            __syncwarp();
           }
         } else {
           // SEED, first chunk: every row is a candidate, position = column (no atomics, 256 B per thread)
