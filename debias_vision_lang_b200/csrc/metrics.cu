@@ -24,6 +24,8 @@
 //   ndkl_partial one warp per sub-slice: 32 rounds of warp-ballot own-class prefix counts
 //   finalize     fixed-order sum of the partials, MaxSkew from the total counts, 4 doubles/query
 //   mean         fixed-tree mean over the queries
+#include <type_traits>
+
 #include "dvl_common.cuh"
 #include "dvl_internal.h"
 
@@ -282,23 +284,32 @@ __global__ void __launch_bounds__(32 * kWarpsPerCta) ndkl_partial_kernel(const P
     if (lane < kMaxClasses) base[lane] = pref[lane];
     __syncwarp();
     const double pwi_m = __ldg(p.pwi + m);
-    for (long long r0 = begin; r0 < end; r0 += 128) {
-      const long long r = r0 + 4 * lane;             // 0-based rank of this lane's first row
-      const int valid = (end - r >= 4) ? 4 : (end > r ? (int)(end - r) : 0);
-      uint32_t four = 0;
-      double2 pa = make_double2(0.0, 0.0), pb = make_double2(0.0, 0.0);
-      if (valid > 0) {                               // the label pitch is padded to 256, the tables to len + 1024
+    // One round = 128 ranked rows.  Full rounds (all but the last of a query) run without any per-row
+    // condition, so the four table gathers of a lane are in flight together; with the `k < valid` tests
+    // each gather sat in its own branch region and the round paid four L2 latencies in sequence.
+    // a lane's inputs of one round: four labels and the four PWI entries of its rows
+    auto load_round = [&](const long long r0, uint32_t& four, double2& pa, double2& pb) {
+      const long long r = r0 + 4 * lane;
+      four = 0;
+      pa = make_double2(0.0, 0.0);
+      pb = make_double2(0.0, 0.0);
+      if (r < end) {                                 // the label pitch is padded to 256, the tables to len + 1024
         four = __ldg(reinterpret_cast<const uint32_t*>(lab + r));
         pa = __ldg(reinterpret_cast<const double2*>(p.pwi + r));
         pb = __ldg(reinterpret_cast<const double2*>(p.pwi + r + 2));
       }
+    };
+    auto round_body = [&](const long long r0, const uint32_t four, const double2 pa, const double2 pb, auto full_tag) {
+      constexpr bool kFullRound = decltype(full_tag)::value;
+      const long long r = r0 + 4 * lane;             // 0-based rank of this lane's first row
+      const int valid = kFullRound ? 4 : ((end - r >= 4) ? 4 : (end > r ? (int)(end - r) : 0));
       unsigned long long own[W];
 #pragma unroll
       for (int w = 0; w < W; ++w) own[w] = 0ull;
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
         const uint32_t l = (four >> (8 * k)) & (kMaxClasses - 1);   // labels >= C are rejected by the caller
-        if (k < valid) {
+        if (kFullRound || k < valid) {
           if (W == 1 || l < 8) own[0] += 1ull << (8 * (l & 7));
           else own[W - 1] += 1ull << (8 * (l & 7));
         }
@@ -317,18 +328,41 @@ __global__ void __launch_bounds__(32 * kWarpsPerCta) ndkl_partial_kernel(const P
 #pragma unroll
       for (int w = 0; w < W; ++w) run[w] = incl[w] - own[w];
       const double pw4[4] = {pa.x, pa.y, pb.x, pb.y};
+      if (kFullRound) {
+        uint32_t tt[4], ll[4];
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        if (k < valid) {
+        for (int k = 0; k < 4; ++k) {
           const uint32_t l = (four >> (8 * k)) & (kMaxClasses - 1);
           const int sh = 8 * (l & 7);
           const bool hi = (W > 1) && l >= 8;
           const uint32_t before = (uint32_t)((hi ? run[W - 1] : run[0]) >> sh) & 0xFFu;
           if (hi) run[W - 1] += 1ull << sh; else run[0] += 1ull << sh;
-          const uint32_t t = base[l] + before + 1u;  // this row is the t-th of its class
+          tt[k] = base[l] + before + 1u;             // this row is the t-th of its class
+          ll[k] = l;
+        }
+        double dx[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) dx[k] = __ldg(p.dxl + tt[k]);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
           const double tj = pwi_m - pw4[k];          // PWI[m] - PWI[j-1], j = r + k + 1
-          acc_eq = fma(tj, __ldg(p.dxl + t), acc_eq);
-          acc_d = fma(tj, ln_d[l], acc_d);
+          acc_eq = fma(tj, dx[k], acc_eq);
+          acc_d = fma(tj, ln_d[ll[k]], acc_d);
+        }
+      } else {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          if (k < valid) {
+            const uint32_t l = (four >> (8 * k)) & (kMaxClasses - 1);
+            const int sh = 8 * (l & 7);
+            const bool hi = (W > 1) && l >= 8;
+            const uint32_t before = (uint32_t)((hi ? run[W - 1] : run[0]) >> sh) & 0xFFu;
+            if (hi) run[W - 1] += 1ull << sh; else run[0] += 1ull << sh;
+            const uint32_t t = base[l] + before + 1u;
+            const double tj = pwi_m - pw4[k];
+            acc_eq = fma(tj, __ldg(p.dxl + t), acc_eq);
+            acc_d = fma(tj, ln_d[l], acc_d);
+          }
         }
       }
       __syncwarp();
@@ -341,6 +375,17 @@ __global__ void __launch_bounds__(32 * kWarpsPerCta) ndkl_partial_kernel(const P
         if (lane < C) base[lane] += (uint32_t)(tot >> (8 * (lane & 7))) & 0xFFu;
       }
       __syncwarp();
+    };
+    // the next round's inputs are requested before the current round is processed
+    uint32_t four_next;
+    double2 pa_next, pb_next;
+    load_round(begin, four_next, pa_next, pb_next);
+    for (long long r0 = begin; r0 < end; r0 += 128) {
+      const uint32_t four = four_next;
+      const double2 pa = pa_next, pb = pb_next;
+      if (r0 + 128 < end) load_round(r0 + 128, four_next, pa_next, pb_next);
+      if (r0 + 128 <= end) round_body(r0, four, pa, pb, std::true_type{});
+      else round_body(r0, four, pa, pb, std::false_type{});
     }
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) {
