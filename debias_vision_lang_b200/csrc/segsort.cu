@@ -382,6 +382,11 @@ int sort_passes(Ctx* c, const SortArgs& a, int tiles, uint32_t* th, cudaStream_t
   //    per-pass histogram and scan kernels: saves 0.11 ms of histogram/scan time but the look-back adds
   //    0.09-0.19 ms to the scatter (a tile lives ~7 us; a published count takes ~1.5 us to become
   //    visible behind the SM's own scatter stores), so it was not kept;
+  //  * key and label staged as one 8-byte shared-memory entry (one scattered 64-bit store instead of a
+  //    32-bit and an 8-bit one, 5.4 instead of 7.3 wavefronts per 32 keys): 0.521 -> 0.518 ms, not kept.
+  //    Source-level profile of the kernel (ncu, second pass): 77 warp instructions per 32 keys, 30 % of
+  //    them the LOP3s of the ballot matching; stall samples are spread thin -- 17 % on the first use of
+  //    the loaded keys, 11 % on the digit-counter reads, no single hot spot;
   //  * persistent CTAs that prefetch the next tile into a shared-memory staging buffer with
   //    cp.async.bulk while the current one is ranked: 0.63 vs 0.52 ms for the four passes -- the kernel
   //    is bound by shared-memory wavefronts (half of them bank conflicts of the digit-indexed counters
