@@ -375,7 +375,7 @@ def run_ours(args):
         t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_ms_sharded = float(t.item())
-        h2d_sharded = int(g_host.numel() * 4) * world
+        h2d_sharded = int(g_host.numel() * g_host.element_size()) * world
         del g_host
     g_host = (w.gallery if not gallery_sharded else w.gallery[:1]).detach().float().cpu().pin_memory()
     t_host = w.queries.detach().float().cpu().pin_memory()
