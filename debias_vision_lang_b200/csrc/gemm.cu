@@ -38,6 +38,7 @@
 // gallery block (read from HBM once, then L2 hits) while the small query matrix stays
 // L2-resident.
 #include <stdarg.h>
+#include <string.h>
 #include <stdlib.h>
 
 #include "dvl_common.cuh"
@@ -105,96 +106,137 @@ __device__ __forceinline__ unsigned long long make_entry(float s, int64_t gidx) 
   return (static_cast<unsigned long long>(score_to_key(s)) << 32) | (static_cast<unsigned long long>(gidx) << 4);
 }
 
+// kPair: the kernel runs as clusters of two CTAs (one TPC) that drive tcgen05.mma.cta_group::2 together: the
+// pair owns 256 queries x 256 gallery rows; each CTA loads its own 128 query rows and HALF of the gallery
+// tile (the tensor cores read the other half from the peer's shared memory), accumulates its own 128 x 256
+// block in its own TMEM and runs its own epilogue.  Per CTA and k-block 32 KB instead of 48 KB cross
+// L2 -> shared memory for the same tensor work -- the single-CTA kernel is bound by exactly that path on
+// the large-Q workloads (config 4: 590 KB per tile at ~54 B/clk/SM = the measured 1340 TFLOP/s) -- and the
+// ring holds six stages instead of four.  The leader CTA (rank 0) issues every MMA; the full barriers it
+// waits on live in its shared memory and collect the bytes of both CTAs' TMA loads; its commits arrive on
+// both CTAs' empty / accumulator-full barriers; both epilogues arrive on the leader's accumulator-empty one.
+template <bool kPair>
 __global__ void __launch_bounds__(kNumThreads, 1)
 sim_gemm_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_g,
                 const KernelParams p) {
+  constexpr int kBRows = kPair ? BN / 2 : BN;              // gallery rows of a tile this CTA loads
+  constexpr int kBBytesCta = kBRows * BK * 2;              // 16 or 32 KB
+  constexpr int kPlaneStage = kABytes + kBBytesCta;        // one plane pair: 32 or 48 KB
+  constexpr int kRingStages = kStages * kStageBytes / kPlaneStage;   // 6 or 4 (192 KB ring either way)
   extern __shared__ uint8_t smem_raw[];
   // 128-byte-swizzle atoms need 1024-byte aligned tiles
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t bar_base = smem_base + kStages * kStageBytes;
-  // barrier addresses
+  // barrier addresses (same offsets in both CTAs of a pair)
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
-  auto empty_bar = [&](int s) { return bar_base + 8u * (kStages + s); };
-  auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * kStages + a); };
-  auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * kStages + 2 + a); };
-  const uint32_t tmem_slot = bar_base + 8u * (2 * kStages + 4);
+  auto empty_bar = [&](int s) { return bar_base + 64u + 8u * s; };
+  auto tfull_bar = [&](int a) { return bar_base + 128u + 8u * a; };
+  auto tempty_bar = [&](int a) { return bar_base + 144u + 8u * a; };
+  const uint32_t tmem_slot = bar_base + 160u;
   uint32_t* epi_scratch = reinterpret_cast<uint32_t*>(smem_raw + (bar_base + 256u - smem_u32(smem_raw)));
   volatile uint32_t* tmem_slot_ptr =
       reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  const uint32_t cta_rank = kPair ? cluster_ctarank() : 0u;
+  const bool leader = cta_rank == 0u;
+  // work units: a CTA, or a CTA pair, walks the tiles with this stride
+  const int64_t unit = kPair ? (int64_t)(blockIdx.x >> 1) : (int64_t)blockIdx.x;
+  const int64_t n_units = kPair ? (int64_t)(gridDim.x >> 1) : (int64_t)gridDim.x;
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < kStages; ++s) {
+    for (int s = 0; s < kRingStages; ++s) {
       mbar_init(full_bar(s), 1);
       mbar_init(empty_bar(s), 1);
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull_bar(a), 1);
-      mbar_init(tempty_bar(a), kEpiThreads);
+      mbar_init(tempty_bar(a), kPair ? 2 * kEpiThreads : kEpiThreads);
     }
     fence_mbar_init();
     tma_prefetch_desc(&map_q);
     tma_prefetch_desc(&map_g);
   }
   if (warp == 1) {
-    tmem_alloc(tmem_slot, kTmemCols);
-    tmem_relinquish();
+    if (kPair) {
+      tmem_alloc_pair(tmem_slot, kTmemCols);
+      tmem_relinquish_pair();
+    } else {
+      tmem_alloc(tmem_slot, kTmemCols);
+      tmem_relinquish();
+    }
   }
   tc_fence_before();
-  __syncthreads();
+  if (kPair) cluster_sync_all(); else __syncthreads();   // the peer's barriers are initialised, too
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
 
-  // pipeline shape: 4 stages of one plane pair (48 KB), or 2 stages of both planes of both operands (96 KB)
+  // pipeline shape: stages of one plane pair, or half as many stages holding both planes of both operands
   const int iters_per_tile = p.fused_planes ? p.k_blocks : p.k_blocks * p.n_terms;
-  const int n_stages = p.fused_planes ? kStages / 2 : kStages;
-  const uint32_t stage_bytes = p.fused_planes ? 2u * kStageBytes : (uint32_t)kStageBytes;
+  const int n_stages = p.fused_planes ? kRingStages / 2 : kRingStages;
+  const uint32_t stage_bytes = p.fused_planes ? 2u * kPlaneStage : (uint32_t)kPlaneStage;
+  // a tile index t means (query tile t % n_qtiles, gallery block t / n_qtiles); in pair mode a query tile
+  // is 256 rows and this CTA takes its half
+  auto my_qt = [&](int64_t t) { return kPair ? (int)(t % p.n_qtiles) * 2 + (int)cta_rank : (int)(t % p.n_qtiles); };
 
   if (warp == 0) {
     // ------------------------------ TMA producer ------------------------------
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int64_t t = blockIdx.x; t < p.n_tiles; t += gridDim.x) {
-        const int qt = (int)(t % p.n_qtiles);
+      for (int64_t t = unit; t < p.n_tiles; t += n_units) {
+        const int qt = my_qt(t);
         const int64_t gb = t / p.n_qtiles;
-        const int grow = (int)(p.row0 + gb * BN);
+        const int grow = (int)(p.row0 + gb * BN) + (int)cta_rank * kBRows;   // this CTA's part of the gallery block
         for (int it = 0; it < iters_per_tile; ++it) {
           mbar_wait(empty_bar(stage), phase ^ 1u);
-          mbar_arrive_expect_tx(full_bar(stage), stage_bytes);
+          // the leader's barrier counts the bytes of both CTAs
+          if (leader) mbar_arrive_expect_tx(full_bar(stage), kPair ? 2u * stage_bytes : stage_bytes);
+          const uint32_t fb = kPair ? (full_bar(stage) & kPeerBitMask) : full_bar(stage);
           const uint32_t sa = smem_base + stage * stage_bytes;
+          auto load = [&](uint32_t dst, const CUtensorMap* map, int c0, int c1, int c2) {
+            if (kPair) tma_load_3d_pair(dst, map, fb, c0, c1, c2);
+            else tma_load_3d(dst, map, fb, c0, c1, c2);
+          };
           if (p.fused_planes) {
             // [A plane 0][A plane 1][B plane 0][B plane 1] of k-block `it`
-            tma_load_3d(sa, &map_q, full_bar(stage), it * BK, qt * BM, 0);
-            tma_load_3d(sa + kABytes, &map_q, full_bar(stage), it * BK, qt * BM, 1);
-            tma_load_3d(sa + 2 * kABytes, &map_g, full_bar(stage), it * BK, grow, 0);
-            tma_load_3d(sa + 2 * kABytes + kBBytes, &map_g, full_bar(stage), it * BK, grow, 1);
+            load(sa, &map_q, it * BK, qt * BM, 0);
+            load(sa + kABytes, &map_q, it * BK, qt * BM, 1);
+            load(sa + 2 * kABytes, &map_g, it * BK, grow, 0);
+            load(sa + 2 * kABytes + kBBytesCta, &map_g, it * BK, grow, 1);
           } else {
             const int term = it / p.k_blocks;
             const int kb = it - term * p.k_blocks;
-            tma_load_3d(sa, &map_q, full_bar(stage), kb * BK, qt * BM, p.term_a[term]);
-            tma_load_3d(sa + kABytes, &map_g, full_bar(stage), kb * BK, grow, p.term_b[term]);
+            load(sa, &map_q, kb * BK, qt * BM, p.term_a[term]);
+            load(sa + kABytes, &map_g, kb * BK, grow, p.term_b[term]);
           }
           if (++stage == n_stages) { stage = 0; phase ^= 1u; }
         }
       }
     }
   } else if (warp == 1) {
-    // ------------------------------ MMA issuer ------------------------------
-    if (lane == 0) {
+    // ------------------------------ MMA issuer (leader CTA only in pair mode) ------------------------------
+    if (lane == 0 && leader) {
       const uint32_t idesc = p.idesc;
       int stage = 0;
       uint32_t phase = 0;
       int as = 0;
       uint32_t aphase = 0;
-      for (int64_t t = blockIdx.x; t < p.n_tiles; t += gridDim.x) {
-        mbar_wait(tempty_bar(as), aphase ^ 1u);   // epilogue has drained this accumulator
+      auto mma = [&](uint32_t d, uint64_t da, uint64_t db, uint32_t acc) {
+        if (kPair) umma_f16_ss_pair(d, da, db, idesc, acc);
+        else umma_bf16_ss(d, da, db, idesc, acc);
+      };
+      auto commit = [&](uint32_t bar) {
+        if (kPair) umma_commit_pair(bar, (uint16_t)0x3);
+        else umma_commit(bar);
+      };
+      for (int64_t t = unit; t < p.n_tiles; t += n_units) {
+        mbar_wait(tempty_bar(as), aphase ^ 1u);   // the epilogue(s) have drained this accumulator
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + (uint32_t)(as * BN);
         for (int it = 0; it < iters_per_tile; ++it) {
-          mbar_wait(full_bar(stage), phase);      // TMA bytes have landed
+          mbar_wait(full_bar(stage), phase);      // TMA bytes (of both CTAs) have landed
           tc_fence_after();
           const uint32_t sa = smem_base + stage * stage_bytes;
           if (p.fused_planes) {
@@ -202,12 +244,12 @@ sim_gemm_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
 #pragma unroll
             for (int term = 0; term < 3; ++term) {   // h1*h0', h0*h1', h0*h0': smallest first
               const uint32_t ta = sa + (term == 0 ? kABytes : 0);
-              const uint32_t tb = sb + (term == 1 ? kBBytes : 0);
+              const uint32_t tb = sb + (term == 1 ? kBBytesCta : 0);
 #pragma unroll
               for (int k = 0; k < BK / UMMA_K; ++k) {
                 const uint64_t da = umma_desc_sw128(ta + k * (UMMA_K * 2));
                 const uint64_t db = umma_desc_sw128(tb + k * (UMMA_K * 2));
-                umma_bf16_ss(tmem_d, da, db, idesc, (it > 0 || term > 0 || k > 0) ? 1u : 0u);
+                mma(tmem_d, da, db, (it > 0 || term > 0 || k > 0) ? 1u : 0u);
               }
             }
           } else {
@@ -216,13 +258,13 @@ sim_gemm_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
             for (int k = 0; k < BK / UMMA_K; ++k) {
               const uint64_t da = umma_desc_sw128(sa + k * (UMMA_K * 2));
               const uint64_t db = umma_desc_sw128(sb + k * (UMMA_K * 2));
-              umma_bf16_ss(tmem_d, da, db, idesc, (it > 0 || k > 0) ? 1u : 0u);
+              mma(tmem_d, da, db, (it > 0 || k > 0) ? 1u : 0u);
             }
           }
-          umma_commit(empty_bar(stage));          // smem slot free once these MMAs retire
+          commit(empty_bar(stage));               // smem slot free (in both CTAs) once these MMAs retire
           if (++stage == n_stages) { stage = 0; phase ^= 1u; }
         }
-        umma_commit(tfull_bar(as));               // accumulator complete -> epilogue
+        commit(tfull_bar(as));                    // accumulator complete -> epilogue(s)
         as ^= 1;
         if (as == 0) aphase ^= 1u;
       }
@@ -235,8 +277,8 @@ sim_gemm_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
     const int chunk0 = ((warp - 2) >> 2) * (BN / 64);   // first of this warp's four 32-column chunks
     int as = 0;
     uint32_t aphase = 0;
-    for (int64_t t = blockIdx.x; t < p.n_tiles; t += gridDim.x) {
-      const int qt = (int)(t % p.n_qtiles);
+    for (int64_t t = unit; t < p.n_tiles; t += n_units) {
+      const int qt = my_qt(t);
       const int64_t gb = t / p.n_qtiles;
       const int qrow = qt * BM + row_in_tile;
       const bool row_ok = qrow < p.q;
@@ -364,15 +406,29 @@ sim_gemm_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
       }
       }
       tc_fence_before();
-      mbar_arrive(tempty_bar(as));
+      if (kPair) mbar_arrive_cluster(tempty_bar(as) & kPeerBitMask);   // the leader's barrier counts both epilogues
+      else mbar_arrive(tempty_bar(as));
       as ^= 1;
       if (as == 0) aphase ^= 1u;
     }
   }
 
   tc_fence_before();
-  __syncthreads();
-  if (warp == 1) tmem_dealloc(tmem_base, kTmemCols);
+  if (kPair) cluster_sync_all(); else __syncthreads();   // neither CTA leaves while the peer may touch its memory
+  if (warp == 1) {
+    if (kPair) tmem_dealloc_pair(tmem_base, kTmemCols);
+    else tmem_dealloc(tmem_base, kTmemCols);
+  }
+}
+
+// DVL_GEMM_PAIR=0 / 1 forces the single-CTA / CTA-pair kernel (measurements); unset: chosen by the query count
+int gemm_pair_mode() {
+  static const int mode = [] {
+    const char* e = getenv("DVL_GEMM_PAIR");
+    if (e == nullptr || e[0] == '\0') return -1;
+    return e[0] == '0' ? 0 : 1;
+  }();
+  return mode;
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -427,13 +483,27 @@ int launch_sim_gemm(Ctx* c, const GemmArgs& a, cudaStream_t st) {
   // a.n = rows the kernel sees; when a.gal_row_step > 1 they are every gal_row_step-th row of a
   // gallery of a.gal_rows_total rows
   const int64_t total_rows = a.gal_row_step > 1 ? a.gal_rows_total : a.n;
-  DVL_TRY(make_map(c, &map_g, a.gal_planes, fp16, total_rows, a.d, a.dp, a.planes, BN, a.n, a.gal_row_step));
+  // CTA pairs (cta_group::2).  Measured on one B200 (DVL_GEMM_PAIR=0/1, same box, same run):
+  //   config 5 (fp32 mode, 1 M x 512 x 1000): 2.49 -> 2.37 ms -- the fp16-pair pipeline gets three 64 KB stages
+  //     instead of two 96 KB ones;
+  //   config 3 / config 4 shard (bf16): 1.524 vs 1.541 ms / 14.06 vs 14.78 ms at 1740 vs 1635 MHz, i.e. the same
+  //     cycle count: the bf16 kernel already runs at the sustained (power-capped) tensor rate of this GPU
+  //     (1340-1365 TFLOP/s against a measured sustained cuBLAS peak of 1368), so halving its L2 -> shared
+  //     memory traffic buys nothing;
+  //   config 2 (319 queries): 0.138 -> 0.171 ms -- the second 256-row query tile is three quarters padding.
+  // Hence: pairs for the fp16-pair mode when the query count fills 256-row tiles, single CTAs otherwise.
+  const int64_t rows_single = (int64_t)((a.q + BM - 1) / BM) * BM, rows_pair = (int64_t)((a.q + 2 * BM - 1) / (2 * BM)) * 2 * BM;
+  const bool pair = gemm_pair_mode() == 1 ||
+                    (gemm_pair_mode() < 0 && fp16 && c->num_sms % 2 == 0 && a.q > BM &&
+                     rows_pair * 100 <= rows_single * 104);
+  DVL_TRY(make_map(c, &map_g, a.gal_planes, fp16, total_rows, a.d, a.dp, a.planes, pair ? BN / 2 : BN, a.n,
+                   a.gal_row_step));
   KernelParams p;
   p.mode = a.mode;
   p.row0 = a.row0;
   p.n = a.row1;
   p.q = a.q;
-  p.n_qtiles = (a.q + BM - 1) / BM;
+  p.n_qtiles = pair ? (a.q + 2 * BM - 1) / (2 * BM) : (a.q + BM - 1) / BM;
   p.n_tiles = (int64_t)p.n_qtiles * ((a.row1 - a.row0 + BN - 1) / BN);
   p.tau = a.tau;
   p.cand = a.cand;
@@ -447,7 +517,8 @@ int launch_sim_gemm(Ctx* c, const GemmArgs& a, cudaStream_t st) {
     p.term_a[i] = (a.planes == 3) ? kTermsX3A[i] : ((a.planes == 2 && i < 3) ? kTermsX2A[i] : 0);
     p.term_b[i] = (a.planes == 3) ? kTermsX3B[i] : ((a.planes == 2 && i < 3) ? kTermsX2B[i] : 0);
   }
-  p.idesc = fp16 ? umma_idesc_f16(BM, BN) : umma_idesc_bf16(BM, BN);
+  const int umma_m = pair ? 2 * BM : BM;
+  p.idesc = fp16 ? umma_idesc_f16(umma_m, BN) : umma_idesc_bf16(umma_m, BN);
   p.fused_planes = fp16 ? 1 : 0;
   p.n_planes = a.planes;
   p.qry_scale = a.qry_scale;
@@ -463,11 +534,33 @@ int launch_sim_gemm(Ctx* c, const GemmArgs& a, cudaStream_t st) {
   if (a.scores != nullptr && (a.lds % 4 != 0 || a.lds < ((a.n + BN - 1) / BN) * BN))
     return set_error(c, DVL_ERR_INVALID, "score pitch must cover whole 256-column tiles");
   if (!c->gemm_attr_set) {
-    DVL_CUDA(c, cudaFuncSetAttribute(sim_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
+    DVL_CUDA(c, cudaFuncSetAttribute(sim_gemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)kSmemBytes));
+    DVL_CUDA(c, cudaFuncSetAttribute(sim_gemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)kSmemBytes));
     c->gemm_attr_set = true;
   }
-  int64_t grid = p.n_tiles < c->num_sms ? p.n_tiles : c->num_sms;
-  sim_gemm_kernel<<<(unsigned)grid, kNumThreads, kSmemBytes, st>>>(map_q, map_g, p);
+  if (!pair) {
+    int64_t grid = p.n_tiles < c->num_sms ? p.n_tiles : c->num_sms;
+    sim_gemm_kernel<false><<<(unsigned)grid, kNumThreads, kSmemBytes, st>>>(map_q, map_g, p);
+  } else {
+    // one persistent CTA pair per TPC: a cluster of two CTAs
+    const int64_t pairs = p.n_tiles < c->num_sms / 2 ? p.n_tiles : c->num_sms / 2;
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3((unsigned)(2 * pairs));
+    cfg.blockDim = dim3(kNumThreads);
+    cfg.dynamicSmemBytes = kSmemBytes;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    DVL_CUDA(c, cudaLaunchKernelEx(&cfg, sim_gemm_kernel<true>, map_q, map_g, p));
+  }
   DVL_LAUNCH_CHECK(c, "sim_gemm_kernel");
   return DVL_OK;
 }
