@@ -161,10 +161,13 @@ class Context:
     # ------------------------------------------------------------------------------------
     def eval_ranking(self, gallery: torch.Tensor, queries: torch.Tensor, labels_u8: torch.Tensor, n_classes: int,
                      top_n: int, precision: int = PRECISION_FP32, flags: int = 0, want_per_query: bool = False,
-                     ranked_cap: int = 0, want_scores: bool = False):
+                     ranked_cap: int = 0, want_scores: bool = False, out_per_query: Optional[torch.Tensor] = None,
+                     out_ranked_len: Optional[torch.Tensor] = None):
         """gallery [N,D], queries [Q,D], labels uint8 [N]: all CUDA, contiguous.  Returns a dict with
         ``mean`` (4 python floats) and optionally ``per_query`` [Q,4] f64, ``ranked_len`` [Q] i32,
-        ``ranked_idx`` [Q,ranked_cap] i32, ``scores`` [Q,N] f32 (device tensors)."""
+        ``ranked_idx`` [Q,ranked_cap] i32, ``scores`` [Q,N] f32 (device tensors).  ``out_per_query`` /
+        ``out_ranked_len``: caller-owned output buffers (contiguous f64 [Q,4] / i32 [Q]); a loop that passes the
+        same buffers every time keeps the call identical, which is what the CUDA-graph replay keys on."""
         assert gallery.is_cuda and queries.is_cuda and labels_u8.is_cuda
         assert gallery.is_contiguous() and queries.is_contiguous() and labels_u8.is_contiguous()
         assert labels_u8.dtype == torch.uint8
@@ -178,6 +181,14 @@ class Context:
         mean = (ctypes.c_double * 4)()
         per_query = torch.empty((q, 4), dtype=torch.float64, device=dev) if want_per_query else None
         ranked_len = torch.empty((q,), dtype=torch.int32, device=dev) if (ranked_cap > 0 or want_per_query) else None
+        if out_per_query is not None:
+            assert out_per_query.is_cuda and out_per_query.dtype == torch.float64 and out_per_query.is_contiguous()
+            assert out_per_query.numel() == q * 4
+            per_query = out_per_query
+        if out_ranked_len is not None:
+            assert out_ranked_len.is_cuda and out_ranked_len.dtype == torch.int32 and out_ranked_len.is_contiguous()
+            assert out_ranked_len.numel() == q
+            ranked_len = out_ranked_len
         ranked_idx = torch.full((q, ranked_cap), -1, dtype=torch.int32, device=dev) if ranked_cap > 0 else None
         scores = torch.empty((q, n), dtype=torch.float32, device=dev) if want_scores else None
         rc = lib().dvl_eval_ranking(self._h, self._ptr(gallery), _dtype_code(gallery.dtype), self._ptr(queries),

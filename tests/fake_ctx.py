@@ -106,9 +106,14 @@ class FakeCtx:
                     ranked_idx=ranked_idx, mean=pq.mean(axis=0).tolist())
 
     def eval_ranking(self, gallery, queries, labels_u8, n_classes, top_n, precision=0, flags=0, want_per_query=False,
-                     ranked_cap=0, want_scores=False):
+                     ranked_cap=0, want_scores=False, out_per_query=None, out_ranked_len=None):
         scores = self.similarity(gallery, queries)
-        return self.rank_and_score(scores, labels_u8, n_classes, top_n, ranked_cap)
+        res = self.rank_and_score(scores, labels_u8, n_classes, top_n, ranked_cap)
+        if out_per_query is not None:          # caller-owned output buffers, as in _capi.Context.eval_ranking
+            out_per_query.view(-1, 4).copy_(res["per_query"])
+        if out_ranked_len is not None:
+            out_ranked_len.copy_(res["ranked_len"])
+        return res
 
     def mean(self, per_query):
         return [float(x) for x in (per_query.sum(dim=0) / per_query.shape[0]).tolist()]
