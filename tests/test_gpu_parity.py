@@ -376,3 +376,23 @@ def test_graph_replay_matches_direct_launches(ctx):
     finally:
         ctx.set_profiling(False)
     assert prof["sort_scatter"][0] > 0 and prof["sort_scatter"][1] == 16 and prof["gemm"][1] == 4
+
+
+def test_cta_pair_gemm_variant_passes_the_parity_suite():
+    """The similarity GEMM has a CTA-pair variant (tcgen05.mma.cta_group::2, clusters of two CTAs) that the
+    library only picks for the fp32 mode on large query counts.  DVL_GEMM_PAIR=1 forces it for every shape
+    (the switch is read once per process, hence the subprocess): similarity tolerances, exactness on the
+    dyadic grid, the fp32 range, fused normalisation, the golden vectors end to end and the streaming
+    top-k route must all hold with it."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, DVL_GEMM_PAIR="1")
+    sel = ("similarity or golden or fused_normalisation or stage_isolation or streaming_equals_full_sort "
+           "or pilot_threshold_route or sharded_stages")
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(root, "tests"), "-m", "gpu", "-x", "-q",
+                        "-k", f"({sel}) and not cta_pair", "-p", "no:cacheprovider"],
+                       cwd=root, env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
+    assert " passed" in r.stdout
