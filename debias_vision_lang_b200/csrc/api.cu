@@ -238,10 +238,17 @@ int rank_full(Ctx* c, const uint8_t* labels, int64_t n, int64_t n_gallery, int q
   s.n = n;
   s.ldk = ldk;
   s.q = q;
+  // the whole segment is ranked: the metrics need the NaN count, not the sorted keys
+  const bool whole = top_n >= n;
+  if (whole) {
+    DVL_TRY(ensure(c, c->nan_cnt, (size_t)q * sizeof(uint32_t)));
+    s.nan_cnt = (uint32_t*)c->nan_cnt.ptr;
+  }
   int buf = 0;
   DVL_TRY(launch_segmented_sort(c, s, &buf, st));
   MetricArgs m;
-  m.keys = s.keys[buf];
+  m.keys = whole ? nullptr : s.keys[buf];
+  m.nan_cnt = whole ? (const uint32_t*)c->nan_cnt.ptr : nullptr;
   m.labs = s.labs[buf];
   m.ldk = ldk;
   m.ldl = ldk;
@@ -614,7 +621,7 @@ DVL_API int dvl_destroy(dvl_ctx* c) {
   if (c == nullptr) return DVL_OK;
   dvl::DeviceGuard guard(c->device);
   cudaDeviceSynchronize();
-  dvl::DevBuf* bufs[] = {&c->gal_planes, &c->qry_planes, &c->gal_inv_norm, &c->qry_inv_norm, &c->keys[0], &c->keys[1],
+  dvl::DevBuf* bufs[] = {&c->nan_cnt, &c->gal_planes, &c->qry_planes, &c->gal_inv_norm, &c->qry_inv_norm, &c->keys[0], &c->keys[1],
                          &c->labs[0], &c->labs[1], &c->idxs[0], &c->idxs[1], &c->tile_hist, &c->class_counts,
                          &c->log_tab, &c->per_query, &c->mean_dev, &c->scores_tmp, &c->seg_len, &c->sub_cnt, &c->partial,
                          &c->h_gallery, &c->h_queries, &c->h_labels, &c->cand, &c->cand_cnt, &c->cand_tau,

@@ -22,13 +22,18 @@ constexpr uint32_t kNanKey = 0xFFFFFFFFu;
 
 __host__ __device__ __forceinline__ uint32_t score_to_key(float s) {
 #ifdef __CUDA_ARCH__
-  uint32_t u = __float_as_uint(s);
+  // five instructions: s + 0.0f turns -0 into +0 (round to nearest; not an identity, so it is kept),
+  // negatives keep their bits, non-negatives get the low 31 bits flipped, NaN is replaced last
+  const uint32_t u = __float_as_uint(s + 0.0f);
+  const uint32_t neg = (uint32_t)((int32_t)u >> 31);
+  const uint32_t key = u ^ (~neg & 0x7FFFFFFFu);
+  return (s != s) ? kNanKey : key;
 #else
   union { float f; uint32_t u; } cvt; cvt.f = s; uint32_t u = cvt.u;
-#endif
   if (s != s) return kNanKey;
   if (s == 0.0f) u = 0u;                        // canonical zero
   return (u & 0x80000000u) ? u : (u ^ 0x7FFFFFFFu);
+#endif
 }
 
 __host__ __device__ __forceinline__ float key_to_score(uint32_t k) {

@@ -29,6 +29,7 @@ struct Ctx {
   // named workspace buffers
   DevBuf gal_planes, qry_planes, gal_inv_norm, qry_inv_norm;
   DevBuf keys[2], labs[2], idxs[2];
+  DevBuf nan_cnt;
   DevBuf tile_hist, class_counts, log_tab, per_query, mean_dev, scores_tmp, seg_len, sub_cnt, partial;
   DevBuf h_gallery, h_queries, h_labels;   // staging for the host-input entry point
   // streaming top-k state
@@ -148,6 +149,10 @@ struct SortArgs {
   int64_t n;
   int64_t ldk;
   int q;
+  // When the whole segment is ranked (top_n >= n) the metrics never look at the sorted keys: all they need
+  // besides the labels is the number of NaN rows (dropped from the ranking).  Then the first pass counts
+  // them into nan_cnt [q] and the last pass does not write its keys (4 of its 10 bytes per pair).
+  uint32_t* nan_cnt = nullptr;
 };
 int launch_segmented_sort(Ctx* c, const SortArgs& a, int* out_buf, cudaStream_t st);
 int launch_scores_to_keys(Ctx* c, const float* scores, int64_t lds, uint32_t* keys, int64_t ldk, int64_t n, int q,
@@ -201,6 +206,7 @@ struct MetricArgs {
   int n_classes;
   const unsigned long long* class_counts;  // [n_classes], global
   const int32_t* avail;                    // [q] or null: rows available per query (streaming top-k route)
+  const uint32_t* nan_cnt = nullptr;       // [q] or null: NaN rows per query when keys is null (full sort, top_n >= n)
   double* per_query;                       // [q][4]
   int32_t* ranked_len;                     // [q], always written
 };

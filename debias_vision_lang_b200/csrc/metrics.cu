@@ -132,7 +132,8 @@ __device__ __forceinline__ long long warp_partition_point(long long lo, long lon
 // one warp per query
 __global__ void __launch_bounds__(128) ranked_len_kernel(const uint32_t* __restrict__ keys, int64_t ldk,
                                                          const int32_t* __restrict__ avail, int64_t n_avail,
-                                                         int64_t top_n, int q, int32_t* __restrict__ ranked_len) {
+                                                         int64_t top_n, int q, int32_t* __restrict__ ranked_len,
+                                                         const uint32_t* __restrict__ nan_cnt) {
   const int qi = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (qi >= q) return;
@@ -149,6 +150,8 @@ __global__ void __launch_bounds__(128) ranked_len_kernel(const uint32_t* __restr
       // first position whose key is > kth: the end of the top_n-th row's tie run (keep="all")
       m = warp_partition_point(top_n, n_valid, lane, [&](long long i) { return __ldg(k + i) <= kth; });
     }
+  } else if (nan_cnt != nullptr) {
+    m = n_avail - (long long)nan_cnt[qi];   // whole segment ranked (top_n >= n_avail): every row but the NaN ones
   } else {
     m = top_n < n_avail ? top_n : n_avail;
   }
@@ -554,7 +557,8 @@ int launch_metrics(Ctx* c, const MetricArgs& a, cudaStream_t st) {
   uint32_t* sub_cnt = (uint32_t*)c->sub_cnt.ptr;
   double* partial = (double*)c->partial.ptr;
 
-  ranked_len_kernel<<<(a.q + 3) / 4, 128, 0, st>>>(a.keys, a.ldk, a.avail, a.n_avail, a.top_n, a.q, a.ranked_len);
+  ranked_len_kernel<<<(a.q + 3) / 4, 128, 0, st>>>(a.keys, a.ldk, a.avail, a.n_avail, a.top_n, a.q, a.ranked_len,
+                                                   a.nan_cnt);
   DVL_LAUNCH_CHECK(c, "ranked_len_kernel");
   const unsigned bx = (unsigned)((subs + kWarpsPerCta - 1) / kWarpsPerCta);
   for (int phase = 0; phase < 2; ++phase) {

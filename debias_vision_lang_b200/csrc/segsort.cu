@@ -37,10 +37,11 @@ __global__ void __launch_bounds__(256) scores_to_keys_kernel(const float* __rest
 
 // ---------------------------------------------------------------------------------------
 // pass step 1: digit histogram of one tile
-template <int BITS>
+template <int BITS, bool kCountNan>
 __global__ void __launch_bounds__(kSortThreads) tile_hist_kernel(const uint32_t* __restrict__ keys, int64_t ldk,
                                                                  int64_t n, int shift, int tiles,
-                                                                 uint32_t* __restrict__ tile_hist) {
+                                                                 uint32_t* __restrict__ tile_hist,
+                                                                 uint32_t* __restrict__ nan_cnt) {
   constexpr int RADIX = 1 << BITS;
   constexpr uint32_t MASK = RADIX - 1;
   __shared__ uint32_t hist[RADIX];
@@ -51,6 +52,7 @@ __global__ void __launch_bounds__(kSortThreads) tile_hist_kernel(const uint32_t*
   const uint32_t* seg = keys + (int64_t)q * ldk;
   const int64_t base = (int64_t)t * kTile;
   // ldk is a multiple of 4 and base a multiple of 4096: 16-byte loads are aligned
+  uint32_t nans = 0;                             // first pass only: rows whose score is NaN (key 0xFFFFFFFF)
   if (base + kTile <= n) {
 #pragma unroll
     for (int r = 0; r < kItems / 4; ++r) {
@@ -59,10 +61,17 @@ __global__ void __launch_bounds__(kSortThreads) tile_hist_kernel(const uint32_t*
       atomicAdd(&hist[(v.y >> shift) & MASK], 1u);
       atomicAdd(&hist[(v.z >> shift) & MASK], 1u);
       atomicAdd(&hist[(v.w >> shift) & MASK], 1u);
+      if (kCountNan && max(max(v.x, v.y), max(v.z, v.w)) == kNanKey)     // rare: one compare per four keys
+        nans += (v.x == kNanKey) + (v.y == kNanKey) + (v.z == kNanKey) + (v.w == kNanKey);
     }
   } else {
-    for (int64_t i = base + threadIdx.x; i < n; i += kSortThreads) atomicAdd(&hist[(__ldg(seg + i) >> shift) & MASK], 1u);
+    for (int64_t i = base + threadIdx.x; i < n; i += kSortThreads) {
+      const uint32_t k = __ldg(seg + i);
+      atomicAdd(&hist[(k >> shift) & MASK], 1u);
+      if (kCountNan) nans += (k == kNanKey);
+    }
   }
+  if (kCountNan && nan_cnt != nullptr && nans != 0u) atomicAdd(nan_cnt + q, nans);   // NaN scores are rare
   __syncthreads();
   uint32_t* out = tile_hist + ((int64_t)q * tiles + t) * RADIX;
   for (int i = threadIdx.x; i < RADIX; i += kSortThreads) out[i] = hist[i];
@@ -151,7 +160,7 @@ __device__ __forceinline__ void
 tile_scatter_body(const uint32_t* __restrict__ keys_in, const uint8_t* __restrict__ labs_in,
                   const int32_t* __restrict__ idx_in, const uint8_t* __restrict__ gallery_labels,
                   uint32_t* __restrict__ keys_out, uint8_t* __restrict__ labs_out, int32_t* __restrict__ idx_out,
-                  int64_t ldk, int64_t n, int tiles, const uint32_t* __restrict__ tile_offs) {
+                  int64_t ldk, int64_t n, int tiles, const uint32_t* __restrict__ tile_offs, int write_keys) {
   constexpr int RADIX = 1 << BITS;
   constexpr uint32_t MASK = RADIX - 1;
   constexpr int DPT = RADIX / kSortThreads;      // digits per thread in phase 2
@@ -304,7 +313,7 @@ tile_scatter_body(const uint32_t* __restrict__ keys_in, const uint8_t* __restric
     if (kFull || p < count) {
       const uint32_t k = s_keys[p];
       const uint32_t dst = out_off[(k >> SHIFT) & MASK] + (uint32_t)p;
-      ko[dst] = k;
+      if (write_keys) ko[dst] = k;               // uniform: the last pass of a whole-segment ranking skips it
       lo[dst] = s_labs[p];
       if (kHasIdx) idx_out[seg_off + dst] = s_idx[p];
     }
@@ -316,13 +325,13 @@ __global__ void __launch_bounds__(kSortThreads, 4)   // 64 registers: 32 of the 
 tile_scatter_kernel(const uint32_t* __restrict__ keys_in, const uint8_t* __restrict__ labs_in,
                     const int32_t* __restrict__ idx_in, const uint8_t* __restrict__ gallery_labels,
                     uint32_t* __restrict__ keys_out, uint8_t* __restrict__ labs_out, int32_t* __restrict__ idx_out,
-                    int64_t ldk, int64_t n, int tiles, const uint32_t* __restrict__ tile_offs) {
+                    int64_t ldk, int64_t n, int tiles, const uint32_t* __restrict__ tile_offs, int write_keys) {
   if ((int64_t)(blockIdx.x + 1) * kTile <= n)    // all tiles of a segment but (at most) the last
     tile_scatter_body<BITS, SHIFT, kRank, kFirst, kHasIdx, true>(keys_in, labs_in, idx_in, gallery_labels, keys_out,
-                                                                 labs_out, idx_out, ldk, n, tiles, tile_offs);
+                                                                 labs_out, idx_out, ldk, n, tiles, tile_offs, write_keys);
   else
     tile_scatter_body<BITS, SHIFT, kRank, kFirst, kHasIdx, false>(keys_in, labs_in, idx_in, gallery_labels, keys_out,
-                                                                  labs_out, idx_out, ldk, n, tiles, tile_offs);
+                                                                  labs_out, idx_out, ldk, n, tiles, tile_offs, write_keys);
 }
 
 int sort_rank_mode() {
@@ -344,7 +353,8 @@ int run_pass(Ctx* c, const SortArgs& a, int cur, int tiles, uint32_t* th, cudaSt
     dim3 grid((unsigned)tiles, (unsigned)qn);
     {
       StageScope scope(c, DVL_STAGE_SORT_HIST, st);
-      tile_hist_kernel<BITS><<<grid, kSortThreads, 0, st>>>(a.keys[cur] + off, a.ldk, a.n, SHIFT, tiles, th_q);
+      tile_hist_kernel<BITS, kFirst><<<grid, kSortThreads, 0, st>>>(a.keys[cur] + off, a.ldk, a.n, SHIFT, tiles, th_q,
+                                                                    a.nan_cnt != nullptr ? a.nan_cnt + q0 : nullptr);
       DVL_LAUNCH_CHECK(c, "tile_hist_kernel");
     }
     {
@@ -364,7 +374,8 @@ int run_pass(Ctx* c, const SortArgs& a, int cur, int tiles, uint32_t* th, cudaSt
     auto kern = tile_scatter_kernel<BITS, SHIFT, kRank, kFirst, IDX>;                                             \
     constexpr size_t smem = scatter_smem_bytes<BITS, IDX>();                                                      \
     static_assert(smem <= 48 * 1024, "above 48 KB the kernel needs cudaFuncAttributeMaxDynamicSharedMemorySize"); \
-    kern<<<grid, kSortThreads, smem, st>>>(ki, li, ii, a.gallery_labels, ko, lo, io, a.ldk, a.n, tiles, th_q);    \
+    kern<<<grid, kSortThreads, smem, st>>>(ki, li, ii, a.gallery_labels, ko, lo, io, a.ldk, a.n, tiles, th_q,     \
+                                           (SHIFT + BITS < 32 || a.nan_cnt == nullptr) ? 1 : 0);                   \
   } while (0)
     if (has_idx) DVL_SCATTER(true); else DVL_SCATTER(false);
 #undef DVL_SCATTER
@@ -419,6 +430,7 @@ int launch_segmented_sort(Ctx* c, const SortArgs& a, int* out_buf, cudaStream_t 
   if (a.ldk % 4 != 0) return set_error(c, DVL_ERR_INVALID, "sort pitch must be a multiple of 4");
   DVL_TRY(ensure(c, c->tile_hist, (size_t)a.q * tiles * (1 << kMaxBits) * sizeof(uint32_t)));
   uint32_t* th = (uint32_t*)c->tile_hist.ptr;
+  if (a.nan_cnt != nullptr) DVL_CUDA(c, cudaMemsetAsync(a.nan_cnt, 0, (size_t)a.q * sizeof(uint32_t), st));
   if (sort_rank_mode() == 1)
     DVL_TRY(sort_passes<1>(c, a, tiles, th, st));
   else
