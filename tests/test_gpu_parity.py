@@ -120,6 +120,26 @@ def test_similarity_over_the_fp32_range(ctx, prec, tol):
         assert err.max().item() <= tol, (n, d, q, err.max().item())
 
 
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
+def test_similarity_of_half_precision_inputs(ctx, dtype):
+    """CLIP runs fp16 on CUDA: 16-bit embeddings go through the same split kernels (vector
+    loads when D % 4 == 0, element loads otherwise, mixed gallery/query dtypes) and every precision mode
+    must reproduce the fp32 product of the 16-bit values."""
+    for n, d, q in ((3000, 512, 150), (1500, 130, 20)):
+        torch.manual_seed(n)
+        g = (torch.randn(n, d, device="cuda") * 3).to(dtype)
+        t = torch.randn(q, d, device="cuda")
+        t = (t / t.norm(dim=-1, keepdim=True)).to(dtype)
+        exact = t.double() @ g.double().T
+        scale = g.double().norm(dim=-1)[None, :] * t.double().norm(dim=-1)[:, None]
+        for prec, tol in ((_capi.PRECISION_FP32, 1e-6), (_capi.PRECISION_FP32X3, 5e-7), (_capi.PRECISION_BF16, 2e-2)):
+            s = ctx.similarity(g, t, prec)
+            assert ((s.double() - exact).abs() / scale).max().item() <= tol, (dtype, n, d, q, prec)
+        # fp32 queries against a 16-bit gallery, as measure_bias hands them over (queries are .float()ed, :81)
+        s = ctx.similarity(g, t.float(), _capi.PRECISION_FP32)
+        assert ((s.double() - exact).abs() / scale).max().item() <= 1e-6
+
+
 def test_fused_normalisation_flags(ctx):
     torch.manual_seed(5)
     g = torch.randn(3000, 256, device="cuda") * 7
