@@ -337,7 +337,7 @@ def run_ours(args):
 
         def step():
             r = sharded.evaluate_query_sharded(ctx, comm, w.gallery, all_queries, lab, w.n_classes, top_n,
-                                               {"precision": precision})
+                                               {"precision": precision, "ranked_len": False, "per_query": False})
             return [r["maxskew"]["eq_opp"], r["maxskew"]["dem_par"], r["ndkl"]["eq_opp"], r["ndkl"]["dem_par"]]
     else:
         def step():

@@ -69,6 +69,11 @@ class TorchDistComm:
         self.dist.all_gather_into_tensor(out.view(-1), t.contiguous().view(-1), group=self.group)
         return out
 
+    def all_gather_into(self, out: torch.Tensor, t: torch.Tensor) -> torch.Tensor:
+        """Same into a caller-owned contiguous [world, *t.shape] buffer (no allocation on the way)."""
+        self.dist.all_gather_into_tensor(out.view(-1), t.view(-1), group=self.group)
+        return out
+
 
 class LocalComm:
     """The collectives as plain tensor ops over a list of per-rank tensors: used by
@@ -310,30 +315,39 @@ def evaluate_query_sharded(ctx, comm, gallery: torch.Tensor, queries: torch.Tens
     q0, qn = _query_slice(q, world, rank)
     block = -(-q // world)
     dev = queries.device
-    # Persistent exchange buffer per (context, shape): [block*4 per-query doubles | block ranked lengths].  The
-    # kernels write the per-query results straight into it, and a caller that repeats the evaluation hands
-    # the C ABI the same pointers every time (the CUDA-graph replay of the full-sort route keys on them).
-    key = (id(ctx), str(dev), block)
+    # Persistent exchange buffers per (context, shape).  The kernels write the per-query results straight
+    # into the send buffer, and a caller that repeats the evaluation hands the C ABI the same pointers
+    # every time (the CUDA-graph replay of the full-sort route keys on them).  The step after the local
+    # ranking is pure launch latency (a few tiny kernels + one NCCL call on an idle GPU), so it is kept
+    # to: all-gather into a persistent [world, block, 4] buffer -- which IS the per-query matrix -- and
+    # the mean.  The ranked lengths travel in a second all-gather only when asked for
+    # (opts["ranked_len"], default on) and the per-query matrix is copied out of the reused receive buffer
+    # only when asked for (opts["per_query"], default on); measure_bias itself only needs the means.
+    want_len = bool((opts or {}).get("ranked_len", True)) or ranked_cap > 0
+    key = (id(ctx), str(dev), block, world)
     bufs = _query_shard_bufs.get(key)
     if bufs is None:
-        bufs = (torch.zeros((block * 5,), dtype=torch.float64, device=dev),
-                torch.zeros((block,), dtype=torch.int32, device=dev))
+        bufs = (torch.zeros((block, 4), dtype=torch.float64, device=dev),
+                torch.zeros((block,), dtype=torch.int32, device=dev),
+                torch.zeros((world, block, 4), dtype=torch.float64, device=dev))
         _query_shard_bufs[key] = bufs
-    flat, len_buf = bufs
+    send, len_buf, recv = bufs
     idx_blk = torch.full((block, ranked_cap), -1, dtype=torch.int32, device=dev) if ranked_cap else None
     if qn > 0:
         res = ctx.eval_ranking(gallery, queries[q0:q0 + qn], labels_u8, n_classes, top_n, precision,
                                flags | _capi.FLAG_FULL_SORT, ranked_cap=ranked_cap,
-                               out_per_query=flat[:qn * 4], out_ranked_len=len_buf[:qn])
-        flat[block * 4:block * 4 + qn] = len_buf[:qn]
+                               out_per_query=send[:qn], out_ranked_len=len_buf[:qn])
         if ranked_cap:
             idx_blk[:qn] = res["ranked_idx"]
-    everything = comm.all_gather(flat)                     # [world, block*5]
-    per_query = everything[:, :block * 4].reshape(world * block, 4)[:q].contiguous()
-    ranked_len = everything[:, block * 4:].reshape(-1)[:q].to(torch.int32)
+    comm.all_gather_into(recv, send)                       # [world, block, 4]
+    per_query = recv.view(world * block, 4)[:q]            # contiguous: a prefix of the receive buffer
     mean = ctx.mean(per_query)
     out = {"maxskew": {"eq_opp": mean[0], "dem_par": mean[1]}, "ndkl": {"eq_opp": mean[2], "dem_par": mean[3]},
-           "per_query": per_query, "ranked_len": ranked_len, "n_flagged": 0}
+           "n_flagged": 0}
+    if bool((opts or {}).get("per_query", True)):
+        out["per_query"] = per_query.clone()               # the receive buffer is reused by the next call
+    if want_len:
+        out["ranked_len"] = comm.all_gather(len_buf).reshape(-1)[:q].contiguous()
     if ranked_cap:
         out["ranked_idx"] = comm.all_gather(idx_blk).reshape(-1, ranked_cap)[:q].contiguous()
     return out
