@@ -1,7 +1,7 @@
 """Diagnostic driver for the GPU box (not a pytest): prints error patterns stage by stage so a
 wrong descriptor / barrier shows up as a recognisable pattern in one gpurun call.
 
-    timeout 300 python tools/gpu_debug.py [stage ...]
+    timeout 300 python tests/gpu_debug.py [stage ...]
 """
 import os
 import sys
