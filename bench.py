@@ -159,355 +159,475 @@ class ClockSampler:
                     samples=len(sm), source="nvidia-smi -lms 200")
 
 
-def make_workload(name: str, device: str, rank: int = 0):
+SHARDED_WORKLOADS = ("cfg3", "cfg4", "cfg5")      # top_n << N: gallery-sharded (strong scaling) at every N
+FULLSORT_WORKLOADS = ("cfg1", "cfg2")             # top_n = N (measure_bias default): one GPU / query-sharded
+CHECKSUMS = os.path.join(ROOT, "tests", "golden", "bench_checksums.json")
+
+
+def config_of(name):
     from debias_vision_lang_b200 import synthetic
-    if name == "cfg4shard":       # one GPU's shard of BASELINE config 4 (1.25 M x 768, 10 k queries, bf16)
-        w = synthetic.clip_like(1_250_000, 768, 10_000, 2, seed=1238 + rank, device=device)
-        w.name, w.topn = "cfg4shard", 1000
-        return w, "bf16"
-    w = synthetic.baseline_workload(name, device=device)
-    return w, synthetic.BASELINE_CONFIGS[name]["precision"]
+    return synthetic.BASELINE_CONFIGS[name]
 
 
-def workload_description(name, w, precision, world, gallery_sharded=False, n_global=None):
-    n, d = w.gallery.shape
-    q = w.queries.shape[0]
-    if gallery_sharded:
-        return {
-            "workload": f"{name}: {n_global}x{d} gallery sharded over {world} GPUs ({n} rows each) x {q} queries, "
-                        f"C={w.n_classes}, top_n={w.topn}, {precision} similarity",
-            "n_gallery": n_global, "depth": d, "n_queries": q, "n_classes": w.n_classes, "top_n": w.topn,
-            "precision": precision, "input_dtype": str(w.gallery.dtype).replace("torch.", ""),
-            "l2_policy": f"inputs larger than L2 ({n * d * 4 / 1e6:.0f} MB gallery shard per GPU vs 126 MB L2); no explicit flush",
-            "parallelism": f"gallery-sharded x{world}: NCCL all-reduce of thresholds/histograms + all-gather of "
-                           "per-shard top-k lists, deterministic merge",
-        }
+def make_sharded_workload(name, device, lo, hi, n_global, q, dtype):
+    """Rows [lo, hi) of the workload's gallery (+ all queries): the same rows whatever the shard layout."""
+    from debias_vision_lang_b200 import synthetic
+    cfg = config_of(name)
+    seed = 1234 + int(name[-1])
+    if name == "cfg5":           # adversarial dyadic batch: generated whole on the host (numpy), then cut
+        w = synthetic.baseline_workload(name, device="cpu", n_override=n_global, q_override=q)
+        w.gallery = w.gallery[lo:hi].to(device=device, dtype=dtype).contiguous()
+        w.queries = w.queries.to(device=device, dtype=dtype)
+        w.labels = w.labels[lo:hi]
+    else:
+        w = synthetic.clip_like_rows(n_global, cfg["d"], q, cfg["c"], seed, lo, hi, device=device, dtype=dtype)
+    w.name, w.topn = name, cfg["topn"]
+    return w
+
+
+def describe_sharded(name, n_global, n_local, d, q, c, top_n, precision, input_dtype, world):
     return {
-        "workload": f"{name}: {n}x{d} gallery x {q} queries, C={w.n_classes}, top_n="
-                    f"{'N (measure_bias default)' if w.topn == 1.0 else w.topn}, {precision} similarity"
+        "workload": f"{name}: {n_global}x{d} gallery x {q} queries, C={c}, top_n={top_n}, {precision} similarity"
+                    + (f" (BASELINE.json configs[{int(name[-1]) - 1}])" if n_global == config_of(name)["n"] else
+                       " (REDUCED gallery: development run, not the BASELINE config)"),
+        "n_gallery": n_global, "depth": d, "n_queries": q, "n_classes": c, "top_n": top_n,
+        "precision": precision, "input_dtype": input_dtype, "rows_per_gpu": n_local,
+        "l2_policy": f"inputs larger than L2 ({n_local * d * (2 if input_dtype == 'bfloat16' else 4) / 1e6:.0f} MB "
+                     "gallery shard per GPU vs 126 MB L2); no explicit flush",
+        "parallelism": f"gallery-sharded x{world} (contiguous row blocks, queries replicated): local streaming top-k, "
+                       "NCCL all-gather of per-shard statistics and candidate lists, deterministic merge"
+                       + ("" if world > 1 else "; one shard holds the whole gallery, the collectives degenerate"),
+    }
+
+
+def describe_fullsort(name, n, d, q, c, world):
+    return {
+        "workload": f"{name}: {n}x{d} gallery x {q} queries, C={c}, top_n=N (measure_bias default), fp32 similarity"
                     + (f"; {world} GPUs, each ranks its own {q} queries over the full gallery" if world > 1 else ""),
-        "n_gallery": n, "depth": d, "n_queries_per_gpu": q, "n_classes": w.n_classes,
-        "top_n": n if w.topn == 1.0 else w.topn, "precision": precision,
-        "input_dtype": str(w.gallery.dtype).replace("torch.", ""),
-        "l2_policy": f"inputs larger than L2 ({n * d * 4 / 1e6:.0f} MB fp32 gallery + {q * n * 4 / 1e6:.0f} MB of keys per pass vs 126 MB L2); no explicit flush",
-        "parallelism": "1 GPU" if world == 1 else f"query-sharded x{world} (no data-path collective; one all-gather of "
-                                                   "the per-query results + global mean inside the timed step)",
+        "n_gallery": n, "depth": d, "n_queries_per_gpu": q, "n_classes": c, "top_n": n, "precision": "fp32",
+        "input_dtype": "float32",
+        "l2_policy": f"inputs larger than L2 ({n * d * 4 / 1e6:.0f} MB fp32 gallery + {q * n * 4 / 1e6:.0f} MB of keys "
+                     "vs 126 MB L2); no explicit flush",
+        "parallelism": "1 GPU" if world == 1 else f"query-sharded x{world} (replicated gallery; one all-gather of the "
+                                                   "per-query results + global mean inside the timed step)",
     }
 
 
 # ------------------------------------------------------------------------------------------
-# reference arm / cpu baseline: the row-by-row port of the reference on the host cores
+# CPU arm: the reference's own eval_ranking (unmodified package staged under baseline/_ref, or
+# /root/reference in the build container) on the host cores; the row-by-row port only if neither exists
 # ------------------------------------------------------------------------------------------
-def cpu_reference_sample(w, n_queries: int):
-    """Times the reference-style port (pandas DataFrame + nlargest + per-row Python loop, both
-    evaluations) on `n_queries` queries of the workload; returns (pairs/s, seconds, description)."""
+def cpu_arm():
+    """(kind, callable(labels, gallery, queries, topn) -> {"maxskew": {...}, "ndkl": {...}})."""
+    from oracle import ref_shim
+    if ref_shim.available():
+        mb = ref_shim.load()
+
+        def run(labels, g, t, topn):
+            return {ev: mb.eval_ranking(labels, g, t, ev, topn) for ev in ("maxskew", "ndkl")}
+        return "reference", run, f"unmodified debias_clip.eval_ranking ({ref_shim.source()}: {ref_shim.REFERENCE_ROOT})"
     from oracle import port
-    g = w.gallery.detach().cpu().float()
-    t = w.queries[:n_queries].detach().cpu().float()
+    return "port", port.measure, "row-by-row port oracle/port.py (reference package not staged)"
+
+
+def cpu_workload(name, rows_cap=1_000_000):
+    """The workload on the host for the CPU arm.  Galleries above `rows_cap` rows are cut to their first
+    `rows_cap` rows (every per-query cost of the reference is O(N): mat-vec, Counter, nlargest -- and the
+    NDKL loop runs over top_n rows either way), which keeps host memory and generation time bounded."""
+    from debias_vision_lang_b200 import synthetic
+    cfg = config_of(name)
+    if name in SHARDED_WORKLOADS:
+        n = min(cfg["n"], rows_cap)
+        w = make_sharded_workload(name, "cpu", 0, n, cfg["n"] if name != "cfg5" else n, cfg["q"], torch.float32)
+        if cfg["precision"] == "bf16":     # the values the GPU arm ranks: embeddings rounded to bf16
+            w.gallery = w.gallery.bfloat16().float()
+            w.queries = w.queries.bfloat16().float()
+        cut = None if n == cfg["n"] else f"first {n} of {cfg['n']} gallery rows (per-query cost is linear in N)"
+    else:
+        w = synthetic.baseline_workload(name, device="cpu")
+        cut = None
+    return w, cut
+
+
+def cpu_sample(run, w, nq):
+    g, t = w.gallery, w.queries[:nq]
     t0 = time.perf_counter()
-    res = port.measure(w.labels, g, t, w.topn)
+    with open(os.devnull, "w") as devnull:       # the reference prints tqdm bars
+        err, sys.stderr = sys.stderr, devnull
+        try:
+            res = run(w.labels, g, t, w.topn)
+        finally:
+            sys.stderr = err
     dt = time.perf_counter() - t0
-    pairs = g.shape[0] * t.shape[0]
-    return pairs / dt, dt, res
-
-
-def cpu_vectorised_sample(w, n_queries: int):
-    from oracle import spec
-    g = w.gallery.detach().cpu().float()
-    t = w.queries[:n_queries].detach().cpu().float()
-    t0 = time.perf_counter()
-    spec.measure(w.labels, g, t, w.topn)
-    dt = time.perf_counter() - t0
-    return g.shape[0] * t.shape[0] / dt, dt
-
-
-def sample_queries_for(name: str) -> int:
-    # ~10-30 s of CPU work with the row-by-row port (BASELINE.md section 3 per-query costs)
-    return {"cfg1": 40, "cfg2": 3, "cfg3": 24, "cfg5": 24, "cfg4shard": 16}.get(name, 4)
+    return g.shape[0] * t.shape[0] / dt, dt, res
 
 
 def run_reference(args):
-    rank = int(os.environ.get("RANK", "0"))
-    if rank != 0:
+    if int(os.environ.get("RANK", "0")) != 0:
         return
-    w, precision = make_workload(args.workload, "cpu")
-    # size the per-step sample so that the K + W steps together take ~150 s of CPU time
     t_all = time.perf_counter()
-    _, t_one, _ = cpu_reference_sample(w, 1)
+    kind, run, what = cpu_arm()
+    w, cut = cpu_workload(args.workload)
+    cfg = config_of(args.workload)
+    _, t_one, _ = cpu_sample(run, w, 1)
+    # each step = a bounded sample: K + W steps together take ~150 s of CPU time
     nq = int(150.0 / ((args.steps + args.warmup) * max(t_one, 1e-3)))
-    nq = max(1, min(nq, w.queries.shape[0], 4 * sample_queries_for(args.workload)))
-    vals = []
+    nq = max(1, min(nq, w.queries.shape[0], 64))
     for _ in range(args.warmup):
-        cpu_reference_sample(w, nq)
-    for _ in range(args.steps):
-        v, dt, _ = cpu_reference_sample(w, nq)
-        vals.append((v, dt))
-    total = time.perf_counter() - t_all
+        cpu_sample(run, w, nq)
+    vals = [cpu_sample(run, w, nq)[:2] for _ in range(args.steps)]
     value = float(np.mean([v for v, _ in vals]))
     ms = float(np.mean([dt for _, dt in vals]) * 1e3)
     cores = torch.get_num_threads()
-    sample = (f"{nq} of {w.queries.shape[0]} queries x full gallery, both evaluations, row-by-row port "
-              f"(pandas nlargest + per-row loop; torch matvec on {cores} threads, the rest single-threaded)")
+    n, d = w.gallery.shape
+    sample = (f"{nq} of {cfg['q']} queries per step" + (f", {cut}" if cut else " x full gallery")
+              + f", both evaluations; {what}; torch mat-vec on {cores} threads, pandas/python part one thread")
+    if args.workload in SHARDED_WORKLOADS:
+        config = describe_sharded(args.workload, cfg["n"], n, d, cfg["q"], cfg["c"], cfg["topn"], cfg["precision"],
+                                  "bfloat16" if cfg["precision"] == "bf16" else "float32", 1)
+        config["parallelism"] = "host CPU, one process"
+    else:
+        config = describe_fullsort(args.workload, n, d, cfg["q"], cfg["c"], 1)
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": workload_description(args.workload, w, precision, 1),
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
+        "scaling": "strong" if args.workload in SHARDED_WORKLOADS else "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic", "config": config,
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample,
                          "host_cpus": os.cpu_count()},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "gpu_launches": 0, "wall_s": total,
+        "gpu_launches": 0, "wall_s": time.perf_counter() - t_all,
     }
     print(json.dumps(line), flush=True)
 
 
+def cpu_baseline_record(name, seconds_budget=20.0):
+    """Bounded sample of the same workload through the reference on this box's host cores."""
+    kind, run, what = cpu_arm()
+    w, cut = cpu_workload(name)
+    _, t_one, _ = cpu_sample(run, w, 1)
+    nq = max(1, min(int(seconds_budget / max(t_one, 1e-3)), w.queries.shape[0], 64))
+    v, dt, _ = cpu_sample(run, w, nq)
+    return {"value": v, "unit": UNIT, "cores": torch.get_num_threads(), "kind": kind,
+            "sample": f"{nq} of {w.queries.shape[0]} queries" + (f", {cut}" if cut else " x full gallery")
+                      + f", both evaluations ({dt:.1f} s); {what}; mat-vec multi-threaded, pandas/python part one thread",
+            "host_cpus": os.cpu_count()}
+
+
 # ------------------------------------------------------------------------------------------
-def run_ours(args):
-    import torch.distributed as dist
-    from debias_vision_lang_b200 import _capi
+class Harness:
+    """Process-group plumbing and the timing rule: barrier + synchronize on both sides, CUDA events on
+    the launching (current) stream, max over ranks."""
 
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    if not torch.cuda.is_available():
-        raise RuntimeError("bench.py needs a B200: there is no CPU fallback for the product path "
-                           "(use --impl reference for the CPU baseline)")
-    torch.cuda.set_device(local_rank)
-    dev = f"cuda:{local_rank}"
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device(dev))
+    def __init__(self):
+        import torch.distributed as dist
+        self.dist = dist
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+        if not torch.cuda.is_available():
+            raise RuntimeError("bench.py needs a B200: there is no CPU fallback for the product path "
+                               "(use --impl reference for the CPU baseline)")
+        torch.cuda.set_device(self.local_rank)
+        self.dev = f"cuda:{self.local_rank}"
+        if self.world > 1:
+            dist.init_process_group("nccl", device_id=torch.device(self.dev))
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
         torch.cuda.synchronize()
 
-    peaks = load_peaks()
-    w, precision = make_workload(args.workload, dev, rank)
-    gallery_sharded = world > 1 and args.workload in ("cfg3", "cfg5", "cfg4shard")
-    if world > 1 and not gallery_sharded:
-        # query sharding: same gallery on every rank, a different slice of a world-times larger query set
-        from debias_vision_lang_b200 import synthetic
-        cfg = synthetic.BASELINE_CONFIGS[args.workload]
-        wq = synthetic.clip_like(1024, cfg["d"], cfg["q"], cfg["c"], seed=4321 + rank, device=dev)
-        w.queries = wq.queries
+    def max_over_ranks(self, values):
+        t = torch.tensor(list(values), dtype=torch.float64, device=self.dev)
+        if self.world > 1:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return t.tolist()
+
+    def timed(self, step, steps):
+        """Milliseconds for exactly `steps` calls of step(), max over ranks; returns (ms, last result)."""
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        self.barrier()
+        ev0.record()
+        out = None
+        for _ in range(steps):
+            out = step()
+        ev1.record()
+        self.barrier()
+        return self.max_over_ranks([ev0.elapsed_time(ev1)])[0], out
+
+    def close(self):
+        if self.world > 1:
+            self.dist.destroy_process_group()
+
+
+def means_of(r):
+    return [r["maxskew"]["eq_opp"], r["maxskew"]["dem_par"], r["ndkl"]["eq_opp"], r["ndkl"]["dem_par"]]
+
+
+def result_digest(per_query, ranked_len):
+    import hashlib
+    h = hashlib.sha256()
+    h.update(per_query.detach().cpu().contiguous().numpy().tobytes())
+    h.update(ranked_len.detach().cpu().to(torch.int32).contiguous().numpy().tobytes())
+    return h.hexdigest()
+
+
+def load_checksums():
+    try:
+        with open(CHECKSUMS) as f:
+            return json.load(f)
+    except (OSError, ValueError):
+        return {}
+
+
+# ------------------------------------------------------------------------------------------
+# top_n << N: gallery-sharded route (BASELINE configs 3, 4, 5), strong scaling
+# ------------------------------------------------------------------------------------------
+def run_sharded(h, args, name, peaks):
+    from debias_vision_lang_b200 import _capi, sharded
+    cfg = config_of(name)
+    n_global = args.rows or cfg["n"]
+    q = args.queries or cfg["q"]
+    precision = cfg["precision"]
+    in_dtype = torch.bfloat16 if (precision == "bf16" and args.input_dtype != "fp32") else torch.float32
+    lo, hi = sharded.shard_bounds(n_global, h.world, h.rank)
+    w = make_sharded_workload(name, h.dev, lo, hi, n_global, q, in_dtype)
+    n_local, d = w.gallery.shape
+    top_n = int(w.topn)
+    lab = torch.from_numpy(w.labels.astype(np.uint8)).to(h.dev)
+    ctx = _capi.context(h.local_rank)
+    comm = sharded.TorchDistComm() if h.world > 1 else sharded.SoloComm()
+    opts = {"precision": precision}
+    g_local, queries = w.gallery, w.queries
+
+    def step():
+        return sharded.evaluate_sharded(ctx, comm, g_local, queries, lab, lo, n_global, w.n_classes, top_n, opts)
+
+    for _ in range(max(args.warmup, 3)):
+        r = step()
+    h.barrier()
+    ctx.get_profile()
+    ctx.set_profiling(True)          # a handful of event records per 10-100 ms step; no graph on this route
+    launches0 = ctx.launch_count
+    sampler = ClockSampler(h.local_rank)
+    sampler.start()
+    elapsed_ms, r = h.timed(step, args.steps)
+    clocks = sampler.stop()
+    profile = ctx.get_profile()
+    ctx.set_profiling(False)
+    launches = ctx.launch_count - launches0
+    pairs_per_step = n_global * q
+    value = pairs_per_step * args.steps / (elapsed_ms * 1e-3)
+    names = sorted(profile)
+    stage_ms = {k: profile[k][0] / args.steps for k in names}
+    stage_launches = {k: profile[k][1] // args.steps for k in names}
+    stage_ms_max = dict(zip(names, h.max_over_ranks([stage_ms[k] for k in names]))) if h.world > 1 else None
+
+    # ---- self-check: per-query results against the committed one-GPU digest of the same workload ----
+    key = f"{name}:{n_global}x{d}x{q}:top{top_n}:{precision}:{str(in_dtype).replace('torch.', '')}"
+    digest = result_digest(r["per_query"], r["ranked_len"])
+    expected = load_checksums().get(key)
+    verify = {"key": key, "per_query_sha256": digest, "expected_from_1gpu": expected,
+              "match": (digest == expected) if expected else None, "n_flagged": int(r["n_flagged"]),
+              "list_len": int(r["list_len"])}
+
+    # ---- end to end: the local shard starts in pinned HOST memory every step ----
+    g_host = torch.empty(g_local.shape, dtype=g_local.dtype, pin_memory=True)
+    g_host.copy_(g_local)
+    l_host = torch.empty(lab.shape, dtype=lab.dtype, pin_memory=True)
+    l_host.copy_(lab)
+    t_host = torch.empty(queries.shape, dtype=queries.dtype, pin_memory=True)
+    t_host.copy_(queries)
+    torch.cuda.synchronize()
+
+    def e2e_step():
+        return sharded.evaluate_sharded_host(ctx, comm, g_host, t_host, l_host, lo, n_global, w.n_classes, top_n, opts)
+
+    for _ in range(2):
+        re = e2e_step()
+    e2e_steps = max(3, min(args.steps, 10))
+    e2e_ms, re = h.timed(e2e_step, e2e_steps)
+    assert means_of(re) == means_of(r), "host-input and device-input entry points disagree"
+    h2d = (g_host.numel() * g_host.element_size() + l_host.numel() + t_host.numel() * t_host.element_size())
+    h2d_all = int(sum(h.max_over_ranks([float(h2d)])) * 0) + int(h2d) * h.world   # shards differ by < 256 rows
+    e2e = {"value": pairs_per_step * e2e_steps / (e2e_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms / e2e_steps,
+           "steps": e2e_steps, "h2d_bytes_per_step": h2d_all, "d2h_bytes_per_step": 56 * h.world,
+           "api": "sharded.evaluate_sharded_host -> dvl_shard_topk_host (C ABI, pinned host gallery shard/queries/"
+                  "labels; row-chunked H2D on a copy stream overlapped with the streaming top-k), then the exchange"}
+    del g_host
+
+    # ---- roofline: the similarity GEMM (the one dense contraction), tensor-bound ----
+    flops = 2.0 * n_local * q * d                      # algorithmic 2*D flop per pair (SURVEY 8d), this rank's pairs
+    terms = 3 if precision == "fp32" else 1
+    gemm_ms = stage_ms["gemm"]
+    achieved = flops / (gemm_ms * 1e-3) / 1e12
+    roof = {"bound": "tensor", "kernel": "sim_gemm_kernel (FILTER epilogue; includes the pilot/seed launches)",
+            "achieved": achieved, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
+            "frac": achieved / peaks["bf16_tflops"], "traffic": None,
+            "peak_source": peaks["source"] + " bf16 burst (cuBLAS 8192^3 best of 10)",
+            "peak_sustained": peaks["bf16_tflops_sustained"],
+            "frac_of_sustained": achieved * terms / peaks["bf16_tflops_sustained"],
+            "issued_tflops": achieved * terms, "ms_per_step": gemm_ms,
+            "launches_per_step": stage_launches.get("gemm"),
+            "algorithmic_flop_per_step_per_gpu": flops,
+            "share_of_step": gemm_ms / (elapsed_ms / args.steps),
+            "note": f"algorithmic 2*D flop/pair x {n_local}x{q} pairs on rank 0; fp32 mode issues {terms}x that in "
+                    "16-bit tensor-core products; long steps run at power-capped clocks, hence frac_of_sustained"}
+    ncu = load_traffic(name)
+    if ncu is not None:
+        roof["traffic"] = ncu.get("traffic_bytes_per_launch")
+        roof["traffic_source"] = ncu.get("source")
+        if "tensor_pipe_active_pct" in ncu:
+            roof["ncu_tensor_pipe_active_pct"] = ncu["tensor_pipe_active_pct"]
+
+    return {
+        "value": value, "ms_per_step": elapsed_ms / args.steps, "scaling": "strong",
+        "dtype": "f32" if precision == "fp32" else "bf16",
+        "config": describe_sharded(name, n_global, n_local, d, q, w.n_classes, top_n, precision,
+                                   str(in_dtype).replace("torch.", ""), h.world),
+        "roofline": roof, "stage_ms": stage_ms, "stage_launches": stage_launches,
+        "stage_ms_max_over_ranks": stage_ms_max, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+        "verify": verify, "result": dict(zip(("maxskew_eq_opp", "maxskew_dem_par", "ndkl_eq_opp", "ndkl_dem_par"),
+                                             means_of(r))),
+    }
+
+
+# ------------------------------------------------------------------------------------------
+# top_n = N: full-sort route (BASELINE configs 1, 2 -- what measure_bias runs by default)
+# ------------------------------------------------------------------------------------------
+def run_fullsort(h, args, name, peaks, steps, warmup):
+    from debias_vision_lang_b200 import _capi, measuring_bias, sharded, synthetic
+    cfg = config_of(name)
+    w = synthetic.baseline_workload(name, device=h.dev)
+    world = h.world
+    if world > 1:     # query sharding: same gallery on every rank, a different slice of a world-times larger query set
+        w.queries = synthetic.clip_like(1024, cfg["d"], cfg["q"], cfg["c"], seed=4321 + h.rank, device=h.dev).queries
     n, d = w.gallery.shape
     q = w.queries.shape[0]
     top_n = n if w.topn == 1.0 else int(w.topn)
-    prec = _capi.PRECISION_FP32 if precision == "fp32" else _capi.PRECISION_BF16
-    lab = torch.from_numpy(w.labels.astype(np.uint8)).to(dev)
-    ctx = _capi.context(local_rank)
-    n_global = n
-    if args.input_dtype == "bf16":
-        if precision != "bf16":
-            raise SystemExit("--input-dtype bf16 needs a bf16-similarity workload (cfg3, cfg4shard)")
-        w.gallery = w.gallery.bfloat16()
-        w.queries = w.queries.bfloat16()
-        torch.cuda.empty_cache()
-    if gallery_sharded:
-        from debias_vision_lang_b200 import sharded
-        comm = sharded.TorchDistComm()
-        opts = {"precision": precision}
-        if args.workload == "cfg4shard":
-            # weak scaling: every rank generated its own 1.25 M-row shard of the 10 M-row gallery;
-            # the queries must be the same everywhere
-            dist.broadcast(w.queries, src=0)
-            n_global, index_base = n * world, n * rank
-            g_local, l_local = w.gallery, lab
-        else:
-            # strong scaling: a fixed gallery split into contiguous row blocks
-            lo, hi = sharded.shard_bounds(n, world, rank)
-            g_local, l_local, index_base = w.gallery[lo:hi].contiguous(), lab[lo:hi].contiguous(), lo
-            w.gallery = g_local
-            torch.cuda.empty_cache()
-
-        def step():
-            r = sharded.evaluate_sharded(ctx, comm, g_local, w.queries, l_local, index_base, n_global, w.n_classes,
-                                         top_n, opts)
-            return [r["maxskew"]["eq_opp"], r["maxskew"]["dem_par"], r["ndkl"]["eq_opp"], r["ndkl"]["dem_par"]]
-    elif world > 1:
-        # query sharding (top_n = N workloads): every rank holds the gallery and ALL queries (gathered once,
-        # outside the timed region, like the replicated prompt embeddings of measure_bias), ranks its own
-        # slice by the full-sort route, and the timed step ends with the all-gather of the per-query results
-        # and the fixed-tree mean over the queries of all ranks -- the number measure_bias returns
-        from debias_vision_lang_b200 import sharded
+    prec = _capi.PRECISION_FP32
+    lab = torch.from_numpy(w.labels.astype(np.uint8)).to(h.dev)
+    ctx = _capi.context(h.local_rank)
+    if world > 1:
         comm = sharded.TorchDistComm()
         all_queries = comm.all_gather(w.queries.contiguous()).reshape(world * q, d).contiguous()
         local_reference = ctx.eval_ranking(w.gallery, w.queries, lab, w.n_classes, top_n, prec)["mean"]
 
         def step():
-            r = sharded.evaluate_query_sharded(ctx, comm, w.gallery, all_queries, lab, w.n_classes, top_n,
-                                               {"precision": precision, "ranked_len": False, "per_query": False})
-            return [r["maxskew"]["eq_opp"], r["maxskew"]["dem_par"], r["ndkl"]["eq_opp"], r["ndkl"]["dem_par"]]
+            return means_of(sharded.evaluate_query_sharded(
+                ctx, comm, w.gallery, all_queries, lab, w.n_classes, top_n,
+                {"precision": "fp32", "ranked_len": False, "per_query": False}))
     else:
         def step():
             return ctx.eval_ranking(w.gallery, w.queries, lab, w.n_classes, top_n, prec)["mean"]
 
-    for _ in range(max(args.warmup, 3)):
+    # the product path: stream-ordered launches, replayed as a CUDA graph from the third identical call on
+    for _ in range(max(warmup, 3)):
         result = step()
-    barrier()
+    launches0 = ctx.launch_count
+    sampler = ClockSampler(h.local_rank)
+    sampler.start()
+    elapsed_ms, result = h.timed(step, steps)
+    clocks = sampler.stop()
+    launches = ctx.launch_count - launches0
+    # the same steps again with per-stage events (direct launches: events cannot bracket stages of a graph)
     ctx.get_profile()
     ctx.set_profiling(True)
-    launches0 = ctx.launch_count
-    sampler = ClockSampler(local_rank)
-    sampler.start()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    ev0.record()
-    for _ in range(args.steps):
-        result = step()
-    ev1.record()
-    barrier()
-    clocks = sampler.stop()
-    elapsed_ms = ev0.elapsed_time(ev1)
+    prof_ms, _ = h.timed(step, steps)
     profile = ctx.get_profile()
     ctx.set_profiling(False)
-    launches = ctx.launch_count - launches0
-    t = torch.tensor([elapsed_ms], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    elapsed_ms = float(t.item())
-    if gallery_sharded:
-        pairs_per_step = n_global * q          # one ranked evaluation of the whole sharded gallery
-    else:
-        pairs_per_step = n * q * world         # every rank evaluates its own queries
-    value = pairs_per_step * args.steps / (elapsed_ms * 1e-3)
+    pairs_per_step = n * q * world
+    pairs_rank = n * q
+    names = sorted(profile)
+    stage_ms = {k: profile[k][0] / steps for k in names}
+    stage_launches = {k: profile[k][1] // steps for k in names}
+
+    # ---- roofline per SURVEY 8(d): unfused k = N ranking = Q*N*4 B of scores in + Q*N*4 B of order out ----
+    rank_ms = stage_ms["sort_hist"] + stage_ms["sort_scan"] + stage_ms["sort_scatter"]
+    alg_bytes = 8.0 * pairs_rank
+    achieved = alg_bytes / (rank_ms * 1e-3) / 1e9
+    ncu = load_traffic(name) or {}
+    roof = {"bound": "hbm", "kernel": ncu.get("kernels", "ranking stage (segmented sort kernels)"),
+            "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"],
+            "traffic": ncu.get("traffic_bytes_per_step"), "traffic_source": ncu.get("source"),
+            "traffic_ratio": (ncu["traffic_bytes_per_step"] / alg_bytes) if ncu.get("traffic_bytes_per_step") else None,
+            "peak_source": peaks["source"] + " copy bandwidth",
+            "algorithmic_bytes_per_step": alg_bytes, "ms_per_step": rank_ms,
+            "launches_per_step": sum(stage_launches[k] for k in ("sort_hist", "sort_scan", "sort_scatter")),
+            "share_of_step": rank_ms / (prof_ms / steps),
+            "note": "algorithmic 8 B per pair per STEP (SURVEY 8d) over the time of every ranking-stage kernel of the step"}
 
     # ---- end to end through the C ABI with pinned host buffers ----
-    if gallery_sharded:
-        # the sharded path's inputs are produced on each GPU by the encoders (embedding hand-off);
-        # its end-to-end number is the timed step itself plus the H2D of the local shard
-        g_host = g_local.detach().cpu().pin_memory()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        barrier()
-        e0.record()
-        for _ in range(args.steps):
-            g_dev = g_host.to(dev, non_blocking=True)
-            r = sharded.evaluate_sharded(ctx, comm, g_dev, w.queries, l_local, index_base, n_global, w.n_classes,
-                                         top_n, opts)
-        e1.record()
-        barrier()
-        t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_ms_sharded = float(t.item())
-        h2d_sharded = int(g_host.numel() * g_host.element_size()) * world
-        del g_host
-    g_host = (w.gallery if not gallery_sharded else w.gallery[:1]).detach().float().cpu().pin_memory()
+    g_host = w.gallery.detach().float().cpu().pin_memory()
     t_host = w.queries.detach().float().cpu().pin_memory()
     l_host = torch.from_numpy(w.labels.astype(np.uint8)).pin_memory()
     g_np, t_np, l_np = g_host.numpy(), t_host.numpy(), l_host.numpy()
-    if not gallery_sharded:
-        for _ in range(2):
-            e2e_result = ctx.eval_ranking_host(g_np, t_np, l_np[:n], w.n_classes, top_n, prec)
-        barrier()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for _ in range(args.steps):
-            e2e_result = ctx.eval_ranking_host(g_np, t_np, l_np[:n], w.n_classes, top_n, prec)
-        e1.record()
-        barrier()
-        e2e_ms = e0.elapsed_time(e1)
-        t = torch.tensor([e2e_ms], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_ms = float(t.item())
-        device_result = result if world == 1 else local_reference     # at N > 1 `result` is the mean over all ranks
-        assert max(abs(a - b) for a, b in zip(e2e_result, device_result)) == 0.0, "host and device entry points disagree"
-        h2d_bytes = int(g_np.nbytes + t_np.nbytes + l_np.nbytes) * world
-        e2e_api = "dvl_eval_ranking_host (C ABI, pinned host buffers)"
-    else:
-        e2e_ms, h2d_bytes = e2e_ms_sharded, h2d_sharded
-        e2e_api = "sharded.evaluate_sharded after an H2D copy of the local gallery shard from pinned memory"
-    e2e_value = pairs_per_step * args.steps / (e2e_ms * 1e-3)
+    for _ in range(2):
+        e2e_result = ctx.eval_ranking_host(g_np, t_np, l_np, w.n_classes, top_n, prec)
+    e2e_ms, e2e_result = h.timed(lambda: ctx.eval_ranking_host(g_np, t_np, l_np, w.n_classes, top_n, prec), steps)
+    device_result = result if world == 1 else local_reference      # at N > 1 `result` is the mean over all ranks
+    assert max(abs(a - b) for a, b in zip(e2e_result, device_result)) == 0.0, "host and device entry points disagree"
+    h2d_bytes = int(g_np.nbytes + t_np.nbytes + l_np.nbytes) * world
+    e2e = {"value": pairs_per_step * steps / (e2e_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms / steps,
+           "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 40 * world,
+           "api": "dvl_eval_ranking_host (C ABI, pinned host buffers)"}
 
-    # slowest rank per stage: the step waits for it at the first collective (power-capped GPUs differ)
-    stage_ms_max = None
-    if world > 1:
-        names = sorted(profile)
-        tv = torch.tensor([profile[k][0] / args.steps for k in names], dtype=torch.float64, device=dev)
-        dist.all_reduce(tv, op=dist.ReduceOp.MAX)
-        stage_ms_max = dict(zip(names, tv.tolist()))
+    # ---- the call a user makes: the Python drop-in with int64 numpy labels and host (pinned) tensors ----
+    labels_np = w.labels.astype(np.int64)
 
-    if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
-        return
+    def api_step():
+        return means_of(measuring_bias.evaluate(labels_np, g_host, t_host, 1.0, {"precision": "fp32"}))
 
-    # ---- roofline of the dominant kernel family, from the per-stage events of the timed region ----
-    stage_ms = {k: v[0] / args.steps for k, v in profile.items()}
-    stage_launches = {k: v[1] // args.steps for k, v in profile.items()}
-    dominant = max(stage_ms, key=lambda k: stage_ms[k])
-    pairs_rank = w.gallery.shape[0] * q
-    if dominant == "gemm":
-        terms = 3 if precision == "fp32" else 1      # scaled fp16 pair: h1*h0', h0*h1', h0*h0'
-        flops = 2.0 * pairs_rank * d                       # algorithmic: 2*D flop per pair (SURVEY 8d)
-        achieved = flops / (stage_ms["gemm"] * 1e-3) / 1e12
-        roof = {"bound": "tensor", "kernel": "sim_gemm_kernel", "achieved": achieved,
-                "peak": peaks["bf16_tflops"], "unit": "TFLOP/s", "frac": achieved / peaks["bf16_tflops"],
-                "traffic": None, "peak_source": peaks["source"] + " bf16 burst",
-                # a GEMM timed inside a long back-to-back step runs at the power-capped clocks: the measured
-                # sustained cuBLAS figure is the ceiling that applies there (reported beside the burst one)
-                "peak_sustained": peaks["bf16_tflops_sustained"],
-                "frac_of_sustained": achieved * terms / peaks["bf16_tflops_sustained"],
-                "issued_tflops": achieved * terms,
-                "note": f"algorithmic 2*D flop/pair; fp32 mode issues {terms}x that in 16-bit tensor-core products"}
-    else:
-        # the radix sort: per launch of tile_scatter_kernel a pair costs key read+write (8 B) and label
-        # read+write (2 B); see DESIGN.md section 4
-        launches_k = max(1, stage_launches.get("sort_scatter", 4))
-        ms_per_launch = stage_ms["sort_scatter"] / launches_k
-        bytes_per_launch = pairs_rank * 10.0
-        achieved = bytes_per_launch / (ms_per_launch * 1e-3) / 1e9
-        sort_ms = stage_ms["sort_hist"] + stage_ms["sort_scan"] + stage_ms["sort_scatter"]
-        roof = {"bound": "hbm", "kernel": "tile_scatter_kernel", "achieved": achieved, "peak": peaks["hbm_gbs"],
-                "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"], "traffic": None,
-                "peak_source": peaks["source"] + " copy bandwidth",
-                "launches_per_step": launches_k, "ms_per_launch": ms_per_launch,
-                "algorithmic_bytes_per_launch": bytes_per_launch,
-                "ranking_stage": {"algorithmic_bytes": pairs_rank * 8.0, "ms": sort_ms,
-                                  "achieved_gbs": pairs_rank * 8.0 / (sort_ms * 1e-3) / 1e9,
-                                  "frac": pairs_rank * 8.0 / (sort_ms * 1e-3) / 1e9 / peaks["hbm_gbs"]}}
-
-    ncu = load_traffic(args.workload)
-    if ncu is not None and ncu["kernel"].split("<")[0].split(" ")[0] == roof["kernel"].split("<")[0]:
-        roof["traffic"] = ncu["traffic_bytes_per_launch"]
-        roof["traffic_source"] = ncu["source"] + " (ncu --set full, per launch: " + ncu["kernel"] + ")"
-        if "tensor_pipe_active_pct" in ncu:
-            roof["ncu_tensor_pipe_active_pct"] = ncu["tensor_pipe_active_pct"]
-
-    # ---- CPU baseline beside it (rank 0, N = 1 only): bounded sample of the same workload ----
-    cpu = None
-    if world == 1 and not args.no_cpu_baseline:
-        nq = sample_queries_for(args.workload)
-        v, dt, _ = cpu_reference_sample(w, nq)
-        vv, vdt = cpu_vectorised_sample(w, min(q, max(nq, 8)))
-        cpu = {"value": v, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
-               "sample": f"{nq} of {q} queries x full gallery, both evaluations, row-by-row port of the reference "
-                         f"({dt:.1f} s; matvec multi-threaded, pandas/python part one thread)",
-               "host_cpus": os.cpu_count(),
-               "vectorised_oracle": {"value": vv, "unit": UNIT, "seconds": vdt,
-                                     "sample": f"{min(q, max(nq, 8))} queries, numpy float64 oracle/spec.py"}}
-
-    line = {
-        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-        "warmup": max(args.warmup, 3), "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True,
-        "scaling": "strong" if (gallery_sharded and args.workload != "cfg4shard") else "weak", "vs_baseline": None,
-        "dtype": "f32" if precision == "fp32" else "bf16",
-        "data": "synthetic (seeded CLIP-like embeddings and labels; no FairFace/CLIP weights offline)",
-        "config": workload_description(args.workload, w, precision, world, gallery_sharded, n_global),
-        "roofline": roof,
-        "stage_ms": stage_ms, "stage_launches": stage_launches, "stage_ms_max_over_ranks": stage_ms_max,
-        "cpu_baseline": cpu,
-        "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_ms / args.steps,
-                "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 32 * world, "api": e2e_api},
-        "gpu_launches": int(launches),
-        "clocks": clocks,
-        "result": {"maxskew_eq_opp": result[0], "maxskew_dem_par": result[1], "ndkl_eq_opp": result[2],
-                   "ndkl_dem_par": result[3]},
+    for _ in range(2):
+        api_result = api_step()
+    api_ms, api_result = h.timed(api_step, steps)
+    assert max(abs(a - b) for a, b in zip(api_result, device_result)) == 0.0, "Python drop-in and C ABI disagree"
+    api_e2e = {"value": pairs_per_step * steps / (api_ms * 1e-3), "unit": UNIT, "ms_per_step": api_ms / steps,
+               "api": "debias_vision_lang_b200.measuring_bias.evaluate(labels int64 ndarray, pinned host tensors) -- what "
+                      "eval_ranking / measure_bias call", "vs_c_abi_e2e": (api_ms / e2e_ms)}
+    return {
+        "value": pairs_per_step * steps / (elapsed_ms * 1e-3), "ms_per_step": elapsed_ms / steps, "scaling": "weak",
+        "dtype": "f32", "config": describe_fullsort(name, n, d, q, w.n_classes, world), "roofline": roof,
+        "profiled_ms_per_step": prof_ms / steps, "stage_ms": stage_ms, "stage_launches": stage_launches,
+        "e2e": e2e, "api_e2e": api_e2e, "gpu_launches": int(launches), "clocks": clocks,
+        "launch_mode": "CUDA-graph replay of the route (timed loop); direct launches in the profiled loop",
+        "result": dict(zip(("maxskew_eq_opp", "maxskew_dem_par", "ndkl_eq_opp", "ndkl_dem_par"), result)),
     }
-    print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
+
+
+def run_ours(args):
+    from debias_vision_lang_b200._capi import build_info
+    h = Harness()
+    peaks = load_peaks()
+    name = args.workload
+    if name in SHARDED_WORKLOADS:
+        rec = run_sharded(h, args, name, peaks)
+        # the k = N regime (measure_bias's default call) stays tracked beside it: one GPU, rank 0's record
+        secondary = None
+        if h.world == 1 and not args.no_secondary:
+            torch.cuda.empty_cache()
+            secondary = run_fullsort(h, args, "cfg2", peaks, max(args.steps, 20), max(args.warmup, 5))
+            secondary.pop("clocks", None)
+    else:
+        rec = run_fullsort(h, args, name, peaks, args.steps, args.warmup)
+        secondary = None
+    cpu = None
+    if h.rank == 0 and h.world == 1 and not args.no_cpu_baseline:
+        cpu = cpu_baseline_record(name)
+    if h.rank == 0:
+        line = {"metric": METRIC, "value": rec.pop("value"), "unit": UNIT, "n_gpus": h.world, "steps": args.steps,
+                "warmup": max(args.warmup, 3), "ms_per_step": rec.pop("ms_per_step"), "higher_is_better": True,
+                "scaling": rec.pop("scaling"), "vs_baseline": None, "dtype": rec.pop("dtype"),
+                "data": "synthetic (seeded CLIP-like embeddings and labels; no FairFace/CLIP weights offline)",
+                "config": rec.pop("config")}
+        line.update(rec)
+        line["cpu_baseline"] = cpu
+        if secondary is not None:
+            line["secondary"] = secondary
+        line["build"] = build_info()
+        print(json.dumps(line), flush=True)
+    h.close()
 
 
 def main():
@@ -516,11 +636,16 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="cfg2", choices=["cfg1", "cfg2", "cfg3", "cfg5", "cfg4shard"])
+    ap.add_argument("--workload", default="cfg4", choices=["cfg1", "cfg2", "cfg3", "cfg4", "cfg5"],
+                    help="BASELINE.json config; default cfg4 = the configuration the metric is quoted on "
+                         "(10 M x 768 gallery, 10 k queries, top-1000, bf16), gallery-sharded over --gpus")
+    ap.add_argument("--rows", type=int, default=0, help="development: cut the gallery of a sharded workload to this many rows")
+    ap.add_argument("--queries", type=int, default=0, help="development: number of queries of a sharded workload")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--input-dtype", default="fp32", choices=["fp32", "bf16"],
-                    help="dtype of the resident embeddings handed to the path (bf16 needs a bf16 workload: the "
-                         "library then reads them in place, without its conversion pass)")
+    ap.add_argument("--no-secondary", action="store_true", help="skip the cfg2 (top_n = N) sub-record")
+    ap.add_argument("--input-dtype", default="auto", choices=["auto", "fp32", "bf16"],
+                    help="dtype of the resident embeddings of a bf16-similarity workload: auto/bf16 = bf16 rows read in "
+                         "place by TMA; fp32 = fp32 rows converted by the library's split pass every step")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -20,14 +20,15 @@ DVL_OK = 0
 DVL_F32, DVL_BF16, DVL_F16 = 0, 1, 2
 PRECISION_FP32, PRECISION_BF16, PRECISION_FP32X3 = 0, 1, 2
 FLAG_NORMALIZE_QUERIES, FLAG_NORMALIZE_GALLERY, FLAG_FULL_SORT, FLAG_STREAM_TOPK, FLAG_NO_PILOT = 1, 2, 4, 8, 16
+FLAG_RADIX_SORT = 32
 MAX_CLASSES = 16
 STAGES = ("prep", "gemm", "sort_hist", "sort_scan", "sort_scatter", "metrics", "select", "copy")
 NUM_STAGES = len(STAGES)
 
 EXPORTS = (
     "dvl_abi_version", "dvl_create", "dvl_destroy", "dvl_last_error", "dvl_workspace_bytes",
-    "dvl_launch_count", "dvl_set_profiling", "dvl_get_profile", "dvl_eval_ranking", "dvl_eval_ranking_host", "dvl_rank_and_score", "dvl_similarity",
-    "dvl_shard_topk", "dvl_shard_trim", "dvl_shard_pack", "dvl_merge_topk", "dvl_mean",
+    "dvl_launch_count", "dvl_set_profiling", "dvl_get_profile", "dvl_encode_labels", "dvl_eval_ranking", "dvl_eval_ranking_host", "dvl_rank_and_score", "dvl_similarity",
+    "dvl_shard_topk", "dvl_shard_topk_host", "dvl_shard_trim", "dvl_shard_pack", "dvl_merge_topk", "dvl_mean",
 )
 
 _STATUS = {-1: "DVL_ERR_INVALID", -2: "DVL_ERR_NO_DEVICE", -3: "DVL_ERR_CUDA", -4: "DVL_ERR_OOM",
@@ -65,6 +66,7 @@ def lib() -> ctypes.CDLL:
     L.dvl_launch_count.restype = ctypes.c_uint64
     L.dvl_set_profiling.argtypes = [c_void_p, c_int]
     L.dvl_get_profile.argtypes = [c_void_p, c_void_p, c_void_p]
+    L.dvl_encode_labels.argtypes = [c_void_p, c_void_p, c_int, c_i64, c_void_p, c_void_p, c_void_p]
     L.dvl_eval_ranking.argtypes = [c_void_p, c_void_p, c_int, c_void_p, c_int, c_void_p, c_i64, c_i32, c_i32, c_i32,
                                    c_i64, c_int, c_u32, c_void_p, c_void_p, c_void_p, c_void_p, c_i64, c_void_p,
                                    c_void_p]
@@ -76,6 +78,9 @@ def lib() -> ctypes.CDLL:
                                  c_void_p, c_i64, c_void_p]
     L.dvl_shard_topk.argtypes = [c_void_p, c_void_p, c_int, c_void_p, c_int, c_void_p, c_i64, c_i64, c_i32, c_i32, c_i32,
                                  c_i64, c_int, c_u32, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]
+    L.dvl_shard_topk_host.argtypes = [c_void_p, c_void_p, c_int, c_void_p, c_int, c_void_p, c_i64, c_i64, c_i32, c_i32,
+                                      c_i32, c_i64, c_int, c_u32, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                      c_void_p, c_void_p, c_void_p]
     L.dvl_shard_trim.argtypes = [c_void_p, c_void_p, c_i32, c_void_p, c_void_p]
     L.dvl_shard_pack.argtypes = [c_void_p, c_void_p, c_i32, c_i64, c_void_p, c_void_p]
     L.dvl_merge_topk.argtypes = [c_void_p, c_void_p, c_i32, c_i32, c_i64, c_i32, c_i32, c_i64, c_void_p, c_i32, c_i64,
@@ -104,6 +109,15 @@ def _np_dtype_code(a: np.ndarray) -> int:
     if a.dtype == np.float16:
         return DVL_F16
     raise TypeError(f"unsupported host embedding dtype {a.dtype}")
+
+
+def build_info() -> dict:
+    """What the in-tree library was built from (csrc/build.py writes it next to the .so)."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("dvl_build", os.path.join(_HERE, "csrc", "build.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod.build_info()
 
 
 class Context:
@@ -159,6 +173,21 @@ class Context:
         return ctypes.c_void_p(t.data_ptr()) if t is not None else ctypes.c_void_p()
 
     # ------------------------------------------------------------------------------------
+    def encode_labels(self, labels: torch.Tensor):
+        """Device integer labels (int64 / int32 / uint8) -> (uint8 codes on the device, info dict with
+        ``counts`` [16], ``n_classes`` = largest label + 1, ``out_of_range``, ``contiguous``)."""
+        assert labels.is_cuda and labels.is_contiguous() and labels.dim() == 1
+        code = {torch.int64: 0, torch.int32: 1, torch.uint8: 2}.get(labels.dtype)
+        if code is None:
+            raise TypeError(f"unsupported label dtype {labels.dtype}")
+        n = labels.numel()
+        codes = torch.empty((n,), dtype=torch.uint8, device=labels.device)
+        info = (ctypes.c_int64 * 19)()
+        self._check(lib().dvl_encode_labels(self._h, self._ptr(labels), code, n, self._ptr(codes),
+                                            ctypes.cast(info, ctypes.c_void_p), ctypes.c_void_p(self._stream())))
+        return codes, dict(counts=[int(x) for x in info[:16]], n_classes=int(info[16]), out_of_range=bool(info[17]),
+                           contiguous=bool(info[18]))
+
     def eval_ranking(self, gallery: torch.Tensor, queries: torch.Tensor, labels_u8: torch.Tensor, n_classes: int,
                      top_n: int, precision: int = PRECISION_FP32, flags: int = 0, want_per_query: bool = False,
                      ranked_cap: int = 0, want_scores: bool = False, out_per_query: Optional[torch.Tensor] = None,
@@ -200,18 +229,27 @@ class Context:
         return dict(mean=[float(x) for x in mean], per_query=per_query, ranked_len=ranked_len,
                     ranked_idx=ranked_idx, scores=scores)
 
-    def eval_ranking_host(self, gallery: np.ndarray, queries: np.ndarray, labels_u8: np.ndarray, n_classes: int,
-                          top_n: int, precision: int = PRECISION_FP32, flags: int = 0,
-                          per_query_out: Optional[np.ndarray] = None):
-        """Host (ideally pinned) inputs; H2D copies happen inside the call."""
-        n, d = gallery.shape
-        q = queries.shape[0]
-        assert gallery.flags["C_CONTIGUOUS"] and queries.flags["C_CONTIGUOUS"] and labels_u8.dtype == np.uint8
+    def eval_ranking_host(self, gallery, queries, labels_u8, n_classes: int, top_n: int,
+                          precision: int = PRECISION_FP32, flags: int = 0, per_query_out: Optional[np.ndarray] = None):
+        """HOST inputs (numpy arrays or CPU torch tensors, ideally pinned): the H2D copies happen inside the
+        call, the gallery in row blocks that are scored as they land."""
+        def host(x):
+            if isinstance(x, torch.Tensor):
+                assert not x.is_cuda and x.is_contiguous()
+                return x.data_ptr(), (_dtype_code(x.dtype) if x.dtype != torch.uint8 else None), tuple(x.shape)
+            assert x.flags["C_CONTIGUOUS"]
+            return x.ctypes.data, (_np_dtype_code(x) if x.dtype != np.uint8 else None), tuple(x.shape)
+        g_ptr, g_dt, (n, d) = host(gallery)
+        t_ptr, t_dt, (q, d2) = host(queries)
+        l_ptr, l_dt, l_shape = host(labels_u8)
+        if d != d2:
+            raise ValueError(f"embedding depth mismatch: gallery {d}, queries {d2}")
+        if l_dt is not None or l_shape != (n,):
+            raise ValueError("labels must be uint8 class codes, one per gallery row")
         mean = (ctypes.c_double * 4)()
         pq = ctypes.c_void_p(per_query_out.ctypes.data) if per_query_out is not None else ctypes.c_void_p()
-        rc = lib().dvl_eval_ranking_host(self._h, ctypes.c_void_p(gallery.ctypes.data), _np_dtype_code(gallery),
-                                         ctypes.c_void_p(queries.ctypes.data), _np_dtype_code(queries),
-                                         ctypes.c_void_p(labels_u8.ctypes.data), n, d, q, int(n_classes), int(top_n),
+        rc = lib().dvl_eval_ranking_host(self._h, ctypes.c_void_p(g_ptr), g_dt, ctypes.c_void_p(t_ptr), t_dt,
+                                         ctypes.c_void_p(l_ptr), n, d, q, int(n_classes), int(top_n),
                                          int(precision), int(flags), ctypes.cast(mean, ctypes.c_void_p), pq,
                                          ctypes.c_void_p(self._stream()))
         self._check(rc)
@@ -262,6 +300,30 @@ class Context:
                                   int(n_classes), int(top_n), int(precision), int(flags), self._ptr(tau),
                                   self._ptr(oflags), self._ptr(counts), ctypes.cast(ctypes.byref(cap), ctypes.c_void_p),
                                   ctypes.c_void_p(self._stream()))
+        self._check(rc)
+        return tau, oflags, counts, int(cap.value)
+
+    def shard_topk_host(self, gallery: torch.Tensor, queries: torch.Tensor, labels_u8: torch.Tensor, index_base: int,
+                        n_classes: int, top_n: int, precision: int = PRECISION_FP32, flags: int = 0):
+        """``shard_topk`` with HOST tensors (pinned for an asynchronous, overlapped upload): the gallery shard
+        travels in row blocks on the context's copy stream while the blocks that have landed are already
+        being scored and filtered."""
+        assert not gallery.is_cuda and not queries.is_cuda and not labels_u8.is_cuda
+        assert gallery.is_contiguous() and queries.is_contiguous() and labels_u8.is_contiguous()
+        assert labels_u8.dtype == torch.uint8
+        n_local, d = gallery.shape
+        q = queries.shape[0]
+        dev = torch.device("cuda", self.device)
+        tau = torch.empty((q,), dtype=torch.float32, device=dev)
+        oflags = torch.empty((q,), dtype=torch.int32, device=dev)
+        counts = torch.empty((MAX_CLASSES + 1,), dtype=torch.int64, device=dev)
+        cap = ctypes.c_int32(0)
+        rc = lib().dvl_shard_topk_host(self._h, self._ptr(gallery), _dtype_code(gallery.dtype), self._ptr(queries),
+                                       _dtype_code(queries.dtype), self._ptr(labels_u8), n_local, int(index_base), d, q,
+                                       int(n_classes), int(top_n), int(precision), int(flags), self._ptr(tau),
+                                       self._ptr(oflags), self._ptr(counts),
+                                       ctypes.cast(ctypes.byref(cap), ctypes.c_void_p), None, None, None,
+                                       ctypes.c_void_p(self._stream()))
         self._check(rc)
         return tau, oflags, counts, int(cap.value)
 

@@ -123,11 +123,46 @@ int planes_of(int precision) {
   return precision == DVL_PRECISION_BF16 ? 1 : (precision == DVL_PRECISION_FP32X3 ? 3 : 2);
 }
 
+// Gallery rows that arrive from the host while the path is already running (host-input entry points):
+// the rows travel in blocks on the context's copy stream, one event per block; a consumer calls
+// arrive(row1) before it touches rows below row1.  The operand split of arrived rows (when the rows are not
+// used in place) happens here as well, range by range, so the similarity of a chunk starts as soon as the
+// chunk is on the device.
+struct RowFeed {
+  Ctx* c = nullptr;
+  int64_t n = 0, block_rows = 0;
+  const char* rows_dev = nullptr;   // staged rows on the device
+  int dtype = 0, d = 0, dp = 0, planes = 0;
+  void* planes_dst = nullptr;       // null: the staged rows are the operand
+  float* scale = nullptr;
+  bool normalize = false;
+  int64_t ready = 0;                // rows [0, ready) are on the device and prepared, in compute-stream order
+  int arrive(int64_t row1, cudaStream_t st);
+};
+
+int RowFeed::arrive(int64_t row1, cudaStream_t st) {
+  if (row1 > n) row1 = n;
+  if (row1 <= ready) return DVL_OK;
+  const int64_t block = (row1 - 1) / block_rows;
+  // the copies are stream-ordered: block b complete means every block before it is
+  DVL_CUDA(c, cudaStreamWaitEvent(st, c->upload_events[(size_t)block], 0));
+  if (planes_dst != nullptr) {
+    StageScope scope(c, DVL_STAGE_PREP, st);
+    const size_t elt = (size_t)(dtype == DVL_F32 ? 4 : 2);
+    DVL_TRY(launch_split_rows(c, rows_dev + (size_t)ready * d * elt, dtype, row1 - ready, d, dp, planes,
+                              (char*)planes_dst + (size_t)ready * dp * 2, scale != nullptr ? scale + ready : nullptr,
+                              normalize, st, n));
+  }
+  ready = row1;
+  return DVL_OK;
+}
+
 // one side of the similarity: 16-bit planes (+ the row factors of the fused scale: 2^-e of the fp16
-// split, inverse row norms) in the context's workspace, or the caller's rows in place
+// split, inverse row norms) in the context's workspace, or the caller's rows in place.  With a feed the
+// split is deferred to RowFeed::arrive.
 int prepare_side(Ctx* c, const void* rows_ptr, int dtype, int64_t rows, int d, int precision, bool need_norm,
                  DevBuf& planes_buf, DevBuf& scale_buf, const void** out_planes, const float** out_scale,
-                 cudaStream_t st) {
+                 cudaStream_t st, RowFeed* feed = nullptr) {
   const int planes = planes_of(precision);
   const int dp = (int)round_up(d, 8);
   const bool direct = operand_direct(rows_ptr, dtype, d, precision, need_norm);
@@ -137,7 +172,16 @@ int prepare_side(Ctx* c, const void* rows_ptr, int dtype, int64_t rows, int d, i
     DVL_TRY(ensure(c, scale_buf, (size_t)rows * 4));
     scale = (float*)scale_buf.ptr;
   }
-  if (!direct) {
+  if (feed != nullptr) {
+    feed->rows_dev = (const char*)rows_ptr;
+    feed->dtype = dtype;
+    feed->d = d;
+    feed->dp = dp;
+    feed->planes = planes;
+    feed->planes_dst = direct ? nullptr : planes_buf.ptr;
+    feed->scale = scale;
+    feed->normalize = need_norm;
+  } else if (!direct) {
     StageScope scope(c, DVL_STAGE_PREP, st);
     DVL_TRY(launch_split_rows(c, rows_ptr, dtype, rows, d, dp, planes, planes_buf.ptr, scale, need_norm, st));
   }
@@ -155,11 +199,11 @@ int prepare_queries(Ctx* c, const void* queries, int qdt, int d, int q, int prec
 
 // a1 + operand preparation: bf16 planes of gallery and queries, inverse norms for the fused scale
 int prepare_operands(Ctx* c, const void* gallery, int gdt, const void* queries, int qdt, int64_t n, int d, int q,
-                     int precision, uint32_t flags, Operands* op, cudaStream_t st) {
+                     int precision, uint32_t flags, Operands* op, cudaStream_t st, RowFeed* feed = nullptr) {
   op->planes = planes_of(precision);
   op->dp = (int)round_up(d, 8);
   DVL_TRY(prepare_side(c, gallery, gdt, n, d, precision, (flags & DVL_FLAG_NORMALIZE_GALLERY) != 0, c->gal_planes,
-                       c->gal_inv_norm, &op->gal_planes, &op->gal_scale, st));
+                       c->gal_inv_norm, &op->gal_planes, &op->gal_scale, st, feed));
   return prepare_queries(c, queries, qdt, d, q, precision, flags, op, st);
 }
 
@@ -195,12 +239,34 @@ int run_similarity_prepared(Ctx* c, const Operands& op, int64_t n, int d, int q,
   return launch_sim_gemm(c, g, st);
 }
 
+// similarity of prepared operands; with a feed (rows still arriving from the host) as a few row-range
+// launches, each as soon as its rows are there
+int run_similarity_slices(Ctx* c, const Operands& op, int64_t n, int d, int q, uint32_t* keys, int64_t ldk,
+                          float* scores, int64_t lds, cudaStream_t st, RowFeed* feed) {
+  if (feed == nullptr || feed->ready >= n) return run_similarity_prepared(c, op, n, d, q, keys, ldk, scores, lds, st);
+  const int64_t slice = round_up((n + 3) / 4, feed->block_rows);
+  for (int64_t row0 = 0; row0 < n; row0 += slice) {
+    const int64_t row1 = row0 + slice < n ? row0 + slice : n;
+    DVL_TRY(feed->arrive(row1, st));
+    StageScope scope(c, DVL_STAGE_GEMM, st);
+    GemmArgs g = gemm_args(op, n, d, q);
+    g.keys = keys;
+    g.ldk = ldk;
+    g.scores = scores;
+    g.lds = lds;
+    g.row0 = row0;
+    g.row1 = row1;
+    DVL_TRY(launch_sim_gemm(c, g, st));
+  }
+  return DVL_OK;
+}
+
 int run_similarity(Ctx* c, const void* gallery, int gdt, const void* queries, int qdt, int64_t n, int d, int q,
                    int precision, uint32_t flags, uint32_t* keys, int64_t ldk, float* scores, int64_t lds,
-                   cudaStream_t st) {
+                   cudaStream_t st, RowFeed* feed = nullptr) {
   Operands op;
-  DVL_TRY(prepare_operands(c, gallery, gdt, queries, qdt, n, d, q, precision, flags, &op, st));
-  return run_similarity_prepared(c, op, n, d, q, keys, ldk, scores, lds, st);
+  DVL_TRY(prepare_operands(c, gallery, gdt, queries, qdt, n, d, q, precision, flags, &op, st, feed));
+  return run_similarity_slices(c, op, n, d, q, keys, ldk, scores, lds, st, feed);
 }
 
 // query-independent statistics: Counter(df.label) and the fp64 tables
@@ -213,6 +279,16 @@ int run_label_stats(Ctx* c, const uint8_t* labels, int64_t n, int n_classes, int
   return DVL_OK;
 }
 
+// the device word a bucket overflow raises: zero between calls (finish_enqueue reads and clears it)
+int ensure_sort_flag(Ctx* c, cudaStream_t st) {
+  if (c->sort_flag.ptr != nullptr) return DVL_OK;
+  DVL_TRY(ensure(c, c->sort_flag, 256));
+  DVL_CUDA(c, cudaMemsetAsync(c->sort_flag.ptr, 0, 256, st));
+  return DVL_OK;
+}
+
+constexpr int kRetryLsd = 1;      // internal: a bucket of the bucket sort overflowed, rank again with the radix sort
+
 // Full-sort route.  keys [q][ldk] already in c->keys[0] -> stable segmented sort -> metrics.
 // Writes per_query [q][4] and ranked_len [q] (device); ranked indices on request.
 int rank_full(Ctx* c, const uint8_t* labels, int64_t n, int64_t n_gallery, int q, int n_classes, int64_t top_n,
@@ -220,13 +296,44 @@ int rank_full(Ctx* c, const uint8_t* labels, int64_t n, int64_t n_gallery, int q
               cudaStream_t st) {
   const bool want_idx = out_ranked_idx != nullptr;
   if (want_idx && ranked_cap < 1) return set_error(c, DVL_ERR_INVALID, "ranked_cap must be >= 1");
-  DVL_TRY(ensure(c, c->keys[1], (size_t)q * ldk * 4));
+  // the whole segment is ranked: the metrics need the NaN count, not the sorted keys
+  const bool whole = top_n >= n;
+  const bool bucket = bucket_sort_eligible(n) && !c->force_lsd && !c->radix_only;
+  if (!whole || !bucket) DVL_TRY(ensure(c, c->keys[1], (size_t)q * ldk * 4));
   DVL_TRY(ensure(c, c->labs[0], (size_t)q * ldk));
-  DVL_TRY(ensure(c, c->labs[1], (size_t)q * ldk));
+  if (!bucket) DVL_TRY(ensure(c, c->labs[1], (size_t)q * ldk));
   if (want_idx) {
     DVL_TRY(ensure(c, c->idxs[0], (size_t)q * ldk * 4));
-    DVL_TRY(ensure(c, c->idxs[1], (size_t)q * ldk * 4));
+    if (!bucket) DVL_TRY(ensure(c, c->idxs[1], (size_t)q * ldk * 4));
   }
+  if (whole) DVL_TRY(ensure(c, c->nan_cnt, (size_t)q * sizeof(uint32_t)));
+  const uint32_t* sorted_keys = nullptr;
+  const uint8_t* ranked_labs = nullptr;
+  const int32_t* ranked_idx = nullptr;
+  if (bucket) {
+    // two-level score-linear bucket sort (bucketsort.cu); a bucket overflow (tie-heavy data) raises
+    // c->sort_flag, which finish_wait turns into one retry of the call with the radix sort
+    DVL_TRY(ensure_sort_flag(c, st));
+    BucketSortArgs b;
+    b.keys = (const uint32_t*)c->keys[0].ptr;
+    b.ldk = ldk;
+    b.n = n;
+    b.q = q;
+    b.gallery_labels = labels;
+    b.labs_out = (uint8_t*)c->labs[0].ptr;
+    b.ldl = ldk;
+    b.idx_out = want_idx ? (int32_t*)c->idxs[0].ptr : nullptr;
+    b.ldi = ldk;
+    b.keys_out = whole ? nullptr : (uint32_t*)c->keys[1].ptr;
+    b.ldko = ldk;
+    b.nan_cnt = whole ? (uint32_t*)c->nan_cnt.ptr : nullptr;
+    b.overflow = (uint32_t*)c->sort_flag.ptr;
+    DVL_TRY(launch_bucket_sort(c, b, st));
+    c->bucket_used = true;
+    sorted_keys = b.keys_out;
+    ranked_labs = b.labs_out;
+    ranked_idx = b.idx_out;
+  } else {
   SortArgs s;
   s.keys[0] = (uint32_t*)c->keys[0].ptr;
   s.keys[1] = (uint32_t*)c->keys[1].ptr;
@@ -238,18 +345,17 @@ int rank_full(Ctx* c, const uint8_t* labels, int64_t n, int64_t n_gallery, int q
   s.n = n;
   s.ldk = ldk;
   s.q = q;
-  // the whole segment is ranked: the metrics need the NaN count, not the sorted keys
-  const bool whole = top_n >= n;
-  if (whole) {
-    DVL_TRY(ensure(c, c->nan_cnt, (size_t)q * sizeof(uint32_t)));
-    s.nan_cnt = (uint32_t*)c->nan_cnt.ptr;
-  }
+  if (whole) s.nan_cnt = (uint32_t*)c->nan_cnt.ptr;
   int buf = 0;
   DVL_TRY(launch_segmented_sort(c, s, &buf, st));
+  sorted_keys = whole ? nullptr : s.keys[buf];
+  ranked_labs = s.labs[buf];
+  ranked_idx = s.idxs[buf];
+  }
   MetricArgs m;
-  m.keys = whole ? nullptr : s.keys[buf];
+  m.keys = sorted_keys;
   m.nan_cnt = whole ? (const uint32_t*)c->nan_cnt.ptr : nullptr;
-  m.labs = s.labs[buf];
+  m.labs = ranked_labs;
   m.ldk = ldk;
   m.ldl = ldk;
   m.n_avail = n;
@@ -267,7 +373,7 @@ int rank_full(Ctx* c, const uint8_t* labels, int64_t n, int64_t n_gallery, int q
   }
   if (want_idx) {
     StageScope scope(c, DVL_STAGE_COPY, st);
-    DVL_TRY(launch_copy_ranked(c, s.idxs[buf], ldk, ranked_len, q, out_ranked_idx, ranked_cap, st));
+    DVL_TRY(launch_copy_ranked(c, ranked_idx, ldk, ranked_len, q, out_ranked_idx, ranked_cap, st));
   }
   return DVL_OK;
 }
@@ -283,12 +389,24 @@ int finish_enqueue(Ctx* c, const double* per_query, int q, bool check_labels, cu
   if (check_labels)   // the out-of-range label flag travels with the class counts
     DVL_CUDA(c, cudaMemcpyAsync(c->mean_pinned + 4, (unsigned long long*)c->class_counts.ptr + kMaxClasses,
                                 sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+  if (c->bucket_used) {   // ... and so does the bucket-overflow word, which is cleared for the next call
+    DVL_CUDA(c, cudaMemcpyAsync(c->mean_pinned + 5, c->sort_flag.ptr, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    DVL_CUDA(c, cudaMemsetAsync(c->sort_flag.ptr, 0, sizeof(uint32_t), st));
+  }
   return DVL_OK;
 }
 
 // waits for the stream and hands the four means to the caller
+// Returns kRetryLsd (> 0) when a bucket sort of this call overflowed: the results are not valid and the
+// caller repeats the ranking with c->force_lsd set.
 int finish_wait(Ctx* c, int n_classes, double* out_mean4, bool check_labels, cudaStream_t st) {
   DVL_CUDA(c, cudaStreamSynchronize(st));
+  if (c->bucket_used) {
+    c->bucket_used = false;
+    uint32_t overflow = 0;
+    memcpy(&overflow, c->mean_pinned + 5, sizeof(overflow));
+    if (overflow != 0u) return kRetryLsd;
+  }
   if (check_labels) {
     unsigned long long bad_flag = 0;
     memcpy(&bad_flag, c->mean_pinned + 4, sizeof(bad_flag));
@@ -359,7 +477,8 @@ bool plan_stream(int64_t n, int q, int64_t top_n, uint32_t flags, StreamPlan* pl
 // query, the sorted list of every row that ranks within top_n (boundary ties included):
 // c->cand [q][cap] (first avail[q] entries), labels in c->topk_labs [q][ldl], lengths in c->topk_avail.
 int stream_topk(Ctx* c, const Operands& op, const uint8_t* labels, int64_t n, int64_t index_base, int d, int q,
-                int64_t top_n, const StreamPlan& plan, int32_t* idx_out, int64_t idx_cap, cudaStream_t st) {
+                int64_t top_n, const StreamPlan& plan, int32_t* idx_out, int64_t idx_cap, cudaStream_t st,
+                RowFeed* feed = nullptr) {
   const int64_t ldl = round_up(plan.sort_cap, 256);
   DVL_TRY(ensure(c, c->cand, (size_t)q * plan.cap * 8));
   DVL_TRY(ensure(c, c->cand_cnt, (size_t)q * 4));
@@ -391,6 +510,7 @@ int stream_topk(Ctx* c, const Operands& op, const uint8_t* labels, int64_t n, in
   sel.index_base = index_base;
 
   auto gemm_launch = [&](int mode, int64_t row0, int64_t row1, int64_t n_view, int64_t row_step) -> int {
+    if (feed != nullptr) DVL_TRY(feed->arrive(row_step > 1 ? n : row1, st));
     StageScope scope(c, DVL_STAGE_GEMM, st);
     GemmArgs g = gemm_args(op, n_view, d, q);
     g.mode = mode;
@@ -471,22 +591,48 @@ struct FullSortCall {
 };
 
 // label statistics -> similarity -> ranking keys -> segmented sort -> metrics -> mean in pinned memory
-int enqueue_full_sort(Ctx* c, const FullSortCall& a, cudaStream_t st) {
+int enqueue_full_sort(Ctx* c, const FullSortCall& a, cudaStream_t st, RowFeed* feed = nullptr) {
   DVL_TRY(run_label_stats(c, a.labels, a.n, a.n_classes, (a.n > a.top_n ? a.n : a.top_n) + 2, st));
   const int64_t ldk = round_up(a.n, 256);
-  DVL_TRY(ensure(c, c->keys[0], (size_t)a.q * ldk * 4));
-  float* scores_tmp = nullptr;
-  if (a.out_scores != nullptr) {
-    DVL_TRY(ensure(c, c->scores_tmp, (size_t)a.q * ldk * 4));
-    scores_tmp = (float*)c->scores_tmp.ptr;
+  // The route materialises keys (and sort workspace) per query: queries are processed in batches bounded by
+  // a workspace budget (DVL_WS_BUDGET_MB, default 8 GB), so Q x N does not have to fit at once.
+  c->radix_only = (a.flags & DVL_FLAG_RADIX_SORT) != 0;
+  const bool bucket = bucket_sort_eligible(a.n) && !c->force_lsd && !c->radix_only;
+  size_t per_query_bytes = (size_t)ldk * 4 + (bucket ? bucket_sort_workspace_per_query(a.n) + (size_t)ldk * 5
+                                                     : (size_t)ldk * 6 + (size_t)((a.n + 4095) / 4096) * 1024);
+  if (a.ranked_idx != nullptr) per_query_bytes += (size_t)ldk * 8;
+  if (a.out_scores != nullptr) per_query_bytes += (size_t)ldk * 4;
+  static const size_t budget = [] {
+    const char* e = getenv("DVL_WS_BUDGET_MB");
+    const long long mb = e != nullptr ? atoll(e) : 0;
+    return (size_t)(mb > 0 ? mb : 8192) << 20;
+  }();
+  int qb = (int)(budget / per_query_bytes < 1 ? 1 : (budget / per_query_bytes > (size_t)a.q ? (size_t)a.q : budget / per_query_bytes));
+  Operands op;
+  op.planes = planes_of(a.precision);
+  op.dp = (int)round_up(a.d, 8);
+  DVL_TRY(prepare_side(c, a.gallery, a.gdt, a.n, a.d, a.precision, (a.flags & DVL_FLAG_NORMALIZE_GALLERY) != 0,
+                       c->gal_planes, c->gal_inv_norm, &op.gal_planes, &op.gal_scale, st, feed));
+  const size_t qrow_bytes = (size_t)a.d * dtype_size(a.qdt);
+  for (int q0 = 0; q0 < a.q; q0 += qb) {
+    const int qn = a.q - q0 < qb ? a.q - q0 : qb;
+    DVL_TRY(ensure(c, c->keys[0], (size_t)qn * ldk * 4));
+    float* scores_tmp = nullptr;
+    if (a.out_scores != nullptr) {
+      DVL_TRY(ensure(c, c->scores_tmp, (size_t)qn * ldk * 4));
+      scores_tmp = (float*)c->scores_tmp.ptr;
+    }
+    DVL_TRY(prepare_queries(c, (const char*)a.queries + (size_t)q0 * qrow_bytes, a.qdt, a.d, qn, a.precision, a.flags, &op,
+                            st));
+    DVL_TRY(run_similarity_slices(c, op, a.n, a.d, qn, (uint32_t*)c->keys[0].ptr, ldk, scores_tmp, ldk, st, feed));
+    if (a.out_scores != nullptr)
+      DVL_CUDA(c, cudaMemcpy2DAsync(a.out_scores + (size_t)q0 * a.n, (size_t)a.n * 4, scores_tmp, (size_t)ldk * 4,
+                                    (size_t)a.n * 4, qn, cudaMemcpyDeviceToDevice, st));
+    DVL_TRY(rank_full(c, a.labels, a.n, a.n, qn, a.n_classes, a.top_n, ldk, a.per_query + (size_t)q0 * 4,
+                      a.ranked_len + q0, a.ranked_idx != nullptr ? a.ranked_idx + (size_t)q0 * a.ranked_cap : nullptr,
+                      a.ranked_cap, st));
   }
-  DVL_TRY(run_similarity(c, a.gallery, a.gdt, a.queries, a.qdt, a.n, a.d, a.q, a.precision, a.flags,
-                         (uint32_t*)c->keys[0].ptr, ldk, scores_tmp, ldk, st));
-  if (a.out_scores != nullptr)
-    DVL_CUDA(c, cudaMemcpy2DAsync(a.out_scores, (size_t)a.n * 4, scores_tmp, (size_t)ldk * 4, (size_t)a.n * 4, a.q,
-                                  cudaMemcpyDeviceToDevice, st));
-  DVL_TRY(rank_full(c, a.labels, a.n, a.n, a.q, a.n_classes, a.top_n, ldk, a.per_query, a.ranked_len, a.ranked_idx,
-                    a.ranked_cap, st));
+  c->radix_only = false;
   return finish_enqueue(c, a.per_query, a.q, true, st);
 }
 
@@ -508,11 +654,12 @@ void drop_graph(Ctx* c) {
 // gaps between launches are a fifth of the step.  The second identical call (same buffers, shapes and
 // options, workspace already sized) is captured into a CUDA graph on the context's own stream; later
 // identical calls replay it.  Any workspace reallocation invalidates the graph (ws_generation).
-int run_full_sort(Ctx* c, const FullSortCall& call, double* out_mean4, cudaStream_t st) {
+int run_full_sort_once(Ctx* c, const FullSortCall& call, double* out_mean4, cudaStream_t st, RowFeed* feed) {
   // per-stage profiling brackets every stage with events: measured slower inside a graph (external
-  // event-record nodes) than as direct launches, so profiled calls are launched directly
-  if (!graphs_enabled() || c->profiling) {
-    DVL_TRY(enqueue_full_sort(c, call, st));
+  // event-record nodes) than as direct launches, so profiled calls are launched directly; so are calls
+  // whose gallery is still arriving from the host (they wait on the copy stream's events block by block)
+  if (!graphs_enabled() || c->profiling || feed != nullptr) {
+    DVL_TRY(enqueue_full_sort(c, call, st, feed));
     return finish_wait(c, call.n_classes, out_mean4, true, st);
   }
   const uint8_t* kb = reinterpret_cast<const uint8_t*>(&call);
@@ -557,6 +704,7 @@ int run_full_sort(Ctx* c, const FullSortCall& call, double* out_mean4, cudaStrea
     }
     c->graph_launches = c->launches - launches0;
     c->launches = launches0;
+    c->graph_bucket = c->bucket_used;          // the captured sequence ranks with the bucket sort (overflow word)
     c->graph_key = key;
     c->graph_generation = c->ws_generation;
   }
@@ -565,8 +713,68 @@ int run_full_sort(Ctx* c, const FullSortCall& call, double* out_mean4, cudaStrea
   DVL_CUDA(c, cudaStreamWaitEvent(c->own_stream, c->fence_event, 0));
   DVL_CUDA(c, cudaGraphLaunch(c->graph_exec, c->own_stream));
   c->launches += c->graph_launches;
+  c->bucket_used = c->graph_bucket;
   DVL_TRY(finish_wait(c, call.n_classes, out_mean4, true, c->own_stream));
   return DVL_OK;   // own_stream is idle again: work the caller enqueues next on `st` is ordered after this return
+}
+
+// Host rows -> device staging buffer in row blocks on the context's copy stream, one event per block
+// (RowFeed::arrive waits on them).  `small` copies (queries, labels) go first on the same stream; the
+// compute stream `st` is made to wait for them here, and the copy stream for everything enqueued on `st`
+// so far (an earlier call may still be reading the staging buffers).
+struct SmallCopy { void* dst; const void* src; size_t bytes; };
+
+int start_upload(Ctx* c, const void* host_rows, void* dev_rows, int64_t n, size_t row_bytes, const SmallCopy* small,
+                 int n_small, RowFeed* feed, cudaStream_t st) {
+  if (c->copy_stream == nullptr) DVL_CUDA(c, cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+  // blocks of >= 16 MB (PCIe efficiency; DVL_UPLOAD_BLOCK_MB overrides) and at most ~512 of them; a multiple
+  // of 256 rows (GEMM tiles)
+  static const size_t block_bytes = [] {
+    const char* e = getenv("DVL_UPLOAD_BLOCK_MB");
+    const long long mb = e != nullptr ? atoll(e) : 0;
+    return (size_t)(mb > 0 ? mb : 16) << 20;
+  }();
+  int64_t block_rows = round_up((int64_t)(block_bytes / row_bytes) + 1, 256);
+  if (block_rows * 512 < n) block_rows = round_up((n + 511) / 512, 256);
+  const int64_t blocks = (n + block_rows - 1) / block_rows;
+  while ((int64_t)c->upload_events.size() < blocks + 2) {
+    cudaEvent_t e = nullptr;
+    DVL_CUDA(c, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    c->upload_events.push_back(e);
+  }
+  cudaEvent_t fence = c->upload_events[(size_t)blocks], small_done = c->upload_events[(size_t)blocks + 1];
+  DVL_CUDA(c, cudaEventRecord(fence, st));
+  DVL_CUDA(c, cudaStreamWaitEvent(c->copy_stream, fence, 0));
+  {
+    StageScope scope(c, DVL_STAGE_COPY, c->copy_stream);
+    for (int i = 0; i < n_small; ++i)
+      DVL_CUDA(c, cudaMemcpyAsync(small[i].dst, small[i].src, small[i].bytes, cudaMemcpyHostToDevice, c->copy_stream));
+    DVL_CUDA(c, cudaEventRecord(small_done, c->copy_stream));
+    for (int64_t b = 0; b < blocks; ++b) {
+      const int64_t r0 = b * block_rows, r1 = (r0 + block_rows < n) ? r0 + block_rows : n;
+      DVL_CUDA(c, cudaMemcpyAsync((char*)dev_rows + (size_t)r0 * row_bytes, (const char*)host_rows + (size_t)r0 * row_bytes,
+                                  (size_t)(r1 - r0) * row_bytes, cudaMemcpyHostToDevice, c->copy_stream));
+      DVL_CUDA(c, cudaEventRecord(c->upload_events[(size_t)b], c->copy_stream));
+    }
+  }
+  DVL_CUDA(c, cudaStreamWaitEvent(st, small_done, 0));
+  feed->c = c;
+  feed->n = n;
+  feed->block_rows = block_rows;
+  feed->ready = 0;
+  return DVL_OK;
+}
+
+int run_full_sort(Ctx* c, const FullSortCall& call, double* out_mean4, cudaStream_t st, RowFeed* feed = nullptr) {
+  int rc = run_full_sort_once(c, call, out_mean4, st, feed);
+  if (rc != kRetryLsd) return rc;
+  // a bucket overflowed (tie-heavy scores): the same call again with the radix sort, launched directly
+  // (the gallery has arrived completely by now, so no feed)
+  c->force_lsd = true;
+  rc = enqueue_full_sort(c, call, st, nullptr);
+  if (rc == DVL_OK) rc = finish_wait(c, call.n_classes, out_mean4, true, st);
+  c->force_lsd = false;
+  return rc;
 }
 
 struct DeviceGuard {
@@ -626,13 +834,16 @@ DVL_API int dvl_destroy(dvl_ctx* c) {
                          &c->log_tab, &c->per_query, &c->mean_dev, &c->scores_tmp, &c->seg_len, &c->sub_cnt, &c->partial,
                          &c->h_gallery, &c->h_queries, &c->h_labels, &c->cand, &c->cand_cnt, &c->cand_tau,
                          &c->cand_flags, &c->topk_labs, &c->topk_avail, &c->fb_queries, &c->fb_per_query, &c->fb_len,
-                         &c->fb_idx, &c->merge_sorted, &c->tab_chunks};
+                         &c->fb_idx, &c->merge_sorted, &c->tab_chunks, &c->bk_store, &c->bk_cnt, &c->bk_lut,
+                         &c->bk_plan, &c->sort_flag, &c->label_info};
   for (dvl::DevBuf* b : bufs)
     if (b->ptr != nullptr) cudaFree(b->ptr);
   if (c->mean_pinned != nullptr) cudaFreeHost(c->mean_pinned);
   if (c->graph_exec != nullptr) cudaGraphExecDestroy(c->graph_exec);
   if (c->fence_event != nullptr) cudaEventDestroy(c->fence_event);
   if (c->own_stream != nullptr) cudaStreamDestroy(c->own_stream);
+  if (c->copy_stream != nullptr) cudaStreamDestroy(c->copy_stream);
+  for (cudaEvent_t e : c->upload_events) cudaEventDestroy(e);
   for (auto& r : c->prof_recs) {
     cudaEventDestroy(r.e0);
     cudaEventDestroy(r.e1);
@@ -674,6 +885,32 @@ DVL_API int dvl_get_profile(dvl_ctx* c, double* stage_ms, uint64_t* stage_launch
   return DVL_OK;
 }
 
+DVL_API int dvl_encode_labels(dvl_ctx* c, const void* labels, int label_dtype, int64_t n, uint8_t* out_codes,
+                              int64_t* out_info_host, void* stream) {
+  if (c == nullptr) return DVL_ERR_INVALID;
+  if (labels == nullptr || out_codes == nullptr || out_info_host == nullptr || n < 1)
+    return dvl::set_error(c, DVL_ERR_INVALID, "bad label arguments");
+  dvl::DeviceGuard guard(c->device);
+  cudaStream_t st = (cudaStream_t)stream;
+  DVL_TRY(dvl::ensure(c, c->label_info, sizeof(unsigned long long) * (dvl::kMaxClasses + 2)));
+  {
+    dvl::StageScope scope(c, DVL_STAGE_PREP, st);
+    DVL_TRY(dvl::launch_encode_labels(c, labels, label_dtype, n, out_codes, (unsigned long long*)c->label_info.ptr, st));
+  }
+  unsigned long long info[dvl::kMaxClasses + 2];
+  DVL_CUDA(c, cudaMemcpyAsync(info, c->label_info.ptr, sizeof(info), cudaMemcpyDeviceToHost, st));
+  DVL_CUDA(c, cudaStreamSynchronize(st));
+  bool contiguous = info[dvl::kMaxClasses] == 0;
+  for (int k = 0; k < dvl::kMaxClasses; ++k) {
+    out_info_host[k] = (int64_t)info[k];
+    if (k <= (int)info[dvl::kMaxClasses + 1] && info[k] == 0) contiguous = false;
+  }
+  out_info_host[16] = (int64_t)info[dvl::kMaxClasses + 1] + 1;
+  out_info_host[17] = info[dvl::kMaxClasses] != 0 ? 1 : 0;
+  out_info_host[18] = contiguous ? 1 : 0;
+  return DVL_OK;
+}
+
 DVL_API int dvl_similarity(dvl_ctx* c, const void* gallery, int gdt, const void* queries, int qdt, int64_t n, int32_t d,
                    int32_t q, int precision, uint32_t flags, float* out, int64_t ld_out, void* stream) {
   DVL_TRY(dvl::check_common(c, n, d, q, 1, 1, precision, gdt, qdt));
@@ -707,7 +944,14 @@ DVL_API int dvl_rank_and_score(dvl_ctx* c, const float* scores, int64_t ld_score
   int32_t* ranked_len = out_ranked_len != nullptr ? out_ranked_len : (int32_t*)c->seg_len.ptr;
   DVL_TRY(dvl::rank_full(c, labels, n, n, q, n_classes, top_n, ldk, per_query, ranked_len, out_ranked_idx, ranked_cap,
                          st));
-  return dvl::finish(c, per_query, q, n_classes, out_mean4, true, st);
+  int rc = dvl::finish(c, per_query, q, n_classes, out_mean4, true, st);
+  if (rc == dvl::kRetryLsd) {      // bucket overflow: the keys are still in place, rank them with the radix sort
+    c->force_lsd = true;
+    rc = dvl::rank_full(c, labels, n, n, q, n_classes, top_n, ldk, per_query, ranked_len, out_ranked_idx, ranked_cap, st);
+    if (rc == DVL_OK) rc = dvl::finish(c, per_query, q, n_classes, out_mean4, true, st);
+    c->force_lsd = false;
+  }
+  return rc;
 }
 
 namespace dvl {
@@ -773,14 +1017,21 @@ int rerank_flagged(Ctx* c, const Operands& gallery_op, const void* queries, int 
 }  // namespace
 }  // namespace dvl
 
-DVL_API int dvl_eval_ranking(dvl_ctx* c, const void* gallery, int gdt, const void* queries, int qdt, const uint8_t* labels,
-                     int64_t n, int32_t d, int32_t q, int32_t n_classes, int64_t top_n, int precision,
-                     uint32_t flags, double* out_mean4, double* out_per_query, int32_t* out_ranked_len,
-                     int32_t* out_ranked_idx, int64_t ranked_cap, float* out_scores, void* stream) {
+namespace dvl {
+namespace {
+
+// dvl_eval_ranking, with the gallery either resident (feed == nullptr) or still arriving from the host
+int eval_ranking_impl(dvl_ctx* c, const void* gallery, int gdt, const void* queries, int qdt, const uint8_t* labels,
+                      int64_t n, int32_t d, int32_t q, int32_t n_classes, int64_t top_n, int precision,
+                      uint32_t flags, double* out_mean4, double* out_per_query, int32_t* out_ranked_len,
+                      int32_t* out_ranked_idx, int64_t ranked_cap, float* out_scores, void* stream, RowFeed* feed) {
   DVL_TRY(dvl::check_common(c, n, d, q, n_classes, top_n, precision, gdt, qdt));
   if (gallery == nullptr || queries == nullptr || labels == nullptr)
     return dvl::set_error(c, DVL_ERR_INVALID, "null input pointer");
   if (out_ranked_idx != nullptr && ranked_cap < 1) return dvl::set_error(c, DVL_ERR_INVALID, "ranked_cap must be >= 1");
+  c->radix_only = false;      // per-call state a failed earlier call may have left behind
+  c->force_lsd = false;
+  c->bucket_used = false;
   dvl::DeviceGuard guard(c->device);
   cudaStream_t st = (cudaStream_t)stream;
   DVL_TRY(dvl::ensure(c, c->per_query, (size_t)q * 4 * sizeof(double)));
@@ -789,7 +1040,9 @@ DVL_API int dvl_eval_ranking(dvl_ctx* c, const void* gallery, int gdt, const voi
   int32_t* ranked_len = out_ranked_len != nullptr ? out_ranked_len : (int32_t*)c->seg_len.ptr;
 
   dvl::StreamPlan plan;
-  const bool stream_route = out_scores == nullptr && dvl::plan_stream(n, q, top_n, flags, &plan);
+  // rows still arriving: no pilot sample (it would need the whole gallery first), progressive thresholds only
+  const bool stream_route = out_scores == nullptr &&
+                            dvl::plan_stream(n, q, top_n, feed != nullptr ? (flags | DVL_FLAG_NO_PILOT) : flags, &plan);
   if (stream_route) {
     DVL_TRY(dvl::run_label_stats(c, labels, n, n_classes, (n > top_n ? n : top_n) + 2, st));
     {   // the ranked lists hold up to sort_cap rows, which can exceed n on a small forced-stream gallery
@@ -797,8 +1050,8 @@ DVL_API int dvl_eval_ranking(dvl_ctx* c, const void* gallery, int gdt, const voi
       DVL_TRY(dvl::ensure_metric_tables(c, (int64_t)plan.sort_cap + 2, st));
     }
     dvl::Operands op;
-    DVL_TRY(dvl::prepare_operands(c, gallery, gdt, queries, qdt, n, d, q, precision, flags, &op, st));
-    DVL_TRY(dvl::stream_topk(c, op, labels, n, 0, d, q, top_n, plan, out_ranked_idx, ranked_cap, st));
+    DVL_TRY(dvl::prepare_operands(c, gallery, gdt, queries, qdt, n, d, q, precision, flags, &op, st, feed));
+    DVL_TRY(dvl::stream_topk(c, op, labels, n, 0, d, q, top_n, plan, out_ranked_idx, ranked_cap, st, feed));
     dvl::MetricArgs m;
     m.keys = nullptr;
     m.labs = (const uint8_t*)c->topk_labs.ptr;
@@ -817,8 +1070,12 @@ DVL_API int dvl_eval_ranking(dvl_ctx* c, const void* gallery, int gdt, const voi
       dvl::StageScope scope(c, DVL_STAGE_METRICS, st);
       DVL_TRY(dvl::launch_metrics(c, m, st));
     }
-    DVL_TRY(dvl::rerank_flagged(c, op, queries, qdt, labels, n, d, q, n_classes, top_n, precision, flags,
-                                per_query, ranked_len, out_ranked_idx, ranked_cap, st));
+    // flagged queries are tie-heavy by construction (a tie run longer than a candidate list): radix sort
+    c->force_lsd = true;
+    const int rr = dvl::rerank_flagged(c, op, queries, qdt, labels, n, d, q, n_classes, top_n, precision, flags,
+                                       per_query, ranked_len, out_ranked_idx, ranked_cap, st);
+    c->force_lsd = false;
+    DVL_TRY(rr);
     return dvl::finish(c, per_query, q, n_classes, out_mean4, true, st);
   }
 
@@ -829,7 +1086,19 @@ DVL_API int dvl_eval_ranking(dvl_ctx* c, const void* gallery, int gdt, const voi
   call.top_n = top_n; call.precision = precision; call.flags = flags;
   call.per_query = per_query; call.ranked_len = ranked_len; call.ranked_idx = out_ranked_idx;
   call.ranked_cap = ranked_cap; call.out_scores = out_scores;
-  return dvl::run_full_sort(c, call, out_mean4, st);
+  return dvl::run_full_sort(c, call, out_mean4, st, feed);
+}
+
+}  // namespace
+}  // namespace dvl
+
+DVL_API int dvl_eval_ranking(dvl_ctx* c, const void* gallery, int gdt, const void* queries, int qdt, const uint8_t* labels,
+                     int64_t n, int32_t d, int32_t q, int32_t n_classes, int64_t top_n, int precision,
+                     uint32_t flags, double* out_mean4, double* out_per_query, int32_t* out_ranked_len,
+                     int32_t* out_ranked_idx, int64_t ranked_cap, float* out_scores, void* stream) {
+  return dvl::eval_ranking_impl(c, gallery, gdt, queries, qdt, labels, n, d, q, n_classes, top_n, precision, flags,
+                                out_mean4, out_per_query, out_ranked_len, out_ranked_idx, ranked_cap, out_scores, stream,
+                                nullptr);
 }
 
 DVL_API int dvl_eval_ranking_host(dvl_ctx* c, const void* gallery_host, int gdt, const void* queries_host, int qdt,
@@ -846,16 +1115,15 @@ DVL_API int dvl_eval_ranking_host(dvl_ctx* c, const void* gallery_host, int gdt,
   DVL_TRY(dvl::ensure(c, c->h_gallery, gbytes));
   DVL_TRY(dvl::ensure(c, c->h_queries, qbytes));
   DVL_TRY(dvl::ensure(c, c->h_labels, (size_t)n));
-  {
-    dvl::StageScope scope(c, DVL_STAGE_COPY, st);
-    DVL_CUDA(c, cudaMemcpyAsync(c->h_gallery.ptr, gallery_host, gbytes, cudaMemcpyHostToDevice, st));
-    DVL_CUDA(c, cudaMemcpyAsync(c->h_queries.ptr, queries_host, qbytes, cudaMemcpyHostToDevice, st));
-    DVL_CUDA(c, cudaMemcpyAsync(c->h_labels.ptr, labels_host, (size_t)n, cudaMemcpyHostToDevice, st));
-  }
+  // queries and labels first, then the gallery in row blocks on the copy stream: operand split and
+  // similarity of a block start when the block has landed, the rest of the upload continues underneath
+  dvl::RowFeed feed;
+  const dvl::SmallCopy small[2] = {{c->h_queries.ptr, queries_host, qbytes}, {c->h_labels.ptr, labels_host, (size_t)n}};
+  DVL_TRY(dvl::start_upload(c, gallery_host, c->h_gallery.ptr, n, (size_t)d * dvl::dtype_size(gdt), small, 2, &feed, st));
   DVL_TRY(dvl::ensure(c, c->per_query, (size_t)q * 4 * sizeof(double)));
-  int rc = dvl_eval_ranking(c, c->h_gallery.ptr, gdt, c->h_queries.ptr, qdt, (const uint8_t*)c->h_labels.ptr, n, d, q,
-                            n_classes, top_n, precision, flags, out_mean4, (double*)c->per_query.ptr, nullptr,
-                            nullptr, 0, nullptr, stream);
+  int rc = dvl::eval_ranking_impl(c, c->h_gallery.ptr, gdt, c->h_queries.ptr, qdt, (const uint8_t*)c->h_labels.ptr, n, d,
+                                  q, n_classes, top_n, precision, flags, out_mean4, (double*)c->per_query.ptr, nullptr,
+                                  nullptr, 0, nullptr, stream, &feed);
   if (rc != DVL_OK) return rc;
   if (out_per_query_host != nullptr) {
     DVL_CUDA(c, cudaMemcpyAsync(out_per_query_host, c->per_query.ptr, (size_t)q * 4 * sizeof(double),
@@ -869,6 +1137,38 @@ DVL_API int dvl_eval_ranking_host(dvl_ctx* c, const void* gallery_host, int gdt,
 // multi-GPU: gallery shards.  The host (torch.distributed over NCCL) moves the small per-query
 // lists between these stages; see debias_vision_lang_b200/sharded.py.
 // ---------------------------------------------------------------------------------------------
+namespace dvl {
+namespace {
+
+int shard_topk_impl(dvl_ctx* c, const void* gallery, int gdt, const void* queries, int qdt, const uint8_t* labels,
+                    int64_t n_local, int64_t index_base, int32_t d, int32_t q, int32_t n_classes, int64_t top_n,
+                    int precision, uint32_t flags, float* out_tau, uint32_t* out_flags,
+                    unsigned long long* out_class_counts, int32_t* out_list_cap, cudaStream_t st, RowFeed* feed) {
+  StreamPlan plan;
+  // a shard always streams: top_n >= n_local just means the whole shard is kept
+  if (top_n > 8192) return set_error(c, DVL_ERR_UNSUPPORTED, "sharded ranking supports top_n <= 8192");
+  // a shard with fewer than top_n rows keeps all of them and leaves tau at -inf: its worst score says
+  // nothing about the global top_n-th
+  if (!plan_stream(n_local, q, top_n, feed != nullptr ? (flags | DVL_FLAG_NO_PILOT) : flags, &plan, true))
+    return set_error(c, DVL_ERR_UNSUPPORTED, "no streaming plan for this shard");
+  DVL_TRY(run_label_stats(c, labels, n_local, n_classes, top_n + 2, st));
+  Operands op;
+  DVL_TRY(prepare_operands(c, gallery, gdt, queries, qdt, n_local, d, q, precision, flags, &op, st, feed));
+  DVL_TRY(stream_topk(c, op, labels, n_local, index_base, d, q, top_n, plan, nullptr, 0, st, feed));
+  c->shard_plan_cap = plan.cap;
+  c->shard_sort_cap = plan.sort_cap;
+  c->shard_q = q;
+  DVL_CUDA(c, cudaMemcpyAsync(out_tau, c->cand_tau.ptr, (size_t)q * 4, cudaMemcpyDeviceToDevice, st));
+  DVL_CUDA(c, cudaMemcpyAsync(out_flags, c->cand_flags.ptr, (size_t)q * 4, cudaMemcpyDeviceToDevice, st));
+  DVL_CUDA(c, cudaMemcpyAsync(out_class_counts, c->class_counts.ptr, sizeof(unsigned long long) * (kMaxClasses + 1),
+                              cudaMemcpyDeviceToDevice, st));
+  if (out_list_cap != nullptr) *out_list_cap = plan.sort_cap;
+  return DVL_OK;    // stream-ordered: the outputs are consumed by collectives enqueued after this call
+}
+
+}  // namespace
+}  // namespace dvl
+
 DVL_API int dvl_shard_topk(dvl_ctx* c, const void* gallery, int gdt, const void* queries, int qdt, const uint8_t* labels,
                    int64_t n_local, int64_t index_base, int32_t d, int32_t q, int32_t n_classes, int64_t top_n,
                    int precision, uint32_t flags, float* out_tau, uint32_t* out_flags,
@@ -878,27 +1178,37 @@ DVL_API int dvl_shard_topk(dvl_ctx* c, const void* gallery, int gdt, const void*
       out_class_counts == nullptr)
     return dvl::set_error(c, DVL_ERR_INVALID, "null pointer");
   dvl::DeviceGuard guard(c->device);
+  return dvl::shard_topk_impl(c, gallery, gdt, queries, qdt, labels, n_local, index_base, d, q, n_classes, top_n,
+                              precision, flags, out_tau, out_flags, out_class_counts, out_list_cap, (cudaStream_t)stream,
+                              nullptr);
+}
+
+DVL_API int dvl_shard_topk_host(dvl_ctx* c, const void* gallery_host, int gdt, const void* queries_host, int qdt,
+                        const uint8_t* labels_host, int64_t n_local, int64_t index_base, int32_t d, int32_t q,
+                        int32_t n_classes, int64_t top_n, int precision, uint32_t flags, float* out_tau,
+                        uint32_t* out_flags, unsigned long long* out_class_counts, int32_t* out_list_cap,
+                        const void** out_gallery_dev, const void** out_queries_dev, const uint8_t** out_labels_dev,
+                        void* stream) {
+  DVL_TRY(dvl::check_common(c, n_local, d, q, n_classes, top_n, precision, gdt, qdt));
+  if (gallery_host == nullptr || queries_host == nullptr || labels_host == nullptr || out_tau == nullptr ||
+      out_flags == nullptr || out_class_counts == nullptr)
+    return dvl::set_error(c, DVL_ERR_INVALID, "null pointer");
+  dvl::DeviceGuard guard(c->device);
   cudaStream_t st = (cudaStream_t)stream;
-  dvl::StreamPlan plan;
-  // a shard always streams: top_n >= n_local just means the whole shard is kept
-  if (top_n > 8192) return dvl::set_error(c, DVL_ERR_UNSUPPORTED, "sharded ranking supports top_n <= 8192");
-  // a shard with fewer than top_n rows keeps all of them and leaves tau at -inf: its worst score says
-  // nothing about the global top_n-th
-  if (!dvl::plan_stream(n_local, q, top_n, flags, &plan, true))
-    return dvl::set_error(c, DVL_ERR_UNSUPPORTED, "no streaming plan for this shard");
-  DVL_TRY(dvl::run_label_stats(c, labels, n_local, n_classes, top_n + 2, st));
-  dvl::Operands op;
-  DVL_TRY(dvl::prepare_operands(c, gallery, gdt, queries, qdt, n_local, d, q, precision, flags, &op, st));
-  DVL_TRY(dvl::stream_topk(c, op, labels, n_local, index_base, d, q, top_n, plan, nullptr, 0, st));
-  c->shard_plan_cap = plan.cap;
-  c->shard_sort_cap = plan.sort_cap;
-  c->shard_q = q;
-  DVL_CUDA(c, cudaMemcpyAsync(out_tau, c->cand_tau.ptr, (size_t)q * 4, cudaMemcpyDeviceToDevice, st));
-  DVL_CUDA(c, cudaMemcpyAsync(out_flags, c->cand_flags.ptr, (size_t)q * 4, cudaMemcpyDeviceToDevice, st));
-  DVL_CUDA(c, cudaMemcpyAsync(out_class_counts, c->class_counts.ptr, sizeof(unsigned long long) * (dvl::kMaxClasses + 1),
-                              cudaMemcpyDeviceToDevice, st));
-  if (out_list_cap != nullptr) *out_list_cap = plan.sort_cap;
-  return DVL_OK;    // stream-ordered: the outputs are consumed by collectives enqueued after this call
+  const size_t row_bytes = (size_t)d * dvl::dtype_size(gdt);
+  const size_t qbytes = (size_t)q * d * dvl::dtype_size(qdt);
+  DVL_TRY(dvl::ensure(c, c->h_gallery, (size_t)n_local * row_bytes));
+  DVL_TRY(dvl::ensure(c, c->h_queries, qbytes));
+  DVL_TRY(dvl::ensure(c, c->h_labels, (size_t)n_local));
+  dvl::RowFeed feed;
+  const dvl::SmallCopy small[2] = {{c->h_queries.ptr, queries_host, qbytes}, {c->h_labels.ptr, labels_host, (size_t)n_local}};
+  DVL_TRY(dvl::start_upload(c, gallery_host, c->h_gallery.ptr, n_local, row_bytes, small, 2, &feed, st));
+  if (out_gallery_dev != nullptr) *out_gallery_dev = c->h_gallery.ptr;
+  if (out_queries_dev != nullptr) *out_queries_dev = c->h_queries.ptr;
+  if (out_labels_dev != nullptr) *out_labels_dev = (const uint8_t*)c->h_labels.ptr;
+  return dvl::shard_topk_impl(c, c->h_gallery.ptr, gdt, c->h_queries.ptr, qdt, (const uint8_t*)c->h_labels.ptr, n_local,
+                              index_base, d, q, n_classes, top_n, precision, flags, out_tau, out_flags, out_class_counts,
+                              out_list_cap, st, &feed);
 }
 
 DVL_API int dvl_shard_trim(dvl_ctx* c, const float* tau_bound, int32_t q, int32_t* out_cnt, void* stream) {

@@ -1,0 +1,507 @@
+// Ranking stage, full-sort route, fast path (measuring_bias.py:29,57 -> pandas
+// nlargest(keep="all"), which for top_n >= N is a stable descending sort of the N scores of a query).
+//
+// The LSD radix sort of segsort.cu moves every key through HBM eight times (four histogram reads, four
+// scatter passes) and spends ~2.4 warp instructions per key and pass on digit matching.  A query's scores
+// are not arbitrary 32-bit patterns, though: they are N samples of one smooth distribution.  This file
+// sorts them the way that structure allows -- two levels of SCORE-LINEAR bucketing, each key touched twice:
+//
+//   bucket_plan_kernel       one CTA per query: a strided sample of the query's keys -> score range, a
+//                            4096-cell histogram of the sample over that range, and from its prefix sums a
+//                            monotone cell -> bucket table that cuts the range into B buckets of about
+//                            equal mass (B ~ N / 2048).
+//   bucket_partition_kernel  one CTA per 4096-key tile: cell = (smax - s) * scale, bucket = table[cell];
+//                            the tile is grouped by bucket in shared memory and appended to the buckets'
+//                            storage (one global atomic per tile and bucket).  An entry is
+//                            key << 32 | gallery index << 4 | label -- the u64 order of the entries IS the
+//                            reference's order (score descending, lowest index first), so the append order
+//                            does not matter.
+//   bucket_sort_kernel       one CTA per bucket (<= 4096 entries, in shared memory): a second score-linear
+//                            split into 2048 sub-bins (counting sort: ~1 entry per sub-bin), then the
+//                            few sub-bins holding several entries are put in order by their full u64 value.
+//                            Emits the ranked labels (all the metrics need), and on request indices / keys.
+//
+// Monotonicity is what makes this exact: s -> (smax - s) * scale -> floor is non-increasing in s step by
+// step in floating point, the cell -> bucket table is non-decreasing, so every key of bucket b ranks
+// before every key of bucket b + 1, and likewise for sub-bins; equal keys always share a bucket and a
+// sub-bin and are ordered by the index inside the entry.  NaN keys (rows pandas drops, selectn.py:133-134)
+// go to the last sub-bin of the last bucket and sort last.
+//
+// Data that defeats the balance (massive exact ties: an all-zero query, a tiny score alphabet) overflows
+// a bucket's 4096-entry storage; the kernels then raise a flag that travels to the host with the results,
+// and the caller repeats the ranking with the radix sort of segsort.cu, which has no such limit.
+#include "dvl_common.cuh"
+#include "dvl_internal.h"
+
+namespace dvl {
+
+namespace {
+
+constexpr int kCells = 4096;                 // first-level cells per query
+constexpr int kBucketCap = 4096;             // entries a bucket can hold
+constexpr int kBucketTarget = 2048;          // planned entries per bucket
+constexpr int kMaxBuckets = 256;
+constexpr int kSubBins = 2048;               // second-level bins per bucket (8 per thread of the sort CTA)
+constexpr int kPartThreads = 256;
+constexpr int kPartItems = 16;
+constexpr int kPartTile = kPartThreads * kPartItems;     // 4096 keys per partition CTA
+constexpr int kSortThreads2 = 256;
+constexpr int kSortItems = kBucketCap / kSortThreads2;   // 16 entries per thread
+constexpr int kGroupMax = 48;                // sub-bins above this size: the CTA sorts the bucket bitonically
+
+struct SegPlan {      // per query
+  float smax;         // cell = clamp((smax - s) * scale)
+  float scale;
+};
+
+__device__ __forceinline__ int cell_of(uint32_t key, float smax, float scale) {
+  if (key == kNanKey) return kCells - 1;
+  const float s = key_to_score(key);
+  // fminf/fmaxf keep the order and turn the +-inf cases into the end cells; (smax - s) is NaN only for
+  // inf - inf, which fmaxf(.., 0) maps to cell 0 -- correct, s = +inf = smax is the best score
+  const float f = fminf(fmaxf((smax - s) * scale, 0.0f), (float)(kCells - 1));
+  return (int)f;
+}
+
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) bucket_plan_kernel(const uint32_t* __restrict__ keys, int64_t ldk, int64_t n,
+                                                          int n_buckets, int n_samples, SegPlan* __restrict__ plans,
+                                                          uint8_t* __restrict__ luts, uint32_t* __restrict__ bucket_cnt) {
+  __shared__ uint32_t hist[kCells];
+  __shared__ float red_min[8], red_max[8];
+  __shared__ uint32_t warp_tot[8];
+  const int q = blockIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const uint32_t* seg = keys + (int64_t)q * ldk;
+  for (int i = tid; i < kCells; i += 256) hist[i] = 0u;
+  for (int i = tid; i < n_buckets; i += 256) bucket_cnt[(int64_t)q * kMaxBuckets + i] = 0u;
+  // every (n / n_samples)-th key; the sample is read twice (range, then histogram) -- it is L2/L1 resident
+  const int64_t step = n / n_samples > 0 ? n / n_samples : 1;
+  const int samples = (int)((n + step - 1) / step);
+  float lo = __int_as_float(0x7f800000), hi = __int_as_float(0xff800000);
+  for (int i = tid; i < samples; i += 256) {
+    const uint32_t k = __ldg(seg + (int64_t)i * step);
+    if (k == kNanKey) continue;
+    const float s = key_to_score(k);
+    if (fabsf(s) <= 3.4028234664e38f) {      // finite scores define the range
+      lo = fminf(lo, s);
+      hi = fmaxf(hi, s);
+    }
+  }
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) {
+    lo = fminf(lo, __shfl_xor_sync(0xffffffffu, lo, off));
+    hi = fmaxf(hi, __shfl_xor_sync(0xffffffffu, hi, off));
+  }
+  if (lane == 0) { red_min[warp] = lo; red_max[warp] = hi; }
+  __syncthreads();
+  lo = red_min[0];
+  hi = red_max[0];
+#pragma unroll
+  for (int w = 1; w < 8; ++w) {
+    lo = fminf(lo, red_min[w]);
+    hi = fmaxf(hi, red_max[w]);
+  }
+  float scale = 0.0f;                         // no finite sample, or all equal: one cell, one bucket
+  if (hi > lo) {
+    scale = (float)kCells / (hi - lo);
+    if (!(fabsf(scale) <= 3.4028234664e38f)) scale = 0.0f;
+  }
+  if (!(hi >= lo)) hi = 0.0f;
+  for (int i = tid; i < samples; i += 256) atomicAdd(&hist[cell_of(__ldg(seg + (int64_t)i * step), hi, scale)], 1u);
+  __syncthreads();
+  // exclusive prefix over the cells, 16 consecutive cells per thread
+  uint32_t local[16];
+  uint32_t sum = 0;
+#pragma unroll
+  for (int j = 0; j < 16; ++j) {
+    local[j] = hist[tid * 16 + j];
+    sum += local[j];
+  }
+  uint32_t incl = sum;
+#pragma unroll
+  for (int off = 1; off < 32; off <<= 1) {
+    const uint32_t o = __shfl_up_sync(0xffffffffu, incl, off);
+    if (lane >= off) incl += o;
+  }
+  if (lane == 31) warp_tot[warp] = incl;
+  __syncthreads();
+  uint32_t run = incl - sum;
+  for (int w = 0; w < warp; ++w) run += warp_tot[w];
+  uint8_t* lut = luts + (int64_t)q * kCells;
+  uint32_t packed[4] = {0u, 0u, 0u, 0u};
+  const float slices = (float)n_buckets / (float)samples;
+#pragma unroll
+  for (int j = 0; j < 16; ++j) {
+    // bucket of a cell = the equal-mass slice its first sample falls into (monotone in the prefix count)
+    uint32_t b = (uint32_t)((float)run * slices);
+    if (b > (uint32_t)(n_buckets - 1)) b = (uint32_t)(n_buckets - 1);
+    packed[j >> 2] |= b << (8 * (j & 3));
+    run += local[j];
+  }
+  reinterpret_cast<uint4*>(lut)[tid] = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+  if (tid == 0) {
+    plans[q].smax = hi;
+    plans[q].scale = scale;
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kPartThreads, 4)
+bucket_partition_kernel(const uint32_t* __restrict__ keys, int64_t ldk, int64_t n,
+                        const uint8_t* __restrict__ gallery_labels, const SegPlan* __restrict__ plans,
+                        const uint8_t* __restrict__ luts, uint32_t* __restrict__ bucket_cnt, int n_buckets,
+                        unsigned long long* __restrict__ store, uint32_t* __restrict__ nan_cnt,
+                        uint32_t* __restrict__ overflow) {
+  __shared__ __align__(16) uint8_t lut[kCells];
+  __shared__ uint32_t hist[kMaxBuckets];       // entries of this tile per bucket, then their staging offset
+  __shared__ uint32_t gbase[kMaxBuckets];      // where the tile's run starts in the bucket's storage
+  __shared__ unsigned long long stage[kPartTile];
+  __shared__ uint32_t warp_tot[kPartThreads / 32];
+  const int q = blockIdx.y;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  reinterpret_cast<uint4*>(lut)[tid] = __ldg(reinterpret_cast<const uint4*>(luts + (int64_t)q * kCells) + tid);
+  hist[tid] = 0u;                              // kPartThreads == kMaxBuckets
+  const float smax = plans[q].smax, scale = plans[q].scale;
+  const uint32_t* seg = keys + (int64_t)q * ldk;
+  const int64_t base = (int64_t)blockIdx.x * kPartTile;
+  const int count = (n - base >= kPartTile) ? kPartTile : (int)(n - base);
+  // thread owns keys base + r*1024 + tid*4 + {0..3}; ldk and base are multiples of 4 (aligned 16-byte loads;
+  // the padding of the last group is read but never used)
+  uint32_t key[kPartItems];
+  uint32_t lab4[kPartItems / 4];
+  const bool lab_aligned = (reinterpret_cast<uintptr_t>(gallery_labels) & 3u) == 0;   // the C ABI takes any pointer
+#pragma unroll
+  for (int r = 0; r < kPartItems / 4; ++r) {
+    const int p = r * (kPartThreads * 4) + tid * 4;
+    uint4 v = make_uint4(0u, 0u, 0u, 0u);
+    uint32_t l = 0u;
+    if (p < count) {
+      v = __ldg(reinterpret_cast<const uint4*>(seg + base + p));
+      if (p + 4 <= count && lab_aligned) {
+        l = __ldg(reinterpret_cast<const uint32_t*>(gallery_labels + base + p));
+      } else {
+        for (int j = 0; j < 4 && p + j < count; ++j) l |= (uint32_t)gallery_labels[base + p + j] << (8 * j);
+      }
+    }
+    key[4 * r] = v.x; key[4 * r + 1] = v.y; key[4 * r + 2] = v.z; key[4 * r + 3] = v.w;
+    lab4[r] = l;
+  }
+  __syncthreads();
+  uint32_t slot[kPartItems];                   // bucket << 16 | arrival order inside the tile's bucket run
+  uint32_t nans = 0;
+#pragma unroll
+  for (int i = 0; i < kPartItems; ++i) {
+    const int p = (i >> 2) * (kPartThreads * 4) + tid * 4 + (i & 3);
+    slot[i] = 0u;
+    if (p < count) {
+      const uint32_t b = lut[cell_of(key[i], smax, scale)];
+      nans += (key[i] == kNanKey);
+      slot[i] = (b << 16) | atomicAdd(&hist[b], 1u);
+    }
+  }
+  if (nan_cnt != nullptr && nans != 0u) atomicAdd(nan_cnt + q, nans);      // NaN scores are rare
+  __syncthreads();
+  {
+    // reserve the runs in the buckets' storage; exclusive prefix of the tile's bucket counts = staging offsets
+    const uint32_t mine = hist[tid];
+    uint32_t g = 0u;
+    if (tid < n_buckets && mine != 0u) g = atomicAdd(bucket_cnt + (int64_t)q * kMaxBuckets + tid, mine);
+    uint32_t incl = mine;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+      const uint32_t o = __shfl_up_sync(0xffffffffu, incl, off);
+      if (lane >= off) incl += o;
+    }
+    if (lane == 31) warp_tot[warp] = incl;
+    __syncthreads();
+    uint32_t excl = incl - mine;
+    for (int w = 0; w < warp; ++w) excl += warp_tot[w];
+    if (g + mine > (uint32_t)kBucketCap) {
+      if (mine != 0u) atomicOr(overflow, 1u);
+    }
+    gbase[tid] = g - excl;                     // storage position = gbase[b] + staging position
+    hist[tid] = excl;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < kPartItems; ++i) {
+    const int p = (i >> 2) * (kPartThreads * 4) + tid * 4 + (i & 3);
+    if (p < count) {
+      const uint32_t b = slot[i] >> 16;
+      const uint32_t lab = (lab4[i >> 2] >> (8 * (i & 3))) & 0xFu;
+      stage[hist[b] + (slot[i] & 0xFFFFu)] =
+          ((unsigned long long)key[i] << 32) | ((unsigned long long)(uint32_t)(base + p) << 4) | lab;
+    }
+  }
+  __syncthreads();
+  unsigned long long* out = store + (int64_t)q * n_buckets * kBucketCap;
+  for (int p = tid; p < count; p += kPartThreads) {
+    const unsigned long long e = stage[p];
+    const uint32_t b = lut[cell_of((uint32_t)(e >> 32), smax, scale)];
+    const uint32_t pos = gbase[b] + (uint32_t)p;
+    if (pos < (uint32_t)kBucketCap) out[(int64_t)b * kBucketCap + pos] = e;
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+struct BucketSortParams {
+  const unsigned long long* store;
+  const uint32_t* bucket_cnt;
+  int n_buckets;
+  uint8_t* labs_out; int64_t ldl;
+  int32_t* idx_out; int64_t ldi;
+  uint32_t* keys_out; int64_t ldko;
+};
+
+constexpr size_t kSortSmem = (size_t)kBucketCap * 8 + (size_t)kSubBins * 4;
+constexpr int kBinsPerThread = kSubBins / kSortThreads2;      // 8 consecutive sub-bins per thread
+
+__global__ void __launch_bounds__(kSortThreads2, 4) bucket_sort_kernel(const BucketSortParams p) {
+  extern __shared__ __align__(16) uint8_t smem_dyn[];
+  unsigned long long* list = reinterpret_cast<unsigned long long*>(smem_dyn);        // [kBucketCap]
+  uint32_t* bins = reinterpret_cast<uint32_t*>(smem_dyn + (size_t)kBucketCap * 8);   // [kSubBins]
+  __shared__ float red_min[8], red_max[8];
+  __shared__ uint32_t warp_tot[8];
+  __shared__ uint32_t sh_big;
+  const int q = blockIdx.y, b = blockIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const uint32_t* cnts = p.bucket_cnt + (int64_t)q * kMaxBuckets;
+  const uint32_t raw = cnts[b];
+  const int count = raw > (uint32_t)kBucketCap ? kBucketCap : (int)raw;   // overflowed: the caller falls back
+  if (count == 0) return;
+  // ranks of this bucket's rows start after the rows of the buckets before it
+  uint32_t before = 0;
+  for (int i = lane; i < b; i += 32) before += cnts[i];
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) before += __shfl_xor_sync(0xffffffffu, before, off);
+  // 8 consecutive sub-bins per thread: zeroed, scanned and fixed up by their owner
+  reinterpret_cast<uint4*>(bins)[2 * tid] = make_uint4(0u, 0u, 0u, 0u);
+  reinterpret_cast<uint4*>(bins)[2 * tid + 1] = make_uint4(0u, 0u, 0u, 0u);
+  if (tid == 0) sh_big = 0u;
+  const unsigned long long* src = p.store + ((int64_t)q * p.n_buckets + b) * kBucketCap;
+  // entry i of this thread = position i * 256 + tid; a bucket is planned half full, so the upper rounds
+  // are usually empty and skipped by the whole CTA (uniform breaks)
+  unsigned long long e[kSortItems];
+  float lo = __int_as_float(0x7f800000), hi = __int_as_float(0xff800000);
+#pragma unroll
+  for (int i = 0; i < kSortItems; ++i) {
+    if (i * kSortThreads2 >= count) break;
+    const int pos = i * kSortThreads2 + tid;
+    e[i] = ~0ull;
+    if (pos < count) {
+      e[i] = __ldg(src + pos);
+      const uint32_t k = (uint32_t)(e[i] >> 32);
+      const float s = key_to_score(k);
+      if (k != kNanKey && fabsf(s) <= 3.4028234664e38f) {
+        lo = fminf(lo, s);
+        hi = fmaxf(hi, s);
+      }
+    }
+  }
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) {
+    lo = fminf(lo, __shfl_xor_sync(0xffffffffu, lo, off));
+    hi = fmaxf(hi, __shfl_xor_sync(0xffffffffu, hi, off));
+  }
+  if (lane == 0) { red_min[warp] = lo; red_max[warp] = hi; }
+  __syncthreads();
+  lo = red_min[0];
+  hi = red_max[0];
+#pragma unroll
+  for (int w = 1; w < 8; ++w) {
+    lo = fminf(lo, red_min[w]);
+    hi = fmaxf(hi, red_max[w]);
+  }
+  float scale = 0.0f;
+  if (hi > lo) {
+    scale = (float)kSubBins / (hi - lo);
+    if (!(fabsf(scale) <= 3.4028234664e38f)) scale = 0.0f;
+  }
+  if (!(hi >= lo)) hi = 0.0f;
+  // counting sort over the sub-bins: the arrival order inside a sub-bin is arbitrary, fixed up below
+  uint32_t sub[kSortItems];                    // sub-bin << 13 | arrival
+#pragma unroll
+  for (int i = 0; i < kSortItems; ++i) {
+    if (i * kSortThreads2 >= count) break;
+    const int pos = i * kSortThreads2 + tid;
+    if (pos < count) {
+      const uint32_t k = (uint32_t)(e[i] >> 32);
+      int sb = kSubBins - 1;
+      if (k != kNanKey) {
+        const float s = key_to_score(k);
+        sb = (int)fminf(fmaxf((hi - s) * scale, 0.0f), (float)(kSubBins - 1));
+      }
+      sub[i] = ((uint32_t)sb << 13) | atomicAdd(&bins[sb], 1u);
+    }
+  }
+  __syncthreads();
+  // exclusive prefix over the sub-bins; the owner keeps its bins' start offsets and sizes in registers
+  uint32_t start[kBinsPerThread + 1];
+  {
+    const uint4 c0 = reinterpret_cast<const uint4*>(bins)[2 * tid];
+    const uint4 c1 = reinterpret_cast<const uint4*>(bins)[2 * tid + 1];
+    const uint32_t cnt8[kBinsPerThread] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
+    uint32_t sum = 0, mx = 0;
+#pragma unroll
+    for (int j = 0; j < kBinsPerThread; ++j) {
+      start[j] = sum;
+      sum += cnt8[j];
+      mx = max(mx, cnt8[j]);
+    }
+    uint32_t incl = sum;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+      const uint32_t o = __shfl_up_sync(0xffffffffu, incl, off);
+      if (lane >= off) incl += o;
+    }
+    if (lane == 31) warp_tot[warp] = incl;
+    if (mx > (uint32_t)kGroupMax) sh_big = 1u;
+    __syncthreads();
+    uint32_t base = incl - sum;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) base += (w < warp) ? warp_tot[w] : 0u;
+#pragma unroll
+    for (int j = 0; j < kBinsPerThread; ++j) start[j] += base;
+    start[kBinsPerThread] = base + sum;
+    reinterpret_cast<uint4*>(bins)[2 * tid] = make_uint4(start[0], start[1], start[2], start[3]);
+    reinterpret_cast<uint4*>(bins)[2 * tid + 1] = make_uint4(start[4], start[5], start[6], start[7]);
+  }
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < kSortItems; ++i) {
+    if (i * kSortThreads2 >= count) break;
+    const int pos = i * kSortThreads2 + tid;
+    if (pos < count) list[bins[sub[i] >> 13] + (sub[i] & 0x1FFFu)] = e[i];
+  }
+  __syncthreads();
+  if (sh_big == 0u) {
+    // sub-bins holding several entries: insertion sort by the full entry (key, index), by the bins' owner
+#pragma unroll
+    for (int j = 0; j < kBinsPerThread; ++j) {
+      const uint32_t s0 = start[j], s1 = start[j + 1];
+      if (s1 - s0 == 2u) {
+        const unsigned long long a = list[s0], c = list[s0 + 1];
+        if (a > c) {
+          list[s0] = c;
+          list[s0 + 1] = a;
+        }
+      } else if (s1 - s0 > 2u) {
+        for (uint32_t i = s0 + 1; i < s1; ++i) {
+          const unsigned long long v = list[i];
+          uint32_t k = i;
+          while (k > s0 && list[k - 1] > v) {
+            list[k] = list[k - 1];
+            --k;
+          }
+          list[k] = v;
+        }
+      }
+    }
+  } else {
+    // a sub-bin is crowded (heavy ties inside the bucket): bitonic sort of the whole bucket
+    int pow2 = 1;
+    while (pow2 < count) pow2 <<= 1;
+    for (int i = count + tid; i < pow2; i += kSortThreads2) list[i] = ~0ull;
+    __syncthreads();
+    for (int size = 2; size <= pow2; size <<= 1) {
+      for (int stride = size >> 1; stride > 0; stride >>= 1) {
+        for (int t = tid; t < (pow2 >> 1); t += kSortThreads2) {
+          const int i = 2 * t - (t & (stride - 1));
+          const int j = i + stride;
+          const bool up = (i & size) == 0;
+          const unsigned long long a = list[i], c = list[j];
+          if ((a > c) == up) {
+            list[i] = c;
+            list[j] = a;
+          }
+        }
+        __syncthreads();
+      }
+    }
+  }
+  __syncthreads();
+  uint8_t* labs = p.labs_out + (int64_t)q * p.ldl + before;
+  for (int i = tid; i < count; i += kSortThreads2) {
+    const unsigned long long v = list[i];
+    labs[i] = (uint8_t)(v & 0xFull);
+    if (p.idx_out != nullptr) p.idx_out[(int64_t)q * p.ldi + before + i] = (int32_t)((v >> 4) & 0x0FFFFFFFull);
+    if (p.keys_out != nullptr) p.keys_out[(int64_t)q * p.ldko + before + i] = (uint32_t)(v >> 32);
+  }
+}
+
+}  // namespace
+
+bool bucket_sort_eligible(int64_t n) {
+  static const bool off = [] {
+    const char* e = getenv("DVL_SORT_LSD");
+    return e != nullptr && e[0] == '1';
+  }();
+  return !off && n >= 1 && n <= (int64_t)kMaxBuckets * kBucketTarget * 85 / 100;
+}
+
+static int buckets_for(int64_t n) {
+  int b = (int)((n + kBucketTarget - 1) / kBucketTarget);
+  return b < 1 ? 1 : (b > kMaxBuckets ? kMaxBuckets : b);
+}
+
+size_t bucket_sort_workspace_per_query(int64_t n) {
+  return (size_t)buckets_for(n) * kBucketCap * 8 + kCells + kMaxBuckets * 4 + sizeof(SegPlan);
+}
+
+int launch_bucket_sort(Ctx* c, const BucketSortArgs& a, cudaStream_t st) {
+  if (!bucket_sort_eligible(a.n)) return set_error(c, DVL_ERR_INVALID, "segment too long for the bucket sort");
+  if (a.ldk % 4 != 0) return set_error(c, DVL_ERR_INVALID, "sort pitch must be a multiple of 4");
+  const int nb = buckets_for(a.n);
+  int n_samples = 64 * nb;
+  if (n_samples < 1024) n_samples = 1024;
+  DVL_TRY(ensure(c, c->bk_store, (size_t)a.q * nb * kBucketCap * 8));
+  DVL_TRY(ensure(c, c->bk_cnt, (size_t)a.q * kMaxBuckets * 4));
+  DVL_TRY(ensure(c, c->bk_lut, (size_t)a.q * kCells));
+  DVL_TRY(ensure(c, c->bk_plan, (size_t)a.q * sizeof(SegPlan)));
+  if (!c->bucket_attr_set) {
+    DVL_CUDA(c, cudaFuncSetAttribute(bucket_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSortSmem));
+    c->bucket_attr_set = true;
+  }
+  if (a.nan_cnt != nullptr) DVL_CUDA(c, cudaMemsetAsync(a.nan_cnt, 0, (size_t)a.q * sizeof(uint32_t), st));
+  const int tiles = (int)((a.n + kPartTile - 1) / kPartTile);
+  for (int q0 = 0; q0 < a.q; q0 += 65535) {
+    const int qn = (a.q - q0) < 65535 ? (a.q - q0) : 65535;
+    const uint32_t* keys = a.keys + (int64_t)q0 * a.ldk;
+    SegPlan* plans = (SegPlan*)c->bk_plan.ptr + q0;
+    uint8_t* luts = (uint8_t*)c->bk_lut.ptr + (int64_t)q0 * kCells;
+    uint32_t* cnt = (uint32_t*)c->bk_cnt.ptr + (int64_t)q0 * kMaxBuckets;
+    unsigned long long* store = (unsigned long long*)c->bk_store.ptr + (int64_t)q0 * nb * kBucketCap;
+    {
+      StageScope scope(c, DVL_STAGE_SORT_HIST, st);
+      bucket_plan_kernel<<<(unsigned)qn, 256, 0, st>>>(keys, a.ldk, a.n, nb, n_samples, plans, luts, cnt);
+      DVL_LAUNCH_CHECK(c, "bucket_plan_kernel");
+    }
+    {
+      StageScope scope(c, DVL_STAGE_SORT_SCATTER, st);
+      dim3 grid((unsigned)tiles, (unsigned)qn);
+      bucket_partition_kernel<<<grid, kPartThreads, 0, st>>>(keys, a.ldk, a.n, a.gallery_labels, plans, luts, cnt, nb, store,
+                                                            a.nan_cnt != nullptr ? a.nan_cnt + q0 : nullptr, a.overflow);
+      DVL_LAUNCH_CHECK(c, "bucket_partition_kernel");
+    }
+    {
+      StageScope scope(c, DVL_STAGE_SORT_SCAN, st);
+      BucketSortParams p;
+      p.store = store;
+      p.bucket_cnt = cnt;
+      p.n_buckets = nb;
+      p.labs_out = a.labs_out + (int64_t)q0 * a.ldl;
+      p.ldl = a.ldl;
+      p.idx_out = a.idx_out != nullptr ? a.idx_out + (int64_t)q0 * a.ldi : nullptr;
+      p.ldi = a.ldi;
+      p.keys_out = a.keys_out != nullptr ? a.keys_out + (int64_t)q0 * a.ldko : nullptr;
+      p.ldko = a.ldko;
+      dim3 grid((unsigned)nb, (unsigned)qn);
+      bucket_sort_kernel<<<grid, kSortThreads2, kSortSmem, st>>>(p);
+      DVL_LAUNCH_CHECK(c, "bucket_sort_kernel");
+    }
+  }
+  return DVL_OK;
+}
+
+}  // namespace dvl

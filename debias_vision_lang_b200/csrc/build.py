@@ -9,7 +9,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 PKG = os.path.dirname(HERE)
 OUT = os.path.join(PKG, "libdvl_b200.so")
-SOURCES = ["api.cu", "prep.cu", "gemm.cu", "segsort.cu", "topk.cu", "metrics.cu"]
+SOURCES = ["api.cu", "prep.cu", "gemm.cu", "segsort.cu", "bucketsort.cu", "topk.cu", "metrics.cu"]
 HEADERS = ["dvl_common.cuh", "dvl_internal.h", os.path.join("..", "..", "include", "dvl_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "--expt-relaxed-constexpr"]
@@ -30,8 +30,43 @@ def stale() -> bool:
     return any(os.path.getmtime(d) > t for d in deps)
 
 
+INFO = os.path.join(PKG, "libdvl_b200.build.json")
+
+
+def sources_digest() -> str:
+    import hashlib
+    h = hashlib.sha256()
+    for f in SOURCES + HEADERS:
+        with open(os.path.join(HERE, f), "rb") as fh:
+            h.update(fh.read())
+    return h.hexdigest()[:16]
+
+
+def build_info() -> dict:
+    """What the in-tree library was built from (written by build(); bench.py copies it into its JSON line).
+    `sources_match` compares the digest recorded at build time with the sources present now."""
+    import json
+    try:
+        with open(INFO) as f:
+            info = json.load(f)
+    except (OSError, ValueError):
+        return {"built": None}
+    try:
+        info["sources_match"] = info.get("sources_sha16") == sources_digest()
+    except OSError:
+        info["sources_match"] = None
+    return info
+
+
 def build(force: bool = False, verbose: bool = False) -> str:
-    if not force and not stale():
+    """Compiles when the library is missing, older than a source, built from different sources, or when
+    forced (argument, or DVL_FORCE_BUILD=1 in the environment)."""
+    import json
+    import time
+    force = force or os.environ.get("DVL_FORCE_BUILD", "") == "1"
+    why = "forced" if force else ("stale" if stale() else
+                                  (None if build_info().get("sources_match") else "sources changed"))
+    if why is None:
         return OUT
     objdir = os.path.join(HERE, "build")
     os.makedirs(objdir, exist_ok=True)
@@ -55,6 +90,9 @@ def build(force: bool = False, verbose: bool = False) -> str:
     cmd = [nvcc(), "-shared", "-o", OUT, *objs, "-gencode", "arch=compute_100a,code=sm_100a",
            "-Xcompiler", "-fPIC", "-cudart", "static"]
     subprocess.check_call(cmd)
+    with open(INFO, "w") as f:
+        json.dump({"built": time.strftime("%Y-%m-%dT%H:%M:%SZ", time.gmtime()), "why": why,
+                   "sources_sha16": sources_digest(), "flags": " ".join(NVCC_FLAGS)}, f)
     return OUT
 
 

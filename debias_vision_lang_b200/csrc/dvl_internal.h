@@ -35,6 +35,14 @@ struct Ctx {
   // streaming top-k state
   DevBuf cand, cand_cnt, cand_tau, cand_flags, topk_labs, topk_avail, fb_queries, fb_per_query, fb_len, fb_idx;
   DevBuf merge_sorted, tab_chunks;
+  // bucket sort (bucketsort.cu): bucket storage, per-bucket counts, cell -> bucket tables, per-query plans,
+  // and the device word a bucket overflow raises
+  DevBuf bk_store, bk_cnt, bk_lut, bk_plan, sort_flag, label_info;
+  bool bucket_attr_set = false;
+  bool bucket_used = false;                // a ranking of the current call went through the bucket sort
+  bool force_lsd = false;                  // retry after an overflow: radix sort only
+  bool radix_only = false;                 // DVL_FLAG_RADIX_SORT of the current call
+  bool graph_bucket = false;               // the captured graph contains bucket-sort kernels
   bool select_attr_set = false;
   int64_t shard_plan_cap = 0;
   int shard_sort_cap = 0;
@@ -51,6 +59,9 @@ struct Ctx {
   cudaGraphExec_t graph_exec = nullptr;
   cudaStream_t own_stream = nullptr;
   cudaEvent_t fence_event = nullptr;
+  // host-input entry points: row blocks of the gallery travel on a copy stream, one event per block
+  cudaStream_t copy_stream = nullptr;
+  std::vector<cudaEvent_t> upload_events;
   // per-stage CUDA-event timing (dvl_set_profiling / dvl_get_profile)
   bool profiling = false;
   struct ProfRec { int stage; cudaEvent_t e0, e1; uint64_t launches; };
@@ -101,10 +112,15 @@ int ensure(Ctx* c, DevBuf& b, size_t bytes);
 // 1 = one bf16 plane, 3 = exact bf16 triple, 2 = two fp16 planes of the power-of-two scaled row.
 // row_scale [r] (required for planes == 2 or normalize): the factor the similarity epilogue applies to
 // the row: 2^-e of the scaled split, times 1/||row||_2 when `normalize`.
+// plane_rows: rows of a whole plane when `rows` is a row range of a larger matrix (src, dst and row_scale then
+// point at the range's first row); 0 = rows.
 int launch_split_rows(Ctx* c, const void* src, int dtype, int64_t rows, int d, int dp, int planes, void* dst,
-                      float* row_scale, bool normalize, cudaStream_t st);
+                      float* row_scale, bool normalize, cudaStream_t st, int64_t plane_rows = 0);
 int launch_class_counts(Ctx* c, const uint8_t* labels, int64_t n, int n_classes, unsigned long long* counts,
                         cudaStream_t st);
+// integer labels -> uint8 codes + info [kMaxClasses + 2]: per-class counts, out-of-range flag, largest label
+int launch_encode_labels(Ctx* c, const void* labels, int label_dtype, int64_t n, uint8_t* codes,
+                         unsigned long long* info, cudaStream_t st);
 
 // ---- gemm.cu ---------------------------------------------------------------------------
 enum { kGemmStore = 0, kGemmSeed = 1, kGemmFilter = 2 };
@@ -157,6 +173,29 @@ struct SortArgs {
 int launch_segmented_sort(Ctx* c, const SortArgs& a, int* out_buf, cudaStream_t st);
 int launch_scores_to_keys(Ctx* c, const float* scores, int64_t lds, uint32_t* keys, int64_t ldk, int64_t n, int q,
                           cudaStream_t st);
+
+// ---- bucketsort.cu ---------------------------------------------------------------------
+// Ascending sort of q segments of n ranking keys by two levels of score-linear bucketing (see the file
+// header).  Emits the ranked labels and optionally ranked indices / sorted keys, packed from position 0 of
+// each output row.  *overflow is OR-ed with 1 when a bucket did not fit (tie-heavy data): the outputs are
+// then garbage and the caller must rank again with launch_segmented_sort.
+struct BucketSortArgs {
+  const uint32_t* keys = nullptr;      // [q][ldk]
+  int64_t ldk = 0, n = 0;
+  int q = 0;
+  const uint8_t* gallery_labels = nullptr;
+  uint8_t* labs_out = nullptr;         // [q][ldl]
+  int64_t ldl = 0;
+  int32_t* idx_out = nullptr;          // [q][ldi] or null
+  int64_t ldi = 0;
+  uint32_t* keys_out = nullptr;        // [q][ldko] or null
+  int64_t ldko = 0;
+  uint32_t* nan_cnt = nullptr;         // [q] or null: number of NaN-keyed rows per segment
+  uint32_t* overflow = nullptr;        // device word
+};
+bool bucket_sort_eligible(int64_t n);
+size_t bucket_sort_workspace_per_query(int64_t n);
+int launch_bucket_sort(Ctx* c, const BucketSortArgs& a, cudaStream_t st);
 
 // ---- topk.cu ---------------------------------------------------------------------------
 struct SelectArgs {

@@ -528,7 +528,6 @@ int launch_sim_gemm(Ctx* c, const GemmArgs& a, cudaStream_t st) {
   p.ldk = a.ldk;
   p.scores = a.scores;
   p.lds = a.lds;
-  if (a.mode == kGemmStore && a.row0 != 0) return set_error(c, DVL_ERR_INVALID, "store mode takes the whole gallery");
   if (a.keys != nullptr && (a.ldk % 4 != 0 || a.ldk < ((a.n + BN - 1) / BN) * BN))
     return set_error(c, DVL_ERR_INVALID, "key pitch must cover whole 256-column tiles");
   if (a.scores != nullptr && (a.lds % 4 != 0 || a.lds < ((a.n + BN - 1) / BN) * BN))

@@ -57,12 +57,12 @@ __device__ __forceinline__ void load_quad(const T* __restrict__ s, int c, int d,
 // whole row is in flight per warp.  HBM-bound: 4 B read + 2*PLANES B written per element.
 template <typename T, int PLANES>
 __global__ void __launch_bounds__(256) split_rows_kernel(const T* __restrict__ src, int64_t rows, int d, int dp,
-                                                         __nv_bfloat16* __restrict__ dst,
+                                                         int64_t plane_rows, __nv_bfloat16* __restrict__ dst,
                                                          float* __restrict__ inv_norm, int vec) {
   constexpr int kUnroll = 4;
   const int lane = threadIdx.x & 31;
   const int64_t warps_total = (int64_t)gridDim.x * (blockDim.x >> 5);
-  const int64_t plane_stride = rows * (int64_t)dp;
+  const int64_t plane_stride = plane_rows * (int64_t)dp;   // rows of a whole plane (>= rows: row-range launches)
   for (int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); row < rows; row += warps_total) {
     const T* s = src + row * (int64_t)d;
     __nv_bfloat16* o = dst + row * (int64_t)dp;
@@ -104,12 +104,12 @@ __global__ void __launch_bounds__(256) split_rows_kernel(const T* __restrict__ s
 // (the second time from L1/L2).
 template <typename T>
 __global__ void __launch_bounds__(256) split_rows_f16x2_kernel(const T* __restrict__ src, int64_t rows, int d, int dp,
-                                                               __half* __restrict__ dst, float* __restrict__ row_scale,
-                                                               int normalize, int vec) {
+                                                               int64_t plane_rows, __half* __restrict__ dst,
+                                                               float* __restrict__ row_scale, int normalize, int vec) {
   constexpr int kUnroll = 4;
   const int lane = threadIdx.x & 31;
   const int64_t warps_total = (int64_t)gridDim.x * (blockDim.x >> 5);
-  const int64_t plane_stride = rows * (int64_t)dp;
+  const int64_t plane_stride = plane_rows * (int64_t)dp;   // rows of a whole plane (>= rows: row-range launches)
   const bool single = dp <= 128 * kUnroll;
   for (int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); row < rows; row += warps_total) {
     const T* s = src + row * (int64_t)d;
@@ -173,7 +173,7 @@ __global__ void __launch_bounds__(256) split_rows_f16x2_kernel(const T* __restri
 
 template <typename T>
 static int launch_split_t(Ctx* c, const T* src, int64_t rows, int d, int dp, int planes, void* dst, float* row_scale,
-                          bool normalize, cudaStream_t st) {
+                          bool normalize, int64_t plane_rows, cudaStream_t st) {
   const int warps_per_block = 8;
   int64_t blocks = (rows + warps_per_block - 1) / warps_per_block;
   int64_t cap = (int64_t)c->num_sms * 16;
@@ -182,30 +182,31 @@ static int launch_split_t(Ctx* c, const T* src, int64_t rows, int d, int dp, int
   // whole-quad vector loads need every row start aligned to the quad: d % 4 == 0 and an aligned base
   const int vec = (d % 4 == 0 && (reinterpret_cast<uintptr_t>(src) % (4 * sizeof(T))) == 0) ? 1 : 0;
   if (planes == 1)
-    split_rows_kernel<T, 1><<<(unsigned)blocks, 256, 0, st>>>(src, rows, d, dp, (__nv_bfloat16*)dst,
+    split_rows_kernel<T, 1><<<(unsigned)blocks, 256, 0, st>>>(src, rows, d, dp, plane_rows, (__nv_bfloat16*)dst,
                                                              normalize ? row_scale : nullptr, vec);
   else if (planes == 3)
-    split_rows_kernel<T, 3><<<(unsigned)blocks, 256, 0, st>>>(src, rows, d, dp, (__nv_bfloat16*)dst,
+    split_rows_kernel<T, 3><<<(unsigned)blocks, 256, 0, st>>>(src, rows, d, dp, plane_rows, (__nv_bfloat16*)dst,
                                                              normalize ? row_scale : nullptr, vec);
   else
-    split_rows_f16x2_kernel<T><<<(unsigned)blocks, 256, 0, st>>>(src, rows, d, dp, (__half*)dst, row_scale,
+    split_rows_f16x2_kernel<T><<<(unsigned)blocks, 256, 0, st>>>(src, rows, d, dp, plane_rows, (__half*)dst, row_scale,
                                                                 normalize ? 1 : 0, vec);
   DVL_LAUNCH_CHECK(c, planes == 2 ? "split_rows_f16x2_kernel" : "split_rows_kernel");
   return DVL_OK;
 }
 
 int launch_split_rows(Ctx* c, const void* src, int dtype, int64_t rows, int d, int dp, int planes, void* dst,
-                      float* row_scale, bool normalize, cudaStream_t st) {
+                      float* row_scale, bool normalize, cudaStream_t st, int64_t plane_rows) {
+  if (plane_rows < rows) plane_rows = rows;
   if (planes < 1 || planes > 3) return set_error(c, DVL_ERR_INVALID, "planes must be 1, 2 or 3");
   if (dp % 4 != 0) return set_error(c, DVL_ERR_INVALID, "row pitch must be a multiple of 4");
   if ((planes == 2 || normalize) && row_scale == nullptr)
     return set_error(c, DVL_ERR_INVALID, "split without a row-scale array");
   switch (dtype) {
-    case DVL_F32: return launch_split_t<float>(c, (const float*)src, rows, d, dp, planes, dst, row_scale, normalize, st);
+    case DVL_F32: return launch_split_t<float>(c, (const float*)src, rows, d, dp, planes, dst, row_scale, normalize, plane_rows, st);
     case DVL_BF16:
       return launch_split_t<__nv_bfloat16>(c, (const __nv_bfloat16*)src, rows, d, dp, planes, dst, row_scale, normalize,
-                                           st);
-    case DVL_F16: return launch_split_t<__half>(c, (const __half*)src, rows, d, dp, planes, dst, row_scale, normalize, st);
+                                           plane_rows, st);
+    case DVL_F16: return launch_split_t<__half>(c, (const __half*)src, rows, d, dp, planes, dst, row_scale, normalize, plane_rows, st);
     default: return set_error(c, DVL_ERR_INVALID, "unknown dtype %d", dtype);
   }
 }
@@ -237,6 +238,70 @@ __global__ void __launch_bounds__(256) class_counts_kernel(const uint8_t* __rest
   if (oob) atomicOr(bad, 1u);
   __syncthreads();
   if (threadIdx.x < n_classes && sh[threadIdx.x]) atomicAdd(&counts[threadIdx.x], (unsigned long long)sh[threadIdx.x]);
+}
+
+// ----------------------------------------------------------------------------------------
+// Integer labels as the dataset hands them over (int64 from np.array / torch.long, datasets.py:44) ->
+// uint8 class codes, plus what Counter(df.label) would see: per-class counts, the largest label, and
+// whether any label lies outside 0..kMaxClasses-1.  One pass, 8 bytes read + 1 byte written per row.
+template <typename T>
+__global__ void __launch_bounds__(256) encode_labels_kernel(const T* __restrict__ labels, int64_t n,
+                                                            uint8_t* __restrict__ codes,
+                                                            unsigned long long* __restrict__ info) {
+  __shared__ unsigned int sh[kMaxClasses + 2];
+  if (threadIdx.x < kMaxClasses + 2) sh[threadIdx.x] = 0;
+  __syncthreads();
+  unsigned int local[kMaxClasses];
+#pragma unroll
+  for (int k = 0; k < kMaxClasses; ++k) local[k] = 0;
+  unsigned int oob = 0, mx = 0;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const long long v = (long long)labels[i];
+    const bool bad = v < 0 || v >= kMaxClasses;
+    oob |= bad;
+    const unsigned int l = bad ? 0u : (unsigned int)v;
+    codes[i] = (uint8_t)(bad ? 0xFFu : l);
+    mx = max(mx, l);
+#pragma unroll
+    for (int k = 0; k < kMaxClasses; ++k) local[k] += (!bad && l == (unsigned)k);
+  }
+#pragma unroll
+  for (int k = 0; k < kMaxClasses; ++k) {
+    unsigned int v = local[k];
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+    if ((threadIdx.x & 31) == 0 && v) atomicAdd(&sh[k], v);
+  }
+  if (oob) atomicOr(&sh[kMaxClasses], 1u);
+  atomicMax(&sh[kMaxClasses + 1], mx);
+  __syncthreads();
+  if (threadIdx.x < kMaxClasses && sh[threadIdx.x]) atomicAdd(&info[threadIdx.x], (unsigned long long)sh[threadIdx.x]);
+  if (threadIdx.x == 0) {
+    if (sh[kMaxClasses]) atomicOr(&info[kMaxClasses], 1ull);
+    atomicMax(&info[kMaxClasses + 1], (unsigned long long)sh[kMaxClasses + 1]);
+  }
+}
+
+int launch_encode_labels(Ctx* c, const void* labels, int label_dtype, int64_t n, uint8_t* codes,
+                         unsigned long long* info, cudaStream_t st) {
+  DVL_CUDA(c, cudaMemsetAsync(info, 0, sizeof(unsigned long long) * (kMaxClasses + 2), st));
+  int64_t blocks = (n + 256 * 8 - 1) / (256 * 8);
+  if (blocks > (int64_t)c->num_sms * 8) blocks = (int64_t)c->num_sms * 8;
+  if (blocks < 1) blocks = 1;
+  switch (label_dtype) {
+    case DVL_LABEL_I64:
+      encode_labels_kernel<long long><<<(unsigned)blocks, 256, 0, st>>>((const long long*)labels, n, codes, info);
+      break;
+    case DVL_LABEL_I32:
+      encode_labels_kernel<int><<<(unsigned)blocks, 256, 0, st>>>((const int*)labels, n, codes, info);
+      break;
+    case DVL_LABEL_U8:
+      encode_labels_kernel<uint8_t><<<(unsigned)blocks, 256, 0, st>>>((const uint8_t*)labels, n, codes, info);
+      break;
+    default: return set_error(c, DVL_ERR_INVALID, "unknown label dtype %d", label_dtype);
+  }
+  DVL_LAUNCH_CHECK(c, "encode_labels_kernel");
+  return DVL_OK;
 }
 
 int launch_class_counts(Ctx* c, const uint8_t* labels, int64_t n, int n_classes, unsigned long long* counts,

@@ -138,7 +138,7 @@ __global__ void __launch_bounds__(kSelThreads) select_kernel(const SelectParams 
     return;
   }
   int64_t n;
-  if (p.segs == 1) {
+  if (p.cnt != nullptr) {                              // a local list (a merge of one shard has segs == 1, too)
     n = p.cnt[q];
     // More survivors than the list holds, or (final pass after an optimistic threshold) fewer than
     // top_n of them: the list is not a superset of the ranked rows -> exact re-rank of this query.

@@ -134,8 +134,10 @@ class EmbeddingGallery(IATDataset):
     FORMAT = "dvl-gallery/1"
 
     def __init__(self, image_embeddings: torch.Tensor, iat_labels: np.ndarray, iat_type: str = "gender",
-                 index_base: int = 0, n_global: Optional[int] = None, n_classes: Optional[int] = None):
+                 index_base: int = 0, n_global: Optional[int] = None, n_classes: Optional[int] = None,
+                 tag: Optional[str] = None):
         super().__init__()
+        self.tag = tag
         assert len(image_embeddings) == len(iat_labels)
         self.image_embeddings = image_embeddings
         self.iat_labels = np.asarray(iat_labels)
@@ -170,7 +172,7 @@ class EmbeddingGallery(IATDataset):
         np.save(os.path.join(path, "embeddings.npy"), arr)
         np.save(os.path.join(path, "labels.npy"), lab.astype(np.uint8))
         meta = {"format": self.FORMAT, "n": int(arr.shape[0]), "d": int(arr.shape[1]), "dtype": dtype,
-                "iat_type": self.iat_type, "n_classes": int(self.n_iat_classes)}
+                "iat_type": self.iat_type, "n_classes": int(self.n_iat_classes), "tag": self.tag}
         with open(os.path.join(path, "meta.json"), "w") as f:      # written last: its presence marks a complete cache
             json.dump(meta, f)
         return path
@@ -180,15 +182,22 @@ class EmbeddingGallery(IATDataset):
         return os.path.isfile(os.path.join(path, "meta.json"))
 
     @classmethod
-    def load(cls, path: str, rank: int = 0, world: int = 1, device: Optional[Union[str, torch.device]] = None
-             ) -> "EmbeddingGallery":
-        """Rows ``shard_bounds(N, world, rank)`` of the cached gallery, optionally moved to ``device``."""
+    def load(cls, path: str, rank: int = 0, world: int = 1, device: Optional[Union[str, torch.device]] = None,
+             expect_iat_type: Optional[str] = None, expect_tag: Optional[str] = None) -> "EmbeddingGallery":
+        """Rows ``shard_bounds(N, world, rank)`` of the cached gallery, optionally moved to ``device``.
+        ``expect_iat_type`` / ``expect_tag``: what the caller is about to measure; a cache written for a
+        different attribute or model tag raises ``ValueError`` instead of being silently reused."""
         import json
         from .sharded import shard_bounds
         with open(os.path.join(path, "meta.json")) as f:
             meta = json.load(f)
         if meta.get("format") != cls.FORMAT:
             raise ValueError(f"{path}: not a {cls.FORMAT} gallery cache")
+        if expect_iat_type is not None and meta.get("iat_type") != expect_iat_type:
+            raise ValueError(f"{path}: cache holds labels of attribute {meta.get('iat_type')!r}, "
+                             f"not {expect_iat_type!r}; delete it or point use_cache elsewhere")
+        if expect_tag is not None and meta.get("tag") != expect_tag:
+            raise ValueError(f"{path}: cache was written for model tag {meta.get('tag')!r}, not {expect_tag!r}")
         n = int(meta["n"])
         lo, hi = shard_bounds(n, world, rank)
         arr = np.load(os.path.join(path, "embeddings.npy"), mmap_mode="r")
@@ -202,5 +211,8 @@ class EmbeddingGallery(IATDataset):
             emb = torch.from_numpy(block)
         if device is not None:
             emb = emb.to(device)
-        return cls(emb, np.array(lab[lo:hi]).astype(np.int64), meta.get("iat_type", "gender"),
-                   index_base=lo, n_global=n, n_classes=int(meta["n_classes"]))
+        lab_block = np.array(lab[lo:hi]).astype(np.int64)
+        if lab_block.size and int(lab_block.max()) >= int(meta["n_classes"]):
+            raise ValueError(f"{path}: a label code is >= n_classes ({meta['n_classes']})")
+        return cls(emb, lab_block, meta.get("iat_type", "gender"),
+                   index_base=lo, n_global=n, n_classes=int(meta["n_classes"]), tag=meta.get("tag"))

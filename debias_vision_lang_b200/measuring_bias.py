@@ -56,7 +56,11 @@ PROMPT_CONCEPTS = (
 #   batch_size / num_workers   DataLoader settings (reference: 256 / 6)
 #   use_cache          directory of an on-disk gallery cache (datasets.EmbeddingGallery.save/load; the
 #                      reference reserves ``use_cache`` but never implements it, datasets.py:26): read if
-#                      present -- the image encoder is then not run at all -- else written after encoding
+#                      present -- the image encoder is then not run at all -- else written after encoding.
+#                      A cache written for another attribute (or another ``cache_tag``) raises instead of
+#                      being reused.
+#   cache_tag          free-form string identifying the model / checkpoint the cached embeddings came from;
+#                      stored in the cache's meta.json and compared on load
 DEFAULT_OPTS: dict = dict()
 
 _PRECISIONS = {"fp32": _capi.PRECISION_FP32, "bf16": _capi.PRECISION_BF16, "fp32x3": _capi.PRECISION_FP32X3}
@@ -70,13 +74,28 @@ def gen_prompts() -> List[str]:
 # ---------------------------------------------------------------------------------------------
 # label handling (Counter(df.label) / datasets.py:30-46)
 # ---------------------------------------------------------------------------------------------
+def _contiguity_error(n_classes: int) -> IndexError:
+    return IndexError(f"labels must be the contiguous ints 0..{n_classes - 1} for ndkl "
+                      "(the reference indexes top_n_label_counts[label])")
+
+
 def _encode_labels(labels_list, need_contiguous: bool) -> Tuple[np.ndarray, int]:
     """labels -> uint8 codes 0..C-1 over the distinct values present (what Counter sees).
     NDKL in the reference indexes its count array with the raw label (measuring_bias.py:33-34),
-    so labels outside 0..C-1 raise IndexError there; we raise the same."""
+    so labels outside 0..C-1 raise IndexError there; we raise the same.
+
+    Integer labels that already are the contiguous codes 0..C-1 (what ``gen_labels`` produces,
+    datasets.py:30-46) take a linear pass (min / max / bincount); anything else -- strings, gaps, large
+    values -- goes through ``np.unique``."""
     lab = np.asarray(labels_list)
     if lab.ndim != 1:
         lab = lab.reshape(-1)
+    if lab.dtype.kind in "iub" and lab.size:
+        lo, hi = int(lab.min()), int(lab.max())
+        if lo >= 0 and hi < _capi.MAX_CLASSES:
+            codes = lab if lab.dtype == np.uint8 else lab.astype(np.uint8)
+            if bool((np.bincount(codes, minlength=hi + 1) > 0).all()):
+                return codes, hi + 1
     values, codes = np.unique(lab, return_inverse=True)
     n_classes = len(values)
     if n_classes > _capi.MAX_CLASSES:
@@ -84,9 +103,29 @@ def _encode_labels(labels_list, need_contiguous: bool) -> Tuple[np.ndarray, int]
     if need_contiguous:
         as_int = values.astype(np.int64)
         if not np.array_equal(as_int, np.arange(n_classes)):
-            raise IndexError(f"labels must be the contiguous ints 0..{n_classes - 1} for ndkl "
-                             "(the reference indexes top_n_label_counts[label])")
+            raise _contiguity_error(n_classes)
     return codes.astype(np.uint8), n_classes
+
+
+def _encode_labels_device(labels_list, need_contiguous: bool, dev: torch.device) -> Tuple[torch.Tensor, int]:
+    """The same for a call whose embeddings already live on the device: integer labels are narrowed to
+    uint8 codes and counted by one kernel (``dvl_encode_labels``) -- no host pass over N labels beyond the
+    upload of the array itself, none at all when the labels are a CUDA tensor."""
+    t = None
+    if isinstance(labels_list, torch.Tensor):
+        if labels_list.dtype in (torch.int64, torch.int32, torch.uint8) and labels_list.dim() == 1:
+            t = labels_list
+    else:
+        lab = np.asarray(labels_list)
+        if lab.ndim == 1 and lab.dtype in (np.int64, np.int32, np.uint8) and lab.size:
+            t = torch.from_numpy(np.ascontiguousarray(lab))
+    if t is not None and t.numel():
+        codes, info = _capi.context(dev.index).encode_labels(t.to(dev, non_blocking=True).contiguous())
+        if not info["out_of_range"] and info["contiguous"]:
+            return codes, info["n_classes"]
+    host = labels_list.detach().cpu().numpy() if isinstance(labels_list, torch.Tensor) else labels_list
+    codes, n_classes = _encode_labels(host, need_contiguous)
+    return torch.from_numpy(codes).to(dev), n_classes
 
 
 def _resolve_topn(topn: Union[int, float], n: int) -> int:
@@ -115,9 +154,6 @@ def _as_device_matrix(x, dev: torch.device) -> torch.Tensor:
     return t.detach().to(dev).contiguous()
 
 
-_last = {"key": None, "value": None}
-
-
 def evaluate(labels_list, image_embeddings, prompts_embeddings, topn: Union[int, float] = 1.0,
              opts: Optional[dict] = None, need_contiguous: bool = True, per_query: bool = False,
              ranked_cap: int = 0) -> Dict[str, object]:
@@ -131,13 +167,10 @@ def evaluate(labels_list, image_embeddings, prompts_embeddings, topn: Union[int,
     n = len(image_embeddings)
     top_n = _resolve_topn(topn, n)
     img = image_embeddings if isinstance(image_embeddings, torch.Tensor) else torch.as_tensor(np.asarray(image_embeddings))
+    txt = prompts_embeddings if isinstance(prompts_embeddings, torch.Tensor) else torch.as_tensor(np.asarray(prompts_embeddings))
+    if txt.dim() == 1:
+        txt = txt[None, :]
     dev = _device_of(img)
-    g = _as_device_matrix(img, dev)
-    t = _as_device_matrix(prompts_embeddings, dev)
-    if t.dim() == 1:
-        t = t[None, :]
-    codes, n_classes = _encode_labels(labels_list, need_contiguous)
-    lab = torch.from_numpy(codes).to(dev)
     precision = _PRECISIONS[opts.get("precision", "fp32")]
     flags = 0
     if opts.get("normalize_gallery", False):
@@ -146,9 +179,28 @@ def evaluate(labels_list, image_embeddings, prompts_embeddings, topn: Union[int,
         flags |= _capi.FLAG_NORMALIZE_QUERIES
     if opts.get("full_sort", False):
         flags |= _capi.FLAG_FULL_SORT
+    ctx = _capi.context(dev.index)
+    host_call = (not img.is_cuda and not txt.is_cuda and not ranked_cap and
+                 img.dtype in (torch.float32, torch.float16, torch.bfloat16) and
+                 txt.dtype in (torch.float32, torch.float16, torch.bfloat16))
+    if host_call:
+        # host-resident embeddings (an embedding cache, or encoders that ran elsewhere): one C-ABI call that
+        # uploads the gallery in row blocks and scores them as they land (dvl_eval_ranking_host)
+        codes, n_classes = _encode_labels(labels_list, need_contiguous)
+        pq = np.empty((txt.shape[0], 4), dtype=np.float64) if per_query else None
+        with torch.cuda.device(dev):
+            m = ctx.eval_ranking_host(img.detach().contiguous(), txt.detach().contiguous(), np.ascontiguousarray(codes),
+                                      n_classes, top_n, precision, flags, per_query_out=pq)
+        out = {"maxskew": {"eq_opp": m[0], "dem_par": m[1]}, "ndkl": {"eq_opp": m[2], "dem_par": m[3]}}
+        if per_query:
+            out["per_query"] = torch.from_numpy(pq)
+        return out
+    g = _as_device_matrix(img, dev)
+    t = _as_device_matrix(txt, dev)
     with torch.cuda.device(dev):
-        res = _capi.context(dev.index).eval_ranking(g, t, lab, n_classes, top_n, precision, flags,
-                                                    want_per_query=per_query, ranked_cap=ranked_cap)
+        lab, n_classes = _encode_labels_device(labels_list, need_contiguous, dev)
+        res = ctx.eval_ranking(g, t, lab, n_classes, top_n, precision, flags,
+                               want_per_query=per_query, ranked_cap=ranked_cap)
     m = res["mean"]
     out = {"maxskew": {"eq_opp": m[0], "dem_par": m[1]}, "ndkl": {"eq_opp": m[2], "dem_par": m[3]}}
     if per_query:
@@ -166,30 +218,12 @@ def eval_ranking(labels_list: np.ndarray, image_embeddings: torch.Tensor, prompt
     requested metric for both desired distributions -> ``{"eq_opp": float, "dem_par": float}``.
 
     The reference calls this twice (once per evaluation, :153) and recomputes similarities and
-    rankings each time; here both evaluations come out of one pass, and a second call on the
-    same tensors reuses it."""
+    rankings each time.  This function is stateless as well: every call runs the fused pass (both
+    evaluations come out of it, the requested one is returned).  Callers that want both without paying
+    twice use ``evaluate`` -- as ``measure_bias`` does."""
     assert evaluation in ("maxskew", "ndkl")
-    key = None
-    if isinstance(image_embeddings, torch.Tensor) and isinstance(prompts_embeddings, torch.Tensor):
-        lab_arr = np.asarray(labels_list)
-        key = (image_embeddings.data_ptr(), image_embeddings._version, tuple(image_embeddings.shape),
-               prompts_embeddings.data_ptr(), prompts_embeddings._version, tuple(prompts_embeddings.shape),
-               lab_arr.__array_interface__["data"][0], hash(lab_arr.tobytes()) if lab_arr.size < (1 << 22) else None,
-               repr(topn), repr(sorted((opts or {}).items())))
-    if key is not None and _last["key"] == key:
-        both = _last["value"]
-    else:
-        both = evaluate(labels_list, image_embeddings, prompts_embeddings, topn, opts,
-                        need_contiguous=(evaluation == "ndkl"))
-        if key is not None and evaluation == "maxskew":
-            # only reusable by an ndkl call if the labels would have passed its check as well
-            try:
-                _encode_labels(labels_list, True)
-                _last["key"], _last["value"] = key, both
-            except IndexError:
-                _last["key"] = None
-        elif key is not None:
-            _last["key"], _last["value"] = key, both
+    both = evaluate(labels_list, image_embeddings, prompts_embeddings, topn, opts,
+                    need_contiguous=(evaluation == "ndkl"))
     return dict(both[evaluation])
 
 
@@ -293,14 +327,16 @@ def measure_bias(cliplike, img_preproc: Optional[Callable] = None, tokenizer: Op
     prompts: List[str] = gen_prompts()
     device = torch.device("cuda")          # hard-coded in the reference too (:148)
     cache = opts.get("use_cache")
+    tag = opts.get("cache_tag")
     if cache and EmbeddingGallery.is_cached(cache):
-        cached = EmbeddingGallery.load(cache, device=device)
+        # a cache only serves the request it was written for: same attribute, same caller-supplied model tag
+        cached = EmbeddingGallery.load(cache, device=device, expect_iat_type=attribute, expect_tag=tag)
         labels_list, image_embeddings = cached.iat_labels, cached.image_embeddings
     else:
         labels_list, image_embeddings = get_labels_img_embeddings(dl(), cliplike, device,
                                                                   progress=opts.get("progress", False))
         if cache:
-            EmbeddingGallery(image_embeddings, labels_list, attribute).save(cache)
+            EmbeddingGallery(image_embeddings, labels_list, attribute, tag=tag).save(cache)
     prompts_embeddings = get_prompt_embeddings(cliplike, tokenizer, device, prompts)
     both = evaluate(labels_list, image_embeddings, prompts_embeddings, opts.get("topn", 1.0), opts)
     return {"maxskew": dict(both["maxskew"]), "ndkl": dict(both["ndkl"])}

@@ -32,7 +32,7 @@ import torch
 
 from . import _capi
 
-__all__ = ["shard_bounds", "TorchDistComm", "LocalComm", "evaluate_sharded", "evaluate_query_sharded",
+__all__ = ["shard_bounds", "TorchDistComm", "SoloComm", "LocalComm", "evaluate_sharded", "evaluate_sharded_host", "evaluate_query_sharded",
            "measure_sharded", "speculative_list_len"]
 
 
@@ -72,6 +72,30 @@ class TorchDistComm:
     def all_gather_into(self, out: torch.Tensor, t: torch.Tensor) -> torch.Tensor:
         """Same into a caller-owned contiguous [world, *t.shape] buffer (no allocation on the way)."""
         self.dist.all_gather_into_tensor(out.view(-1), t.view(-1), group=self.group)
+        return out
+
+
+class SoloComm:
+    """world = 1: the gallery-sharded protocol on ONE GPU holding the whole gallery (the N = 1 point of the
+    strong-scaling curve).  The collectives degenerate to views; no process group is needed."""
+    world = 1
+    rank = 0
+
+    @staticmethod
+    def all_reduce_max(t: torch.Tensor) -> torch.Tensor:
+        return t
+
+    @staticmethod
+    def all_reduce_sum(t: torch.Tensor) -> torch.Tensor:
+        return t
+
+    @staticmethod
+    def all_gather(t: torch.Tensor) -> torch.Tensor:
+        return t.contiguous()[None]
+
+    @staticmethod
+    def all_gather_into(out: torch.Tensor, t: torch.Tensor) -> torch.Tensor:
+        out.view(-1).copy_(t.view(-1))
         return out
 
 
@@ -125,9 +149,20 @@ def speculative_list_len(top_n: int, rows_per_shard: int, n_global: int) -> int:
     return int(-(-math.ceil(mu + 6.0 * math.sqrt(mu) + 32.0) // 8) * 8)
 
 
+def evaluate_sharded_host(ctx, comm, gallery_local: torch.Tensor, queries: torch.Tensor, labels_local_u8: torch.Tensor,
+                          index_base: int, n_global: int, n_classes: int, top_n: int, opts: Optional[dict] = None,
+                          ranked_cap: int = 0) -> Dict[str, object]:
+    """``evaluate_sharded`` for a shard that lives in HOST memory (pinned tensors: the embedding cache, or
+    the encoders' host copy): the upload of the gallery rows is overlapped with the local streaming top-k
+    (``dvl_shard_topk_host``); everything after it is the same exchange."""
+    assert not gallery_local.is_cuda and not queries.is_cuda and not labels_local_u8.is_cuda
+    return evaluate_sharded(ctx, comm, gallery_local, queries, labels_local_u8, index_base, n_global, n_classes, top_n,
+                            opts, ranked_cap, host_inputs=True)
+
+
 def evaluate_sharded(ctx, comm, gallery_local: torch.Tensor, queries: torch.Tensor, labels_local_u8: torch.Tensor,
                      index_base: int, n_global: int, n_classes: int, top_n: int, opts: Optional[dict] = None,
-                     ranked_cap: int = 0) -> Dict[str, object]:
+                     ranked_cap: int = 0, host_inputs: bool = False) -> Dict[str, object]:
     """One rank's part of the sharded evaluation.  Returns the same dict on every rank:
     ``{"maxskew": {...}, "ndkl": {...}, "per_query": [Q,4] f64, "ranked_len": [Q] i32, "n_flagged": int}``.
 
@@ -147,7 +182,7 @@ def evaluate_sharded(ctx, comm, gallery_local: torch.Tensor, queries: torch.Tens
     q = queries.shape[0]
     if top_n < 1:
         raise ZeroDivisionError("top_n must be >= 1")
-    dev = queries.device
+    dev = torch.device("cuda", ctx.device) if host_inputs else queries.device
     rows_per_shard = shard_bounds(n_global, world, 0)[1]
     key = (world, q, int(top_n), rows_per_shard, n_global)
     length = _learnt_list_len.get(key) or speculative_list_len(top_n, rows_per_shard, n_global)
@@ -155,8 +190,9 @@ def evaluate_sharded(ctx, comm, gallery_local: torch.Tensor, queries: torch.Tens
     # 1. local streaming top-k (a rank may own no rows when the gallery is tiny)
     have_rows = gallery_local.shape[0] > 0
     if have_rows:
-        tau, oflags, counts, _ = ctx.shard_topk(gallery_local, queries, labels_local_u8, index_base, n_classes,
-                                                top_n, precision, flags)
+        local_topk = ctx.shard_topk_host if host_inputs else ctx.shard_topk
+        tau, oflags, counts, _ = local_topk(gallery_local, queries, labels_local_u8, index_base, n_classes,
+                                            top_n, precision, flags)
     else:
         tau = torch.full((q,), float("-inf"), dtype=torch.float32, device=dev)
         oflags = torch.zeros((q,), dtype=torch.int32, device=dev)
@@ -219,6 +255,8 @@ def evaluate_sharded(ctx, comm, gallery_local: torch.Tensor, queries: torch.Tens
     n_flagged = 0
     # 5. exact re-rank of flagged queries (tie run longer than a candidate list); rare
     if any_flag:
+        if host_inputs:      # rare path: the dense scores of the flagged queries need the shard on the device
+            gallery_local, queries, labels_local_u8 = gallery_local.to(dev), queries.to(dev), labels_local_u8.to(dev)
         flagged = torch.nonzero(flag_mask).reshape(-1)
         n_flagged = int(flagged.numel())
         n_local = gallery_local.shape[0]

@@ -91,6 +91,57 @@ def clip_like(n: int, d: int, q: int, n_classes: int, seed: int = 1234,
     return Workload(f"clip_like_{n}x{d}x{q}_c{n_classes}", gallery, queries, labels, n_classes, 1.0)
 
 
+GEN_CHUNK = 65536          # rows per independently seeded block of a `clip_like_rows` gallery
+
+
+def clip_like_rows(n_total: int, d: int, q: int, n_classes: int, seed: int, lo: int = 0, hi: Optional[int] = None,
+                   device: str = "cpu", dtype: torch.dtype = torch.float32) -> Workload:
+    """Rows [lo, hi) of a `clip_like` gallery of `n_total` rows whose content does not depend on how it is
+    cut: every block of GEN_CHUNK rows (and its labels) has its own seed, the shared directions and the
+    queries come from the header seed.  Rank r of a gallery-sharded run generates only its own row block
+    and gets exactly the rows a single GPU holding the whole gallery would have there -- which is what
+    lets `bench.py` compare the per-query results of an N-GPU run with the one-GPU ones bit for bit.
+    (Same generator family as `clip_like`; bit-identical across runs on the same device type only.)"""
+    hi = n_total if hi is None else hi
+    assert 0 <= lo <= hi <= n_total
+    gen = torch.Generator(device=device)
+    gen.manual_seed(seed)
+
+    def rn(*shape, g=gen):
+        return torch.randn(*shape, generator=g, device=device, dtype=torch.float32)
+
+    mu_img = _unit(rn(d))
+    mu_txt = _unit(0.25 * mu_img + (1 - 0.25 ** 2) ** 0.5 * _unit(rn(d) - (rn(d) @ mu_img) * mu_img))
+    v = _unit(rn(n_classes, d))
+    u = _unit(rn(N_TEMPLATES, d))
+    w = _unit(rn(N_CONCEPTS, d))
+    qi = torch.arange(q, device=device)
+    tmpl = (qi // N_CONCEPTS) % N_TEMPLATES
+    conc = qi % N_CONCEPTS
+    zq = rn(q, d) / d ** 0.5 * 0.3
+    bias = 0.08 * v[conc % n_classes]
+    queries = _unit(1.2 * mu_txt[None, :] + u[tmpl] + 0.3 * w[conc] + bias + zq).to(dtype)
+
+    pri = np.asarray(CLASS_PRIORS.get(n_classes, np.full(n_classes, 1.0 / n_classes)), dtype=np.float64)
+    gallery = torch.empty(hi - lo, d, dtype=dtype, device=device)
+    labels = np.empty(hi - lo, dtype=np.int64)
+    cgen = torch.Generator(device=device)
+    for c in range(lo // GEN_CHUNK, -(-hi // GEN_CHUNK) if hi > lo else 0):
+        c_lo, c_hi = c * GEN_CHUNK, min(n_total, (c + 1) * GEN_CHUNK)
+        rows = c_hi - c_lo
+        lab_c = np.random.RandomState((seed * 1000003 + c) % (2 ** 31)).choice(n_classes, size=rows, p=pri / pri.sum())
+        if c == 0:
+            lab_c[:n_classes] = np.arange(n_classes)          # every class present (datasets.py:43)
+        cgen.manual_seed(seed * 7919 + 104729 * (c + 1))
+        z = rn(rows, d, g=cgen) / d ** 0.5
+        body = _unit(1.2 * mu_img[None, :] + 0.15 * v[torch.from_numpy(lab_c).to(device)] + z)
+        r = 10.0 * torch.exp(0.05 * rn(rows, 1, g=cgen))
+        a, b = max(lo, c_lo), min(hi, c_hi)
+        gallery[a - lo:b - lo] = (r * body)[a - c_lo:b - c_lo].to(dtype)
+        labels[a - lo:b - lo] = lab_c[a - c_lo:b - c_lo]
+    return Workload(f"clip_like_rows_{n_total}x{d}x{q}_c{n_classes}[{lo}:{hi}]", gallery, queries, labels, n_classes, 1.0)
+
+
 def dyadic_grid(n: int, d: int, q: int, n_classes: int, seed: int = 7, lim: int = 127,
                 device: str = "cpu") -> Workload:
     """All components k/64, |k| <= lim <= 127: order-independent exact fp32 dot products

@@ -73,6 +73,9 @@ typedef enum dvl_precision { DVL_PRECISION_FP32 = 0, DVL_PRECISION_BF16 = 1, DVL
 #define DVL_FLAG_NO_PILOT          0x10u /* streaming route: do not take an optimistic first threshold
                                            from a pilot sample (large galleries); use the progressive
                                            chunk-by-chunk scheme only */
+#define DVL_FLAG_RADIX_SORT        0x20u /* full-sort route: rank with the stable LSD radix sort (segsort.cu) instead
+                                           of the score-linear bucket sort (bucketsort.cu) that is tried first;
+                                           same results, used for A/B measurements and tests */
 #define DVL_FLAG_STREAM_TOPK       0x8u /* force the streaming top-k route even on a small gallery
                                            (chunks of N/4 rows); needs top_n < N and top_n <= 8192 */
 
@@ -113,6 +116,20 @@ DVL_API uint64_t dvl_launch_count(const dvl_ctx* ctx);
 DVL_API int dvl_set_profiling(dvl_ctx* ctx, int enabled);
 DVL_API int dvl_get_profile(dvl_ctx* ctx, double* stage_ms, uint64_t* stage_launches);
 
+/* ---- labels (a4 input) ---------------------------------------------------------------------
+ * The reference's labels are an int64 ndarray (datasets.py:44 -> measuring_bias.py:96,99) that every
+ * per-query DataFrame and Counter re-reads (measuring_bias.py:23,56,115).  This turns DEVICE-resident
+ * integer labels into the uint8 class codes the path takes, in one pass, and reports what
+ * Counter(df.label) would see:
+ *   out_info_host [19]  0..15 rows per class; 16 n_classes = largest label + 1; 17 out_of_range (a label
+ *                       < 0 or >= DVL_MAX_CLASSES: codes are not usable, remap on the host);
+ *                       18 contiguous (every class 0..n_classes-1 present -- what NDKL's
+ *                       top_n_label_counts[label] indexing needs, measuring_bias.py:33-34)
+ * Synchronises `stream` (the info is returned on the host). */
+typedef enum dvl_label_dtype { DVL_LABEL_I64 = 0, DVL_LABEL_I32 = 1, DVL_LABEL_U8 = 2 } dvl_label_dtype;
+DVL_API int dvl_encode_labels(dvl_ctx* ctx, const void* labels /* dev [n] */, int label_dtype, int64_t n,
+                              uint8_t* out_codes /* dev [n] */, int64_t* out_info_host /* [19] */, void* stream);
+
 /* ---- the hot path, device-resident inputs ----------------------------------------------
  * Replaces BOTH calls `eval_ranking(labels, image_embeddings, prompts_embeddings, ev, topn)`
  * for ev in ("maxskew", "ndkl") (measuring_bias.py:153-154 -> :102-119) with one pass:
@@ -144,9 +161,10 @@ DVL_API int dvl_eval_ranking(dvl_ctx* ctx,
                      float* out_scores,
                      void* stream);
 
-/* Same computation with HOST inputs: copies gallery, queries and labels to the device
- * (cudaMemcpyAsync on `stream`; pinned buffers make it asynchronous), runs the path and
- * returns the four means.  This is the call bench.py times for its end-to-end number. */
+/* Same computation with HOST inputs: queries and labels are copied first, the gallery follows in row
+ * blocks on the context's copy stream (pinned buffers make it asynchronous) while operand split and
+ * similarity already run on the blocks that have landed; returns the four means.  This is the call
+ * bench.py times for the end-to-end number of the top_n = N workloads. */
 DVL_API int dvl_eval_ranking_host(dvl_ctx* ctx,
                           const void* gallery_host, int gallery_dtype,
                           const void* queries_host, int query_dtype,
@@ -204,6 +222,19 @@ DVL_API int dvl_shard_topk(dvl_ctx* ctx, const void* gallery, int gallery_dtype,
                            float* out_tau /* dev [q] */, uint32_t* out_flags /* dev [q] */,
                            unsigned long long* out_class_counts /* dev [17] */, int32_t* out_list_cap /* host */,
                            void* stream);
+/* dvl_shard_topk with HOST inputs (the shard as the embedding cache or the encoders' host copy holds it):
+ * queries and labels are copied first, the gallery shard follows in row blocks on the context's copy
+ * stream, and the operand split + similarity + threshold filter of a block start as soon as the block
+ * has landed -- the upload (PCIe, the end-to-end bound) runs under the compute.  The device copies stay
+ * valid until the next host-input call on this context; their addresses are returned so that the rare
+ * exact re-rank of a flagged query (dvl_similarity on the shard) needs no second upload. */
+DVL_API int dvl_shard_topk_host(dvl_ctx* ctx, const void* gallery_host, int gallery_dtype, const void* queries_host,
+                                int query_dtype, const uint8_t* labels_host, int64_t n_local, int64_t index_base,
+                                int32_t d, int32_t q, int32_t n_classes, int64_t top_n, int precision, uint32_t flags,
+                                float* out_tau /* dev [q] */, uint32_t* out_flags /* dev [q] */,
+                                unsigned long long* out_class_counts /* dev [17] */, int32_t* out_list_cap /* host */,
+                                const void** out_gallery_dev, const void** out_queries_dev,
+                                const uint8_t** out_labels_dev, void* stream);
 DVL_API int dvl_shard_trim(dvl_ctx* ctx, const float* tau_bound /* dev [q] */, int32_t q, int32_t* out_cnt /* dev [q] */,
                            void* stream);
 DVL_API int dvl_shard_pack(dvl_ctx* ctx, const int32_t* cnt /* dev [q] */, int32_t q, int64_t len,

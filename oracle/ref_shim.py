@@ -1,8 +1,12 @@
-"""Import shim for the *unmodified* reference.  TEST INFRASTRUCTURE ONLY; build-container only.
+"""Import shim for the *unmodified* reference.  TEST / BASELINE INFRASTRUCTURE ONLY.
 
-``/root/reference`` exists only in the build container (never on the GPU box), so this
-module is used by ``oracle/make_golden.py`` to generate ``tests/golden/*.json`` and by the
+``/root/reference`` exists only in the build container (never on the GPU box).  There this module
+is used by ``oracle/make_golden.py`` to generate ``tests/golden/*.json`` and by the
 ``needs_reference`` CPU tests that cross-check ``oracle/spec.py`` against the live reference.
+On the GPU box the same unmodified package is found under ``baseline/_ref/`` -- installed there by
+``oracle/stage_reference.py`` (``pip install --no-index --no-deps --target baseline/_ref``, run from
+``__graft_entry__.build()`` in the build container; git-ignored, ships with the gpurun snapshot) --
+and is what ``bench.py --impl reference`` and the ``cpu_baseline`` leg time (``kind: "reference"``).
 
 Why a shim: the package does not import as shipped -- ``debias_clip/__init__.py:26``
 does ``from measuring_bias import measure_bias`` (a top-level import) and
@@ -17,11 +21,34 @@ import os
 import sys
 import types
 
-REFERENCE_ROOT = os.environ.get("DVL_REFERENCE_ROOT", "/root/reference")
+_REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+STAGED_ROOT = os.path.join(_REPO, "baseline", "_ref")
+
+
+def _has_reference(root: str) -> bool:
+    return os.path.isfile(os.path.join(root, "debias_clip", "measuring_bias.py"))
+
+
+def _find_root() -> str:
+    env = os.environ.get("DVL_REFERENCE_ROOT")
+    for root in ([env] if env else []) + ["/root/reference", STAGED_ROOT]:
+        if _has_reference(root):
+            return root
+    return env or "/root/reference"
+
+
+REFERENCE_ROOT = _find_root()
 
 
 def available() -> bool:
-    return os.path.isfile(os.path.join(REFERENCE_ROOT, "debias_clip", "measuring_bias.py"))
+    return _has_reference(REFERENCE_ROOT)
+
+
+def source() -> str:
+    """Where the reference comes from: "mounted" (/root/reference), "staged" (baseline/_ref) or "absent"."""
+    if not available():
+        return "absent"
+    return "staged" if os.path.abspath(REFERENCE_ROOT) == os.path.abspath(STAGED_ROOT) else "mounted"
 
 
 def load():

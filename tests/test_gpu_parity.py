@@ -395,7 +395,8 @@ def test_graph_replay_matches_direct_launches(ctx):
         prof = ctx.get_profile()
     finally:
         ctx.set_profiling(False)
-    assert prof["sort_scatter"][0] > 0 and prof["sort_scatter"][1] == 16 and prof["gemm"][1] == 4
+    # four profiled calls, each: one GEMM, one partition launch of the bucket sort (its "scatter" stage)
+    assert prof["sort_scatter"][0] > 0 and prof["sort_scatter"][1] == 4 and prof["gemm"][1] == 4
 
 
 def test_cta_pair_gemm_variant_passes_the_parity_suite():
