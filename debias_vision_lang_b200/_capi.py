@@ -28,7 +28,8 @@ NUM_STAGES = len(STAGES)
 EXPORTS = (
     "dvl_abi_version", "dvl_create", "dvl_destroy", "dvl_last_error", "dvl_workspace_bytes",
     "dvl_launch_count", "dvl_set_profiling", "dvl_get_profile", "dvl_encode_labels", "dvl_eval_ranking", "dvl_eval_ranking_host", "dvl_rank_and_score", "dvl_similarity",
-    "dvl_shard_topk", "dvl_shard_topk_host", "dvl_shard_trim", "dvl_shard_pack", "dvl_merge_topk", "dvl_mean",
+    "dvl_shard_topk", "dvl_shard_topk_host", "dvl_shard_stats", "dvl_shard_reduce", "dvl_shard_trim_pack",
+    "dvl_shard_finish", "dvl_shard_trim", "dvl_shard_pack", "dvl_merge_topk", "dvl_mean",
 )
 
 _STATUS = {-1: "DVL_ERR_INVALID", -2: "DVL_ERR_NO_DEVICE", -3: "DVL_ERR_CUDA", -4: "DVL_ERR_OOM",
@@ -81,6 +82,10 @@ def lib() -> ctypes.CDLL:
     L.dvl_shard_topk_host.argtypes = [c_void_p, c_void_p, c_int, c_void_p, c_int, c_void_p, c_i64, c_i64, c_i32, c_i32,
                                       c_i32, c_i64, c_int, c_u32, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                       c_void_p, c_void_p, c_void_p]
+    L.dvl_shard_stats.argtypes = [c_void_p, c_void_p, c_i32, c_void_p]
+    L.dvl_shard_reduce.argtypes = [c_void_p, c_void_p, c_i32, c_i32, c_void_p]
+    L.dvl_shard_trim_pack.argtypes = [c_void_p, c_i32, c_i64, c_void_p, c_void_p, c_void_p]
+    L.dvl_shard_finish.argtypes = [c_void_p, c_void_p, c_i32, c_i32, c_i64, c_i32, c_void_p, c_void_p, c_void_p]
     L.dvl_shard_trim.argtypes = [c_void_p, c_void_p, c_i32, c_void_p, c_void_p]
     L.dvl_shard_pack.argtypes = [c_void_p, c_void_p, c_i32, c_i64, c_void_p, c_void_p]
     L.dvl_merge_topk.argtypes = [c_void_p, c_void_p, c_i32, c_i32, c_i64, c_i32, c_i32, c_i64, c_void_p, c_i32, c_i64,
@@ -326,6 +331,51 @@ class Context:
                                        ctypes.c_void_p(self._stream()))
         self._check(rc)
         return tau, oflags, counts, int(cap.value)
+
+    # the lean exchange (caller-owned persistent buffers, no allocation, one host synchronisation)
+    def shard_stats(self, out_stats: torch.Tensor):
+        """This rank's statistics record [tau | flags | label counts] as 2q + 34 int32 words."""
+        q = (out_stats.numel() - 2 * (MAX_CLASSES + 1)) // 2
+        assert out_stats.is_cuda and out_stats.dtype == torch.int32 and out_stats.is_contiguous()
+        self._check(lib().dvl_shard_stats(self._h, self._ptr(out_stats), q, ctypes.c_void_p(self._stream())))
+
+    def shard_reduce(self, stats_all: torch.Tensor, q: int):
+        """[world, 2q + 34] gathered records -> tau bound / flags / global label counts kept in the context."""
+        assert stats_all.is_cuda and stats_all.dtype == torch.int32 and stats_all.is_contiguous()
+        self._check(lib().dvl_shard_reduce(self._h, self._ptr(stats_all), stats_all.shape[0], int(q),
+                                           ctypes.c_void_p(self._stream())))
+
+    def shard_trim_pack(self, out_packed: torch.Tensor, out_need: torch.Tensor):
+        """Local lists cut at the global bound, packed into out_packed [q, len]; out_need [1] i32 = longest."""
+        q, length = out_packed.shape
+        assert out_packed.is_contiguous() and out_packed.dtype == torch.int64 and out_need.dtype == torch.int32
+        self._check(lib().dvl_shard_trim_pack(self._h, q, length, self._ptr(out_packed), self._ptr(out_need),
+                                              ctypes.c_void_p(self._stream())))
+
+    def merge_topk_into(self, gathered: torch.Tensor, q0: int, qn: int, n_global: int, n_classes: int, top_n: int,
+                        per_query: torch.Tensor, ranked_len: torch.Tensor, flags: torch.Tensor,
+                        ranked_idx: Optional[torch.Tensor] = None):
+        """``merge_topk`` writing into caller-owned buffers, against the label counts ``shard_reduce`` summed."""
+        world, q_total, length = gathered.shape
+        assert gathered.is_contiguous() and gathered.dtype == torch.int64
+        assert per_query.dtype == torch.float64 and ranked_len.dtype == torch.int32 and flags.dtype == torch.int32
+        cap = ranked_idx.shape[1] if ranked_idx is not None else 0
+        rc = lib().dvl_merge_topk(self._h, self._ptr(gathered), world, q_total, length, int(q0), int(qn), int(n_global),
+                                  None, int(n_classes), int(top_n), self._ptr(per_query), self._ptr(ranked_len),
+                                  self._ptr(ranked_idx), int(cap), self._ptr(flags), ctypes.c_void_p(self._stream()))
+        self._check(rc)
+
+    def shard_finish(self, records_all: torch.Tensor, block: int, q: int):
+        """[world, rec_bytes] gathered result records -> (four means, (any_flag, bad_label, need_max)); the
+        exchange's one host synchronisation."""
+        assert records_all.is_cuda and records_all.dtype == torch.uint8 and records_all.is_contiguous()
+        world, rec_bytes = records_all.shape
+        mean = (ctypes.c_double * 4)()
+        status = (ctypes.c_int64 * 3)()
+        self._check(lib().dvl_shard_finish(self._h, self._ptr(records_all), world, int(block), rec_bytes, int(q),
+                                           ctypes.cast(mean, ctypes.c_void_p), ctypes.cast(status, ctypes.c_void_p),
+                                           ctypes.c_void_p(self._stream())))
+        return [float(x) for x in mean], tuple(int(x) for x in status)
 
     def shard_trim(self, tau_bound: torch.Tensor) -> torch.Tensor:
         q = tau_bound.numel()

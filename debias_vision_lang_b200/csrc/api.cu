@@ -835,7 +835,8 @@ DVL_API int dvl_destroy(dvl_ctx* c) {
                          &c->h_gallery, &c->h_queries, &c->h_labels, &c->cand, &c->cand_cnt, &c->cand_tau,
                          &c->cand_flags, &c->topk_labs, &c->topk_avail, &c->fb_queries, &c->fb_per_query, &c->fb_len,
                          &c->fb_idx, &c->merge_sorted, &c->tab_chunks, &c->bk_store, &c->bk_cnt, &c->bk_lut,
-                         &c->bk_plan, &c->sort_flag, &c->label_info};
+                         &c->bk_plan, &c->sort_flag, &c->label_info, &c->shard_tau_bound, &c->shard_flags_any,
+                         &c->shard_counts, &c->shard_out, &c->merge_labs, &c->merge_avail};
   for (dvl::DevBuf* b : bufs)
     if (b->ptr != nullptr) cudaFree(b->ptr);
   if (c->mean_pinned != nullptr) cudaFreeHost(c->mean_pinned);
@@ -1231,12 +1232,76 @@ DVL_API int dvl_shard_pack(dvl_ctx* c, const int32_t* cnt, int32_t q, int64_t le
   return dvl::launch_pack_lists(c, (const unsigned long long*)c->cand.ptr, c->shard_plan_cap, cnt, q, len, out, st);
 }
 
+DVL_API int dvl_shard_stats(dvl_ctx* c, int32_t* out_stats, int32_t q, void* stream) {
+  if (c == nullptr) return DVL_ERR_INVALID;
+  if (q != c->shard_q || c->shard_plan_cap <= 0) return dvl::set_error(c, DVL_ERR_INVALID, "dvl_shard_topk has not run");
+  if (out_stats == nullptr) return dvl::set_error(c, DVL_ERR_INVALID, "null pointer");
+  dvl::DeviceGuard guard(c->device);
+  cudaStream_t st = (cudaStream_t)stream;
+  dvl::StageScope scope(c, DVL_STAGE_SELECT, st);
+  return dvl::launch_pack_stats(c, (const float*)c->cand_tau.ptr, (const uint32_t*)c->cand_flags.ptr,
+                                (const unsigned long long*)c->class_counts.ptr, q, (uint32_t*)out_stats, st);
+}
+
+DVL_API int dvl_shard_reduce(dvl_ctx* c, const int32_t* stats_all, int32_t world, int32_t q, void* stream) {
+  if (c == nullptr) return DVL_ERR_INVALID;
+  if (stats_all == nullptr || world < 1 || q < 1) return dvl::set_error(c, DVL_ERR_INVALID, "bad arguments");
+  dvl::DeviceGuard guard(c->device);
+  cudaStream_t st = (cudaStream_t)stream;
+  DVL_TRY(dvl::ensure(c, c->shard_tau_bound, (size_t)q * 4));
+  DVL_TRY(dvl::ensure(c, c->shard_flags_any, (size_t)q * 4));
+  DVL_TRY(dvl::ensure(c, c->shard_counts, sizeof(unsigned long long) * (dvl::kMaxClasses + 1)));
+  c->shard_reduced_q = q;
+  dvl::StageScope scope(c, DVL_STAGE_SELECT, st);
+  return dvl::launch_reduce_stats(c, (const uint32_t*)stats_all, world, q, (float*)c->shard_tau_bound.ptr,
+                                  (uint32_t*)c->shard_flags_any.ptr, (unsigned long long*)c->shard_counts.ptr, st);
+}
+
+DVL_API int dvl_shard_trim_pack(dvl_ctx* c, int32_t q, int64_t len, unsigned long long* out, int32_t* out_need,
+                                void* stream) {
+  if (c == nullptr) return DVL_ERR_INVALID;
+  if (q != c->shard_q || c->shard_plan_cap <= 0) return dvl::set_error(c, DVL_ERR_INVALID, "dvl_shard_topk has not run");
+  if (q != c->shard_reduced_q) return dvl::set_error(c, DVL_ERR_INVALID, "dvl_shard_reduce has not run");
+  if (len < 1 || out == nullptr || out_need == nullptr) return dvl::set_error(c, DVL_ERR_INVALID, "bad arguments");
+  dvl::DeviceGuard guard(c->device);
+  cudaStream_t st = (cudaStream_t)stream;
+  dvl::StageScope scope(c, DVL_STAGE_SELECT, st);
+  return dvl::launch_trim_pack(c, (const unsigned long long*)c->cand.ptr, c->shard_plan_cap,
+                               (const int32_t*)c->topk_avail.ptr, (const float*)c->shard_tau_bound.ptr, q, len, out,
+                               out_need, st);
+}
+
+DVL_API int dvl_shard_finish(dvl_ctx* c, const void* records_all, int32_t world, int32_t block, int64_t rec_bytes,
+                             int32_t q, double* out_mean4, int64_t* out_status3, void* stream) {
+  if (c == nullptr) return DVL_ERR_INVALID;
+  if (records_all == nullptr || world < 1 || block < 1 || q < 1 || q > world * block || rec_bytes < (int64_t)block * 40 + 4 ||
+      rec_bytes % 8 != 0 || out_mean4 == nullptr || out_status3 == nullptr)
+    return dvl::set_error(c, DVL_ERR_INVALID, "bad arguments");
+  if (q != c->shard_reduced_q) return dvl::set_error(c, DVL_ERR_INVALID, "dvl_shard_reduce has not run");
+  dvl::DeviceGuard guard(c->device);
+  cudaStream_t st = (cudaStream_t)stream;
+  DVL_TRY(dvl::ensure(c, c->shard_out, 8 * sizeof(double)));
+  {
+    dvl::StageScope scope(c, DVL_STAGE_METRICS, st);
+    DVL_TRY(dvl::launch_shard_finish(c, (const uint8_t*)records_all, world, block, rec_bytes, q,
+                                     (const uint32_t*)c->shard_flags_any.ptr,
+                                     (const unsigned long long*)c->shard_counts.ptr, (double*)c->shard_out.ptr, st));
+  }
+  DVL_CUDA(c, cudaMemcpyAsync(c->mean_pinned, c->shard_out.ptr, 7 * sizeof(double), cudaMemcpyDeviceToHost, st));
+  DVL_CUDA(c, cudaStreamSynchronize(st));
+  memcpy(out_mean4, c->mean_pinned, 4 * sizeof(double));
+  for (int i = 0; i < 3; ++i) out_status3[i] = (int64_t)c->mean_pinned[4 + i];
+  return DVL_OK;
+}
+
 DVL_API int dvl_merge_topk(dvl_ctx* c, const unsigned long long* gathered, int32_t world, int32_t q_total, int64_t len,
                    int32_t q0, int32_t qn, int64_t n_global, const unsigned long long* class_counts_global,
                    int32_t n_classes, int64_t top_n, double* out_per_query, int32_t* out_ranked_len,
                    int32_t* out_ranked_idx, int64_t ranked_cap, uint32_t* out_flags, void* stream) {
   if (c == nullptr) return DVL_ERR_INVALID;
-  if (gathered == nullptr || class_counts_global == nullptr || out_per_query == nullptr || out_ranked_len == nullptr ||
+  if (class_counts_global == nullptr && c->shard_counts.ptr == nullptr)
+    return dvl::set_error(c, DVL_ERR_INVALID, "no global label counts: pass them or run dvl_shard_reduce first");
+  if (gathered == nullptr || out_per_query == nullptr || out_ranked_len == nullptr ||
       out_flags == nullptr || world < 1 || qn < 1 || q0 < 0 || q0 + qn > q_total || len < 1 || top_n < 1)
     return dvl::set_error(c, DVL_ERR_INVALID, "bad merge arguments");
   if (n_classes < 1 || n_classes > DVL_MAX_CLASSES) return dvl::set_error(c, DVL_ERR_INVALID, "n_classes out of range");
@@ -1246,11 +1311,13 @@ DVL_API int dvl_merge_topk(dvl_ctx* c, const unsigned long long* gathered, int32
   while (s < 2 * top_n && s < 16384) s <<= 1;
   const int64_t ldl = dvl::round_up(s, 256);
   DVL_TRY(dvl::ensure(c, c->merge_sorted, (size_t)qn * s * 8));
-  DVL_TRY(dvl::ensure(c, c->topk_labs, (size_t)qn * ldl));
-  DVL_TRY(dvl::ensure(c, c->topk_avail, (size_t)qn * 4));
-  DVL_TRY(dvl::ensure(c, c->class_counts, sizeof(unsigned long long) * (dvl::kMaxClasses + 1)));
-  DVL_CUDA(c, cudaMemcpyAsync(c->class_counts.ptr, class_counts_global, sizeof(unsigned long long) * dvl::kMaxClasses,
-                              cudaMemcpyDeviceToDevice, st));
+  // the merge's own ranked labels / lengths: the local lists' (topk_labs / topk_avail) must survive it -- a
+  // too-short speculative list length is repaired by trimming and packing the local lists a second time
+  DVL_TRY(dvl::ensure(c, c->merge_labs, (size_t)qn * ldl));
+  DVL_TRY(dvl::ensure(c, c->merge_avail, (size_t)qn * 4));
+  // NULL: the counts dvl_shard_reduce summed over the ranks (no copy, and this rank's own counts stay intact)
+  const unsigned long long* counts_global =
+      class_counts_global != nullptr ? class_counts_global : (const unsigned long long*)c->shard_counts.ptr;
   DVL_CUDA(c, cudaMemsetAsync(out_flags, 0, (size_t)qn * 4, st));
   {
     dvl::StageScope scope(c, DVL_STAGE_PREP, st);
@@ -1271,11 +1338,11 @@ DVL_API int dvl_merge_topk(dvl_ctx* c, const unsigned long long* gathered, int32
   sel.trigger = 0;
   sel.final_pass = true;
   sel.sorted_out = (unsigned long long*)c->merge_sorted.ptr;
-  sel.labs = (uint8_t*)c->topk_labs.ptr;
+  sel.labs = (uint8_t*)c->merge_labs.ptr;
   sel.ldl = ldl;
   sel.idx_out = out_ranked_idx;
   sel.idx_cap = ranked_cap;
-  sel.avail = (int32_t*)c->topk_avail.ptr;
+  sel.avail = (int32_t*)c->merge_avail.ptr;
   sel.q_offset = 0;
   sel.q_count = qn;
   {
@@ -1284,7 +1351,7 @@ DVL_API int dvl_merge_topk(dvl_ctx* c, const unsigned long long* gathered, int32
   }
   dvl::MetricArgs m;
   m.keys = nullptr;
-  m.labs = (const uint8_t*)c->topk_labs.ptr;
+  m.labs = (const uint8_t*)c->merge_labs.ptr;
   m.ldk = 0;
   m.ldl = ldl;
   m.n_avail = s;
@@ -1292,8 +1359,8 @@ DVL_API int dvl_merge_topk(dvl_ctx* c, const unsigned long long* gathered, int32
   m.top_n = top_n;
   m.q = qn;
   m.n_classes = n_classes;
-  m.class_counts = (const unsigned long long*)c->class_counts.ptr;
-  m.avail = (const int32_t*)c->topk_avail.ptr;
+  m.class_counts = counts_global;
+  m.avail = (const int32_t*)c->merge_avail.ptr;
   m.per_query = out_per_query;
   m.ranked_len = out_ranked_len;
   {

@@ -64,28 +64,47 @@ __device__ __forceinline__ int cell_of(uint32_t key, float smax, float scale) {
 }
 
 // ---------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) bucket_plan_kernel(const uint32_t* __restrict__ keys, int64_t ldk, int64_t n,
-                                                          int n_buckets, int n_samples, SegPlan* __restrict__ plans,
-                                                          uint8_t* __restrict__ luts, uint32_t* __restrict__ bucket_cnt) {
+constexpr int kPlanThreads = 1024;
+
+__global__ void __launch_bounds__(kPlanThreads) bucket_plan_kernel(const uint32_t* __restrict__ keys, int64_t ldk,
+                                                                   int64_t n, int n_buckets, int n_samples,
+                                                                   SegPlan* __restrict__ plans, uint8_t* __restrict__ luts,
+                                                                   uint32_t* __restrict__ bucket_cnt) {
   __shared__ uint32_t hist[kCells];
-  __shared__ float red_min[8], red_max[8];
-  __shared__ uint32_t warp_tot[8];
+  __shared__ float red_min[32], red_max[32];
+  __shared__ uint32_t warp_tot[32];
+  __shared__ uint32_t sh_valid;
   const int q = blockIdx.x;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const uint32_t* seg = keys + (int64_t)q * ldk;
-  for (int i = tid; i < kCells; i += 256) hist[i] = 0u;
-  for (int i = tid; i < n_buckets; i += 256) bucket_cnt[(int64_t)q * kMaxBuckets + i] = 0u;
-  // every (n / n_samples)-th key; the sample is read twice (range, then histogram) -- it is L2/L1 resident
+  if (tid == 0) sh_valid = 0u;
+#pragma unroll
+  for (int i = 0; i < kCells / kPlanThreads; ++i) hist[i * kPlanThreads + tid] = 0u;
+  if (tid < n_buckets) bucket_cnt[(int64_t)q * kMaxBuckets + tid] = 0u;
+  // The sample: groups of 8 consecutive keys (one 32-byte sector) spread evenly over the segment, read twice
+  // (range, then histogram; the second read hits L2).  Single keys at a stride below 32 would touch every
+  // 128-byte line of the segment -- the whole key matrix from DRAM, twice (measured: 271 MB for config 2).
+  // Four independent loads in flight per thread.
   const int64_t step = n / n_samples > 0 ? n / n_samples : 1;
-  const int samples = (int)((n + step - 1) / step);
+  const int64_t gstep = 8 * step;
+  const int samples = (int)((n + gstep - 1) / gstep) * 8;
+  auto sample_pos = [&](int i) { return (int64_t)(i >> 3) * gstep + (i & 7); };
   float lo = __int_as_float(0x7f800000), hi = __int_as_float(0xff800000);
-  for (int i = tid; i < samples; i += 256) {
-    const uint32_t k = __ldg(seg + (int64_t)i * step);
-    if (k == kNanKey) continue;
-    const float s = key_to_score(k);
-    if (fabsf(s) <= 3.4028234664e38f) {      // finite scores define the range
-      lo = fminf(lo, s);
-      hi = fmaxf(hi, s);
+  for (int i0 = tid; i0 < samples; i0 += 4 * kPlanThreads) {
+    uint32_t k[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int i = i0 + u * kPlanThreads;
+      const int64_t pos = sample_pos(i);
+      k[u] = (i < samples && pos < n) ? __ldg(seg + pos) : kNanKey;
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const float s = key_to_score(k[u]);
+      if (k[u] != kNanKey && fabsf(s) <= 3.4028234664e38f) {      // finite scores define the range
+        lo = fminf(lo, s);
+        hi = fmaxf(hi, s);
+      }
     }
   }
 #pragma unroll
@@ -95,12 +114,12 @@ __global__ void __launch_bounds__(256) bucket_plan_kernel(const uint32_t* __rest
   }
   if (lane == 0) { red_min[warp] = lo; red_max[warp] = hi; }
   __syncthreads();
-  lo = red_min[0];
-  hi = red_max[0];
+  lo = red_min[lane];
+  hi = red_max[lane];
 #pragma unroll
-  for (int w = 1; w < 8; ++w) {
-    lo = fminf(lo, red_min[w]);
-    hi = fmaxf(hi, red_max[w]);
+  for (int off = 16; off > 0; off >>= 1) {
+    lo = fminf(lo, __shfl_xor_sync(0xffffffffu, lo, off));
+    hi = fmaxf(hi, __shfl_xor_sync(0xffffffffu, hi, off));
   }
   float scale = 0.0f;                         // no finite sample, or all equal: one cell, one bucket
   if (hi > lo) {
@@ -108,16 +127,31 @@ __global__ void __launch_bounds__(256) bucket_plan_kernel(const uint32_t* __rest
     if (!(fabsf(scale) <= 3.4028234664e38f)) scale = 0.0f;
   }
   if (!(hi >= lo)) hi = 0.0f;
-  for (int i = tid; i < samples; i += 256) atomicAdd(&hist[cell_of(__ldg(seg + (int64_t)i * step), hi, scale)], 1u);
-  __syncthreads();
-  // exclusive prefix over the cells, 16 consecutive cells per thread
-  uint32_t local[16];
-  uint32_t sum = 0;
+  uint32_t n_valid = 0;
+  for (int i0 = tid; i0 < samples; i0 += 4 * kPlanThreads) {
+    uint32_t k[4];
+    bool ok[4];
 #pragma unroll
-  for (int j = 0; j < 16; ++j) {
-    local[j] = hist[tid * 16 + j];
-    sum += local[j];
+    for (int u = 0; u < 4; ++u) {
+      const int i = i0 + u * kPlanThreads;
+      const int64_t pos = sample_pos(i);
+      ok[u] = i < samples && pos < n;
+      k[u] = ok[u] ? __ldg(seg + pos) : 0u;
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+      if (ok[u]) {
+        atomicAdd(&hist[cell_of(k[u], hi, scale)], 1u);
+        ++n_valid;
+      }
   }
+  n_valid = __reduce_add_sync(0xffffffffu, n_valid);
+  if (lane == 0) atomicAdd(&sh_valid, n_valid);
+  __syncthreads();
+  // exclusive prefix over the cells, 4 consecutive cells per thread
+  const uint4 c4 = reinterpret_cast<const uint4*>(hist)[tid];
+  const uint32_t local[4] = {c4.x, c4.y, c4.z, c4.w};
+  const uint32_t sum = c4.x + c4.y + c4.z + c4.w;
   uint32_t incl = sum;
 #pragma unroll
   for (int off = 1; off < 32; off <<= 1) {
@@ -126,20 +160,24 @@ __global__ void __launch_bounds__(256) bucket_plan_kernel(const uint32_t* __rest
   }
   if (lane == 31) warp_tot[warp] = incl;
   __syncthreads();
-  uint32_t run = incl - sum;
-  for (int w = 0; w < warp; ++w) run += warp_tot[w];
-  uint8_t* lut = luts + (int64_t)q * kCells;
-  uint32_t packed[4] = {0u, 0u, 0u, 0u};
-  const float slices = (float)n_buckets / (float)samples;
+  uint32_t wsum = warp_tot[lane];
 #pragma unroll
-  for (int j = 0; j < 16; ++j) {
+  for (int off = 1; off < 32; off <<= 1) {
+    const uint32_t o = __shfl_up_sync(0xffffffffu, wsum, off);
+    if (lane >= off) wsum += o;
+  }
+  uint32_t run = incl - sum + __shfl_sync(0xffffffffu, wsum - warp_tot[lane], warp);
+  uint32_t packed = 0u;
+  const float slices = (float)n_buckets / (float)(sh_valid > 0u ? sh_valid : 1u);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
     // bucket of a cell = the equal-mass slice its first sample falls into (monotone in the prefix count)
     uint32_t b = (uint32_t)((float)run * slices);
     if (b > (uint32_t)(n_buckets - 1)) b = (uint32_t)(n_buckets - 1);
-    packed[j >> 2] |= b << (8 * (j & 3));
+    packed |= b << (8 * j);
     run += local[j];
   }
-  reinterpret_cast<uint4*>(lut)[tid] = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+  reinterpret_cast<uint32_t*>(luts + (int64_t)q * kCells)[tid] = packed;
   if (tid == 0) {
     plans[q].smax = hi;
     plans[q].scale = scale;
@@ -147,17 +185,27 @@ __global__ void __launch_bounds__(256) bucket_plan_kernel(const uint32_t* __rest
 }
 
 // ---------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kPartThreads, 4)
-bucket_partition_kernel(const uint32_t* __restrict__ keys, int64_t ldk, int64_t n,
-                        const uint8_t* __restrict__ gallery_labels, const SegPlan* __restrict__ plans,
-                        const uint8_t* __restrict__ luts, uint32_t* __restrict__ bucket_cnt, int n_buckets,
-                        unsigned long long* __restrict__ store, uint32_t* __restrict__ nan_cnt,
-                        uint32_t* __restrict__ overflow) {
-  __shared__ __align__(16) uint8_t lut[kCells];
-  __shared__ uint32_t hist[kMaxBuckets];       // entries of this tile per bucket, then their staging offset
-  __shared__ uint32_t gbase[kMaxBuckets];      // where the tile's run starts in the bucket's storage
-  __shared__ unsigned long long stage[kPartTile];
-  __shared__ uint32_t warp_tot[kPartThreads / 32];
+struct PartSmem {          // the partition CTA's shared memory (one copy for both instantiations of the body)
+  uint8_t* lut;            // [kCells] cell -> bucket
+  uint32_t* hist;          // [kMaxBuckets] entries of this tile per bucket, then their staging offset
+  uint32_t* gbase;         // [kMaxBuckets] where the tile's run starts in the bucket's storage
+  unsigned long long* stage;   // [kPartTile] the tile grouped by bucket
+  uint8_t* stage_b;        // [kPartTile] bucket of the staged entry
+  uint32_t* warp_tot;
+};
+
+template <bool kFull>
+__device__ __forceinline__ void
+partition_body(const uint32_t* __restrict__ keys, int64_t ldk, int64_t n, const uint8_t* __restrict__ gallery_labels,
+               const SegPlan* __restrict__ plans, const uint8_t* __restrict__ luts, uint32_t* __restrict__ bucket_cnt,
+               int n_buckets, unsigned long long* __restrict__ store, uint32_t* __restrict__ nan_cnt,
+               uint32_t* __restrict__ overflow, const PartSmem& sm) {
+  uint8_t* lut = sm.lut;
+  uint32_t* hist = sm.hist;
+  uint32_t* gbase = sm.gbase;
+  unsigned long long* stage = sm.stage;
+  uint8_t* stage_b = sm.stage_b;
+  uint32_t* warp_tot = sm.warp_tot;
   const int q = blockIdx.y;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   reinterpret_cast<uint4*>(lut)[tid] = __ldg(reinterpret_cast<const uint4*>(luts + (int64_t)q * kCells) + tid);
@@ -165,7 +213,7 @@ bucket_partition_kernel(const uint32_t* __restrict__ keys, int64_t ldk, int64_t 
   const float smax = plans[q].smax, scale = plans[q].scale;
   const uint32_t* seg = keys + (int64_t)q * ldk;
   const int64_t base = (int64_t)blockIdx.x * kPartTile;
-  const int count = (n - base >= kPartTile) ? kPartTile : (int)(n - base);
+  const int count = kFull ? kPartTile : (int)(n - base);
   // thread owns keys base + r*1024 + tid*4 + {0..3}; ldk and base are multiples of 4 (aligned 16-byte loads;
   // the padding of the last group is read but never used)
   uint32_t key[kPartItems];
@@ -176,9 +224,9 @@ bucket_partition_kernel(const uint32_t* __restrict__ keys, int64_t ldk, int64_t 
     const int p = r * (kPartThreads * 4) + tid * 4;
     uint4 v = make_uint4(0u, 0u, 0u, 0u);
     uint32_t l = 0u;
-    if (p < count) {
+    if (kFull || p < count) {
       v = __ldg(reinterpret_cast<const uint4*>(seg + base + p));
-      if (p + 4 <= count && lab_aligned) {
+      if ((kFull || p + 4 <= count) && lab_aligned) {
         l = __ldg(reinterpret_cast<const uint32_t*>(gallery_labels + base + p));
       } else {
         for (int j = 0; j < 4 && p + j < count; ++j) l |= (uint32_t)gallery_labels[base + p + j] << (8 * j);
@@ -194,7 +242,7 @@ bucket_partition_kernel(const uint32_t* __restrict__ keys, int64_t ldk, int64_t 
   for (int i = 0; i < kPartItems; ++i) {
     const int p = (i >> 2) * (kPartThreads * 4) + tid * 4 + (i & 3);
     slot[i] = 0u;
-    if (p < count) {
+    if (kFull || p < count) {
       const uint32_t b = lut[cell_of(key[i], smax, scale)];
       nans += (key[i] == kNanKey);
       slot[i] = (b << 16) | atomicAdd(&hist[b], 1u);
@@ -216,10 +264,9 @@ bucket_partition_kernel(const uint32_t* __restrict__ keys, int64_t ldk, int64_t 
     if (lane == 31) warp_tot[warp] = incl;
     __syncthreads();
     uint32_t excl = incl - mine;
-    for (int w = 0; w < warp; ++w) excl += warp_tot[w];
-    if (g + mine > (uint32_t)kBucketCap) {
-      if (mine != 0u) atomicOr(overflow, 1u);
-    }
+#pragma unroll
+    for (int w = 0; w < kPartThreads / 32; ++w) excl += (w < warp) ? warp_tot[w] : 0u;
+    if (mine != 0u && g + mine > (uint32_t)kBucketCap) atomicOr(overflow, 1u);
     gbase[tid] = g - excl;                     // storage position = gbase[b] + staging position
     hist[tid] = excl;
   }
@@ -227,21 +274,41 @@ bucket_partition_kernel(const uint32_t* __restrict__ keys, int64_t ldk, int64_t 
 #pragma unroll
   for (int i = 0; i < kPartItems; ++i) {
     const int p = (i >> 2) * (kPartThreads * 4) + tid * 4 + (i & 3);
-    if (p < count) {
+    if (kFull || p < count) {
       const uint32_t b = slot[i] >> 16;
       const uint32_t lab = (lab4[i >> 2] >> (8 * (i & 3))) & 0xFu;
-      stage[hist[b] + (slot[i] & 0xFFFFu)] =
-          ((unsigned long long)key[i] << 32) | ((unsigned long long)(uint32_t)(base + p) << 4) | lab;
+      const uint32_t sp = hist[b] + (slot[i] & 0xFFFFu);
+      stage[sp] = ((unsigned long long)key[i] << 32) | (unsigned long long)(((uint32_t)(base + p) << 4) | lab);
+      stage_b[sp] = (uint8_t)b;
     }
   }
   __syncthreads();
   unsigned long long* out = store + (int64_t)q * n_buckets * kBucketCap;
+#pragma unroll 4
   for (int p = tid; p < count; p += kPartThreads) {
-    const unsigned long long e = stage[p];
-    const uint32_t b = lut[cell_of((uint32_t)(e >> 32), smax, scale)];
+    const uint32_t b = stage_b[p];
     const uint32_t pos = gbase[b] + (uint32_t)p;
-    if (pos < (uint32_t)kBucketCap) out[(int64_t)b * kBucketCap + pos] = e;
+    if (pos < (uint32_t)kBucketCap) out[b * kBucketCap + pos] = stage[p];
   }
+}
+
+__global__ void __launch_bounds__(kPartThreads, 4)
+bucket_partition_kernel(const uint32_t* __restrict__ keys, int64_t ldk, int64_t n,
+                        const uint8_t* __restrict__ gallery_labels, const SegPlan* __restrict__ plans,
+                        const uint8_t* __restrict__ luts, uint32_t* __restrict__ bucket_cnt, int n_buckets,
+                        unsigned long long* __restrict__ store, uint32_t* __restrict__ nan_cnt,
+                        uint32_t* __restrict__ overflow) {
+  __shared__ __align__(16) uint8_t lut[kCells];
+  __shared__ uint32_t hist[kMaxBuckets];
+  __shared__ uint32_t gbase[kMaxBuckets];
+  __shared__ unsigned long long stage[kPartTile];
+  __shared__ uint8_t stage_b[kPartTile];
+  __shared__ uint32_t warp_tot[kPartThreads / 32];
+  const PartSmem sm = {lut, hist, gbase, stage, stage_b, warp_tot};
+  if ((int64_t)(blockIdx.x + 1) * kPartTile <= n)     // all tiles of a segment but (at most) the last
+    partition_body<true>(keys, ldk, n, gallery_labels, plans, luts, bucket_cnt, n_buckets, store, nan_cnt, overflow, sm);
+  else
+    partition_body<false>(keys, ldk, n, gallery_labels, plans, luts, bucket_cnt, n_buckets, store, nan_cnt, overflow, sm);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -254,7 +321,7 @@ struct BucketSortParams {
   uint32_t* keys_out; int64_t ldko;
 };
 
-constexpr size_t kSortSmem = (size_t)kBucketCap * 8 + (size_t)kSubBins * 4;
+constexpr size_t kSortSmem = (size_t)kBucketCap * 8 + (size_t)kSubBins * 4 + kBucketCap;   // list, sub-bins, ranked labels
 constexpr int kBinsPerThread = kSubBins / kSortThreads2;      // 8 consecutive sub-bins per thread
 
 __global__ void __launch_bounds__(kSortThreads2, 4) bucket_sort_kernel(const BucketSortParams p) {
@@ -375,30 +442,32 @@ __global__ void __launch_bounds__(kSortThreads2, 4) bucket_sort_kernel(const Buc
     if (pos < count) list[bins[sub[i] >> 13] + (sub[i] & 0x1FFFu)] = e[i];
   }
   __syncthreads();
+  uint8_t* labs = p.labs_out + (int64_t)q * p.ldl + before;
   if (sh_big == 0u) {
-    // sub-bins holding several entries: insertion sort by the full entry (key, index), by the bins' owner
+    // Entry-parallel: every entry counts the entries of its own sub-bin that rank before it (~1 entry per
+    // sub-bin: the loop is one or two iterations, and every lane works on an entry of its own).  That count
+    // is its final position; the ranked labels are collected in shared memory and written out in order.
+    uint8_t* labs_s = reinterpret_cast<uint8_t*>(bins + kSubBins);                   // [kBucketCap]
 #pragma unroll
-    for (int j = 0; j < kBinsPerThread; ++j) {
-      const uint32_t s0 = start[j], s1 = start[j + 1];
-      if (s1 - s0 == 2u) {
-        const unsigned long long a = list[s0], c = list[s0 + 1];
-        if (a > c) {
-          list[s0] = c;
-          list[s0 + 1] = a;
-        }
-      } else if (s1 - s0 > 2u) {
-        for (uint32_t i = s0 + 1; i < s1; ++i) {
-          const unsigned long long v = list[i];
-          uint32_t k = i;
-          while (k > s0 && list[k - 1] > v) {
-            list[k] = list[k - 1];
-            --k;
-          }
-          list[k] = v;
-        }
+    for (int i = 0; i < kSortItems; ++i) {
+      if (i * kSortThreads2 >= count) break;
+      const int pos = i * kSortThreads2 + tid;
+      if (pos < count) {
+        const uint32_t sb = sub[i] >> 13;
+        const uint32_t s0 = bins[sb];
+        const uint32_t s1 = (sb + 1 < (uint32_t)kSubBins) ? bins[sb + 1] : (uint32_t)count;
+        uint32_t rank = s0;
+        for (uint32_t j = s0; j < s1; ++j) rank += (list[j] < e[i]);
+        labs_s[rank] = (uint8_t)(e[i] & 0xFull);
+        if (p.idx_out != nullptr) p.idx_out[(int64_t)q * p.ldi + before + rank] = (int32_t)((e[i] >> 4) & 0x0FFFFFFFull);
+        if (p.keys_out != nullptr) p.keys_out[(int64_t)q * p.ldko + before + rank] = (uint32_t)(e[i] >> 32);
       }
     }
-  } else {
+    __syncthreads();
+    for (int i = tid; i < count; i += kSortThreads2) labs[i] = labs_s[i];
+    return;
+  }
+  {
     // a sub-bin is crowded (heavy ties inside the bucket): bitonic sort of the whole bucket
     int pow2 = 1;
     while (pow2 < count) pow2 <<= 1;
@@ -420,8 +489,6 @@ __global__ void __launch_bounds__(kSortThreads2, 4) bucket_sort_kernel(const Buc
       }
     }
   }
-  __syncthreads();
-  uint8_t* labs = p.labs_out + (int64_t)q * p.ldl + before;
   for (int i = tid; i < count; i += kSortThreads2) {
     const unsigned long long v = list[i];
     labs[i] = (uint8_t)(v & 0xFull);
@@ -474,7 +541,7 @@ int launch_bucket_sort(Ctx* c, const BucketSortArgs& a, cudaStream_t st) {
     unsigned long long* store = (unsigned long long*)c->bk_store.ptr + (int64_t)q0 * nb * kBucketCap;
     {
       StageScope scope(c, DVL_STAGE_SORT_HIST, st);
-      bucket_plan_kernel<<<(unsigned)qn, 256, 0, st>>>(keys, a.ldk, a.n, nb, n_samples, plans, luts, cnt);
+      bucket_plan_kernel<<<(unsigned)qn, kPlanThreads, 0, st>>>(keys, a.ldk, a.n, nb, n_samples, plans, luts, cnt);
       DVL_LAUNCH_CHECK(c, "bucket_plan_kernel");
     }
     {

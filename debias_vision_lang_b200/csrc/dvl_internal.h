@@ -34,10 +34,12 @@ struct Ctx {
   DevBuf h_gallery, h_queries, h_labels;   // staging for the host-input entry point
   // streaming top-k state
   DevBuf cand, cand_cnt, cand_tau, cand_flags, topk_labs, topk_avail, fb_queries, fb_per_query, fb_len, fb_idx;
-  DevBuf merge_sorted, tab_chunks;
+  DevBuf merge_sorted, merge_labs, merge_avail, tab_chunks;
   // bucket sort (bucketsort.cu): bucket storage, per-bucket counts, cell -> bucket tables, per-query plans,
   // and the device word a bucket overflow raises
   DevBuf bk_store, bk_cnt, bk_lut, bk_plan, sort_flag, label_info;
+  DevBuf shard_tau_bound, shard_flags_any, shard_counts, shard_out;   // reduced over the ranks (dvl_shard_reduce)
+  int shard_reduced_q = 0;
   bool bucket_attr_set = false;
   bool bucket_used = false;                // a ranking of the current call went through the bucket sort
   bool force_lsd = false;                  // retry after an overflow: radix sort only
@@ -232,6 +234,17 @@ int launch_trim_count(Ctx* c, const unsigned long long* sorted, int64_t row_stri
                       const float* tau_bound, int q, int32_t* out_cnt, cudaStream_t st);
 int launch_pack_lists(Ctx* c, const unsigned long long* sorted, int64_t row_stride, const int32_t* cnt, int q,
                       int64_t len, unsigned long long* out, cudaStream_t st);
+
+// gallery-sharded exchange (topk.cu): statistics record of a rank, its reduction over the ranks, trim + pack of
+// the local lists in one kernel, and the final mean / status reduction over the ranks' result records
+int launch_pack_stats(Ctx* c, const float* tau, const uint32_t* flags, const unsigned long long* counts, int q,
+                      uint32_t* out, cudaStream_t st);
+int launch_reduce_stats(Ctx* c, const uint32_t* all, int world, int q, float* tau_bound, uint32_t* flags,
+                        unsigned long long* counts, cudaStream_t st);
+int launch_trim_pack(Ctx* c, const unsigned long long* sorted, int64_t row_stride, const int32_t* avail,
+                     const float* tau_bound, int q, int64_t len, unsigned long long* out, int32_t* need, cudaStream_t st);
+int launch_shard_finish(Ctx* c, const uint8_t* rec_all, int world, int block, int64_t rec_bytes, int q,
+                        const uint32_t* local_flags, const unsigned long long* counts, double* out, cudaStream_t st);
 
 // ---- metrics.cu ------------------------------------------------------------------------
 struct MetricArgs {

@@ -262,6 +262,10 @@ __global__ void __launch_bounds__(kSelThreads) select_kernel(const SelectParams 
   }
 
   // ---- final: sort, emit ----
+  // the exact score of the local top_n-th row: the tightest bound this shard can contribute to the exchange
+  // (the running threshold is only a lower bound of it: a pilot sample's optimistic guess, or the k-th score
+  // before the last chunks arrived)
+  if (tid == 0 && p.tau != nullptr && n > p.k && kth != kNanKey) p.tau[q] = key_to_score(kth);
   uint32_t pow2 = 1;
   while (pow2 < kept) pow2 <<= 1;
   const uint32_t n_sort = pow2 <= 4u * kSelThreads ? 4u * kSelThreads : 8u * kSelThreads;
@@ -354,7 +358,146 @@ __global__ void __launch_bounds__(256) pack_lists_kernel(const unsigned long lon
     out[(int64_t)q * len + i] = (i < n) ? sorted[(int64_t)q * row_stride + i] : ~0ull;
 }
 
+// ---- gallery-sharded exchange: statistics, trim + pack, finish -------------------------------------
+// Per-rank statistics record: [tau f32 x q][overflow flags u32 x q][label counts u64 x 17] = 2q + 34 words.
+__global__ void __launch_bounds__(256) pack_stats_kernel(const float* __restrict__ tau, const uint32_t* __restrict__ flags,
+                                                         const unsigned long long* __restrict__ counts, int q,
+                                                         uint32_t* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < q) {
+    out[i] = __float_as_uint(tau[i]);
+    out[q + i] = flags[i];
+  }
+  if (i < 2 * (kMaxClasses + 1)) out[2 * q + i] = reinterpret_cast<const uint32_t*>(counts)[i];
+}
+
+// all ranks' records -> tau bound (max: no row scoring below it can rank globally), flags (or), counts (sum)
+__global__ void __launch_bounds__(256) reduce_stats_kernel(const uint32_t* __restrict__ all, int world, int q,
+                                                           float* __restrict__ tau_bound, uint32_t* __restrict__ flags,
+                                                           unsigned long long* __restrict__ counts) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t stride = 2 * (int64_t)q + 2 * (kMaxClasses + 1);
+  if (i < q) {
+    float t = __int_as_float(0xff800000);
+    uint32_t f = 0u;
+    for (int w = 0; w < world; ++w) {
+      t = fmaxf(t, __uint_as_float(all[w * stride + i]));
+      f |= all[w * stride + q + i];
+    }
+    tau_bound[i] = t;
+    flags[i] = f;
+  }
+  if (i < kMaxClasses + 1) {
+    unsigned long long sum = 0ull;
+    for (int w = 0; w < world; ++w) sum += reinterpret_cast<const unsigned long long*>(all + w * stride + 2 * q)[i];
+    counts[i] = sum;
+  }
+}
+
+// one CTA per query: entries of the sorted local list that can still rank globally (key <= key(tau bound)),
+// copied to the exchange buffer and padded; the longest such prefix goes to *need
+__global__ void __launch_bounds__(128) trim_pack_kernel(const unsigned long long* __restrict__ sorted, int64_t row_stride,
+                                                        const int32_t* __restrict__ avail,
+                                                        const float* __restrict__ tau_bound, int64_t len,
+                                                        unsigned long long* __restrict__ out, int32_t* __restrict__ need) {
+  __shared__ int sh_cnt;
+  const int q = blockIdx.x;
+  const unsigned long long* e = sorted + (int64_t)q * row_stride;
+  if (threadIdx.x == 0) {
+    const uint32_t bound = score_to_key(tau_bound[q]);
+    int lo = 0, hi = avail[q];
+    while (lo < hi) {
+      const int mid = (lo + hi) >> 1;
+      if ((uint32_t)(e[mid] >> 32) <= bound) lo = mid + 1; else hi = mid;
+    }
+    sh_cnt = lo;
+    if (lo > 0) atomicMax(need, lo);
+  }
+  __syncthreads();
+  const int64_t n = sh_cnt;
+  for (int64_t i = threadIdx.x; i < len; i += blockDim.x) out[(int64_t)q * len + i] = (i < n) ? e[i] : ~0ull;
+}
+
+// Every rank's result record: [per_query f64 x block x 4][ranked_len i32 x block][flags u32 x block][need i32].
+// Mean over the q queries with the reduction tree of mean_kernel (metrics.cu) -- so the numbers are
+// bit-identical to the single-GPU path --, any merge / overflow flag, the longest list any rank needed.
+__global__ void __launch_bounds__(1024) shard_finish_kernel(const uint8_t* __restrict__ rec_all, int world, int block,
+                                                            int64_t rec_bytes, int q,
+                                                            const uint32_t* __restrict__ local_flags,
+                                                            const unsigned long long* __restrict__ counts,
+                                                            double* __restrict__ out) {
+  __shared__ double sh[32][4];
+  __shared__ uint32_t sh_flag;
+  if (threadIdx.x == 0) sh_flag = 0u;
+  __syncthreads();
+  double acc[4] = {0.0, 0.0, 0.0, 0.0};
+  uint32_t flag = 0u;
+  for (int i = threadIdx.x; i < q; i += blockDim.x) {
+    const int seg = i / block, j = i - seg * block;
+    const uint8_t* rec = rec_all + (int64_t)seg * rec_bytes;
+    const double* pq = reinterpret_cast<const double*>(rec) + (int64_t)j * 4;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) acc[k] += pq[k];
+    flag |= reinterpret_cast<const uint32_t*>(rec + (int64_t)block * 36)[j] | local_flags[i];
+  }
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) acc[k] += __shfl_xor_sync(0xffffffffu, acc[k], off);
+  }
+  if ((threadIdx.x & 31) == 0) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) sh[threadIdx.x >> 5][k] = acc[k];
+  }
+  if (flag != 0u) atomicOr(&sh_flag, 1u);
+  __syncthreads();
+  if (threadIdx.x < 4) {
+    double v = 0.0;
+    for (int w = 0; w < 32; ++w) v += sh[w][threadIdx.x];
+    out[threadIdx.x] = v / (double)q;
+  }
+  if (threadIdx.x == 4) {
+    int need = 0;
+    for (int w = 0; w < world; ++w)
+      need = max(need, *reinterpret_cast<const int32_t*>(rec_all + (int64_t)w * rec_bytes + (int64_t)block * 40));
+    out[4] = (double)(sh_flag != 0u);
+    out[5] = (double)(counts[kMaxClasses] != 0ull);
+    out[6] = (double)need;
+  }
+}
+
 }  // namespace
+
+int launch_pack_stats(Ctx* c, const float* tau, const uint32_t* flags, const unsigned long long* counts, int q,
+                      uint32_t* out, cudaStream_t st) {
+  const int items = q > 2 * (kMaxClasses + 1) ? q : 2 * (kMaxClasses + 1);
+  pack_stats_kernel<<<(items + 255) / 256, 256, 0, st>>>(tau, flags, counts, q, out);
+  DVL_LAUNCH_CHECK(c, "pack_stats_kernel");
+  return DVL_OK;
+}
+
+int launch_reduce_stats(Ctx* c, const uint32_t* all, int world, int q, float* tau_bound, uint32_t* flags,
+                        unsigned long long* counts, cudaStream_t st) {
+  const int items = q > kMaxClasses + 1 ? q : kMaxClasses + 1;
+  reduce_stats_kernel<<<(items + 255) / 256, 256, 0, st>>>(all, world, q, tau_bound, flags, counts);
+  DVL_LAUNCH_CHECK(c, "reduce_stats_kernel");
+  return DVL_OK;
+}
+
+int launch_trim_pack(Ctx* c, const unsigned long long* sorted, int64_t row_stride, const int32_t* avail,
+                     const float* tau_bound, int q, int64_t len, unsigned long long* out, int32_t* need, cudaStream_t st) {
+  DVL_CUDA(c, cudaMemsetAsync(need, 0, sizeof(int32_t), st));
+  trim_pack_kernel<<<(unsigned)q, 128, 0, st>>>(sorted, row_stride, avail, tau_bound, len, out, need);
+  DVL_LAUNCH_CHECK(c, "trim_pack_kernel");
+  return DVL_OK;
+}
+
+int launch_shard_finish(Ctx* c, const uint8_t* rec_all, int world, int block, int64_t rec_bytes, int q,
+                        const uint32_t* local_flags, const unsigned long long* counts, double* out, cudaStream_t st) {
+  shard_finish_kernel<<<1, 1024, 0, st>>>(rec_all, world, block, rec_bytes, q, local_flags, counts, out);
+  DVL_LAUNCH_CHECK(c, "shard_finish_kernel");
+  return DVL_OK;
+}
 
 int launch_topk_reset(Ctx* c, uint32_t* cnt, float* tau, uint32_t* flags, int q, uint32_t cnt_value, bool reset_all,
                       cudaStream_t st) {

@@ -160,23 +160,67 @@ def evaluate_sharded_host(ctx, comm, gallery_local: torch.Tensor, queries: torch
                             opts, ranked_cap, host_inputs=True)
 
 
+class _ExchangeBufs:
+    """Persistent device buffers of one (context, Q, world, list length, ranked_cap) exchange: send / receive
+    buffers of the three all-gathers, with typed views into this rank's result record
+    ``[per_query f64 x block x 4][ranked_len i32 x block][flags u32 x block][need i32]`` that the merge
+    kernels write directly.  Nothing is allocated, concatenated or sliced on the device inside a step."""
+
+    def __init__(self, dev, q: int, world: int, length: int, ranked_cap: int):
+        block = -(-q // world)
+        words = 2 * q + 2 * (_capi.MAX_CLASSES + 1)
+        self.block, self.length = block, length
+        self.stats_send = torch.zeros((words,), dtype=torch.int32, device=dev)
+        self.stats_all = torch.zeros((world, words), dtype=torch.int32, device=dev)
+        self.packed = torch.full((q, length), -1, dtype=torch.int64, device=dev)
+        self.gathered = torch.empty((world, q, length), dtype=torch.int64, device=dev)
+        self.rec_bytes = -(-(40 * block + 4) // 16) * 16
+        self.rec_send = torch.zeros((self.rec_bytes,), dtype=torch.uint8, device=dev)
+        self.rec_all = torch.zeros((world, self.rec_bytes), dtype=torch.uint8, device=dev)
+        self.pq = self.rec_send[:32 * block].view(torch.float64).view(block, 4)
+        self.len = self.rec_send[32 * block:36 * block].view(torch.int32)
+        self.flags = self.rec_send[36 * block:40 * block].view(torch.int32)
+        self.need = self.rec_send[40 * block:40 * block + 4].view(torch.int32)
+        self.idx_send = torch.full((block, ranked_cap), -1, dtype=torch.int32, device=dev) if ranked_cap else None
+        self.idx_all = torch.empty((world, block, ranked_cap), dtype=torch.int32, device=dev) if ranked_cap else None
+
+    def column(self, lo: int, hi: int, dtype, q: int):
+        """Bytes [lo, hi) of every rank's record as one [world * block, ...] tensor of `dtype`, first q rows."""
+        return self.rec_all[:, lo:hi].contiguous().view(dtype).reshape(-1)[:q] if dtype != torch.float64 else \
+            self.rec_all[:, lo:hi].contiguous().view(dtype).reshape(-1, 4)[:q]
+
+
+_exchange_bufs: Dict[tuple, _ExchangeBufs] = {}
+
+
+def _bufs_for(ctx, dev, q: int, world: int, length: int, ranked_cap: int) -> _ExchangeBufs:
+    key = (id(ctx), str(dev), q, world, length, ranked_cap)
+    bufs = _exchange_bufs.get(key)
+    if bufs is None:
+        if len(_exchange_bufs) > 16:
+            _exchange_bufs.clear()
+        bufs = _exchange_bufs[key] = _ExchangeBufs(dev, q, world, length, ranked_cap)
+    return bufs
+
+
 def evaluate_sharded(ctx, comm, gallery_local: torch.Tensor, queries: torch.Tensor, labels_local_u8: torch.Tensor,
                      index_base: int, n_global: int, n_classes: int, top_n: int, opts: Optional[dict] = None,
                      ranked_cap: int = 0, host_inputs: bool = False) -> Dict[str, object]:
     """One rank's part of the sharded evaluation.  Returns the same dict on every rank:
     ``{"maxskew": {...}, "ndkl": {...}, "per_query": [Q,4] f64, "ranked_len": [Q] i32, "n_flagged": int}``.
 
-    Three collectives and ONE host synchronisation on the usual path: everything is enqueued behind the
-    local similarity GEMM, so launch and collective set-up latencies hide under it.
+    Three collectives and ONE host synchronisation on the usual path, all enqueued behind the local
+    similarity GEMM, into persistent buffers (no allocation or tensor glue inside a step):
 
-    1. all-gather of the per-shard statistics (thresholds, overflow flags, label histogram -- one packed
-       buffer), reduced locally: tau = max over shards, histogram = sum;
-    2. all-gather of the trimmed candidate lists, packed to a *speculative* common length (the exact
-       one would need a host round trip in the middle of the pipeline);
-    3. all-gather of the per-query results of every rank's query slice, together with the list length
-       each rank really needed.
-    The host then reads the four means and a status word; only if a list was longer than the guess
-    (or a tie run overflowed a list) is there a second, exact round."""
+    1. all-gather of the per-shard statistics record (thresholds, overflow flags, label histogram),
+       reduced by one kernel on every rank: tau = max over shards, histogram = sum;
+    2. all-gather of the candidate lists, cut at tau and packed (one kernel) to a *speculative* common
+       length (the exact one would need a host round trip in the middle of the pipeline);
+    3. all-gather of every rank's result record: the per-query results of its query slice, written there
+       directly by the merge kernels, and the list length it really needed.
+    ``dvl_shard_finish`` then reduces the records to the four means and a status word in one kernel and one
+    device-to-host copy; only if a list was longer than the guess (or a tie run overflowed a list) is there
+    a second, exact round."""
     precision, flags = _flags_and_precision(opts)
     world, rank = comm.world, comm.rank
     q = queries.shape[0]
@@ -186,60 +230,41 @@ def evaluate_sharded(ctx, comm, gallery_local: torch.Tensor, queries: torch.Tens
     rows_per_shard = shard_bounds(n_global, world, 0)[1]
     key = (world, q, int(top_n), rows_per_shard, n_global)
     length = _learnt_list_len.get(key) or speculative_list_len(top_n, rows_per_shard, n_global)
+    q0, qn = _query_slice(q, world, rank)
+    have_rows = gallery_local.shape[0] > 0       # a rank may own no rows when the gallery is tiny
+    bufs = _bufs_for(ctx, dev, q, world, length, ranked_cap)
 
-    # 1. local streaming top-k (a rank may own no rows when the gallery is tiny)
-    have_rows = gallery_local.shape[0] > 0
+    # 1. local streaming top-k -> this rank's statistics record -> reduced over the ranks
     if have_rows:
         local_topk = ctx.shard_topk_host if host_inputs else ctx.shard_topk
-        tau, oflags, counts, _ = local_topk(gallery_local, queries, labels_local_u8, index_base, n_classes,
-                                            top_n, precision, flags)
+        local_topk(gallery_local, queries, labels_local_u8, index_base, n_classes, top_n, precision, flags)
+        ctx.shard_stats(bufs.stats_send)
     else:
-        tau = torch.full((q,), float("-inf"), dtype=torch.float32, device=dev)
-        oflags = torch.zeros((q,), dtype=torch.int32, device=dev)
-        counts = torch.zeros((_capi.MAX_CLASSES + 1,), dtype=torch.int64, device=dev)
-    stats = comm.all_gather(torch.cat([tau.view(torch.int32), oflags.view(torch.int32), counts.view(torch.int32)]))
-    tau = stats[:, :q].view(torch.float32).max(dim=0).values.contiguous()   # no row below it can rank globally
-    oflags = stats[:, q:2 * q].max(dim=0).values
-    counts = stats[:, 2 * q:].contiguous().view(torch.int64).sum(dim=0)
+        bufs.stats_send.zero_()
+        bufs.stats_send[:q] = torch.full((q,), float("-inf"), dtype=torch.float32, device=dev).view(torch.int32)
+    comm.all_gather_into(bufs.stats_all, bufs.stats_send)
+    ctx.shard_reduce(bufs.stats_all, q)
 
-    q0, qn = _query_slice(q, world, rank)
-    block = -(-q // world)
-
-    def exchange_and_merge(length: int):
-        # 2. what can still rank globally, packed to `length` entries per query
+    def exchange_and_merge(bufs: _ExchangeBufs):
+        # 2. what can still rank globally, packed to bufs.length entries per query
         if have_rows:
-            cnt = ctx.shard_trim(tau)
-            need = cnt.max().to(torch.float64)
-            packed = ctx.shard_pack(cnt, length)
+            ctx.shard_trim_pack(bufs.packed, bufs.need)
         else:
-            need = torch.zeros((), dtype=torch.float64, device=dev)
-            packed = torch.full((q, length), -1, dtype=torch.int64, device=dev)
-        gathered = comm.all_gather(packed)                  # [world, Q, length]
-        # 3. merge this rank's slice of the queries; results + the length this rank needed in one buffer
-        results = torch.zeros((block + 1, 6), dtype=torch.float64, device=dev)
-        idx_blk = torch.full((block, ranked_cap), -1, dtype=torch.int32, device=dev) if ranked_cap else None
+            bufs.packed.fill_(-1)
+            bufs.need.zero_()
+        comm.all_gather_into(bufs.gathered, bufs.packed)           # [world, Q, length]
+        # 3. merge this rank's slice of the queries straight into its result record
+        if ranked_cap:
+            bufs.idx_send.fill_(-1)
         if qn > 0:
-            res = ctx.merge_topk(gathered, q0, qn, n_global, counts[:_capi.MAX_CLASSES].contiguous(), n_classes,
-                                 top_n, ranked_cap)
-            results[:qn, :4] = res["per_query"]
-            results[:qn, 4] = res["ranked_len"]
-            results[:qn, 5] = res["flags"]
-            if ranked_cap:
-                idx_blk[:qn] = res["ranked_idx"]
-        results[block, 0] = need
-        everything = comm.all_gather(results)               # [world, block + 1, 6]
-        per_query = everything[:, :block, :4].reshape(-1, 4)[:q].contiguous()
-        ranked_len = everything[:, :block, 4].reshape(-1)[:q].to(torch.int32)
-        merge_flags = everything[:, :block, 5].reshape(-1)[:q]
-        need_max = everything[:, block, 0].max()
-        ranked_idx = comm.all_gather(idx_blk).reshape(-1, ranked_cap)[:q].contiguous() if ranked_cap else None
-        return per_query, ranked_len, merge_flags, need_max, ranked_idx
+            ctx.merge_topk_into(bufs.gathered, q0, qn, n_global, n_classes, top_n, bufs.pq[:qn], bufs.len[:qn],
+                                bufs.flags[:qn], bufs.idx_send[:qn] if ranked_cap else None)
+        comm.all_gather_into(bufs.rec_all, bufs.rec_send)          # [world, rec_bytes]
+        if ranked_cap:
+            comm.all_gather_into(bufs.idx_all, bufs.idx_send)
+        return ctx.shard_finish(bufs.rec_all, bufs.block, q)       # the path's host synchronisation
 
-    per_query, ranked_len, merge_flags, need_max, ranked_idx = exchange_and_merge(length)
-    flag_mask = (oflags != 0) | (merge_flags != 0)
-    status = torch.stack([flag_mask.any().to(torch.float64), counts[_capi.MAX_CLASSES].to(torch.float64), need_max])
-    mean = ctx.mean(per_query)                # the path's host synchronisation
-    any_flag, bad_label, need_max = (int(x) for x in status.tolist())
+    mean, (any_flag, bad_label, need_max) = exchange_and_merge(bufs)
     if bad_label:
         raise _capi.DvlError(-1, f"a label is >= n_classes ({n_classes})")
     if need_max > length:
@@ -247,14 +272,20 @@ def evaluate_sharded(ctx, comm, gallery_local: torch.Tensor, queries: torch.Tens
         # need_max, so every rank takes this branch): exchange again with the exact length and remember it
         length = int(-(-need_max // 8) * 8)
         _learnt_list_len[key] = max(length, _learnt_list_len.get(key, 0))
-        per_query, ranked_len, merge_flags, _, ranked_idx = exchange_and_merge(length)
-        flag_mask = (oflags != 0) | (merge_flags != 0)
-        status = flag_mask.any().to(torch.float64).reshape(1)
-        mean = ctx.mean(per_query)
-        any_flag = int(status.tolist()[0])
+        stats_all = bufs.stats_all
+        bufs = _bufs_for(ctx, dev, q, world, length, ranked_cap)
+        bufs.stats_all.copy_(stats_all)
+        mean, (any_flag, bad_label, need_max) = exchange_and_merge(bufs)
+    block = bufs.block
+    per_query = bufs.column(0, 32 * block, torch.float64, q).clone()
+    ranked_len = bufs.column(32 * block, 36 * block, torch.int32, q).clone()
+    ranked_idx = bufs.idx_all.reshape(-1, ranked_cap)[:q].clone() if ranked_cap else None
     n_flagged = 0
-    # 5. exact re-rank of flagged queries (tie run longer than a candidate list); rare
+    # exact re-rank of flagged queries (tie run longer than a candidate list); rare
     if any_flag:
+        oflags = bufs.stats_all[:, q:2 * q].max(dim=0).values
+        merge_flags = bufs.column(36 * block, 40 * block, torch.int32, q)
+        flag_mask = (oflags != 0) | (merge_flags != 0)
         if host_inputs:      # rare path: the dense scores of the flagged queries need the shard on the device
             gallery_local, queries, labels_local_u8 = gallery_local.to(dev), queries.to(dev), labels_local_u8.to(dev)
         flagged = torch.nonzero(flag_mask).reshape(-1)
@@ -284,7 +315,87 @@ def evaluate_sharded(ctx, comm, gallery_local: torch.Tensor, queries: torch.Tens
 
 
 def evaluate_sharded_emulated(contexts: Sequence, gallery: torch.Tensor, queries: torch.Tensor, labels_u8: torch.Tensor,
-                              n_classes: int, top_n: int, opts: Optional[dict] = None, ranked_cap: int = 0):
+                              n_classes: int, top_n: int, opts: Optional[dict] = None, ranked_cap: int = 0,
+                              lean: bool = True, length: Optional[int] = None):
+    """All `len(contexts)` ranks in ONE process on one GPU, stage by stage (no kernel ever waits on
+    another rank): the same C-ABI stage calls as `evaluate_sharded` (``lean``: the statistics record /
+    reduce / trim+pack / merge-into-record / finish sequence it uses; otherwise the separate
+    trim / pack / merge / mean stages), with the collectives replaced by tensor ops.  Used by the GPU tests."""
+    if not lean:
+        return _evaluate_sharded_emulated_stages(contexts, gallery, queries, labels_u8, n_classes, top_n, opts, ranked_cap)
+    precision, flags = _flags_and_precision(opts)
+    world = len(contexts)
+    n, q = gallery.shape[0], queries.shape[0]
+    dev = queries.device
+    bounds = [shard_bounds(n, world, r) for r in range(world)]
+    shards = [(gallery[lo:hi].contiguous(), labels_u8[lo:hi].contiguous(), lo) for lo, hi in bounds]
+    live = [r for r in range(world) if shards[r][0].shape[0] > 0]
+    if length is None:
+        length = speculative_list_len(top_n, bounds[0][1], n)
+    bufs = [_ExchangeBufs(dev, q, world, length, ranked_cap) for _ in range(world)]
+    for r in range(world):
+        if r in live:
+            g, l, lo = shards[r]
+            contexts[r].shard_topk(g, queries, l, lo, n_classes, top_n, precision, flags)
+            contexts[r].shard_stats(bufs[r].stats_send)
+        else:
+            bufs[r].stats_send[:q] = torch.full((q,), float("-inf"), dtype=torch.float32, device=dev).view(torch.int32)
+    stats_all = torch.stack([b.stats_send for b in bufs]).contiguous()
+    for r in range(world):
+        bufs[r].stats_all.copy_(stats_all)
+        contexts[r].shard_reduce(bufs[r].stats_all, q)
+
+    def exchange(bufs):
+        for r in live:
+            contexts[r].shard_trim_pack(bufs[r].packed, bufs[r].need)
+        gathered = torch.stack([b.packed for b in bufs]).contiguous()
+        for r in range(world):
+            q0, qn = _query_slice(q, world, r)
+            if qn > 0:
+                contexts[r].merge_topk_into(gathered, q0, qn, n, n_classes, top_n, bufs[r].pq[:qn], bufs[r].len[:qn],
+                                            bufs[r].flags[:qn], bufs[r].idx_send[:qn] if ranked_cap else None)
+        rec_all = torch.stack([b.rec_send for b in bufs]).contiguous()
+        bufs[0].rec_all.copy_(rec_all)
+        if ranked_cap:
+            bufs[0].idx_all.copy_(torch.stack([b.idx_send for b in bufs]))
+        return contexts[0].shard_finish(bufs[0].rec_all, bufs[0].block, q)
+
+    mean, (any_flag, bad_label, need_max) = exchange(bufs)
+    if bad_label:
+        raise _capi.DvlError(-1, f"a label is >= n_classes ({n_classes})")
+    if need_max > length:
+        length = int(-(-need_max // 8) * 8)
+        bufs = [_ExchangeBufs(dev, q, world, length, ranked_cap) for _ in range(world)]
+        bufs[0].stats_all.copy_(stats_all)
+        mean, (any_flag, bad_label, need_max) = exchange(bufs)
+    block = bufs[0].block
+    per_query = bufs[0].column(0, 32 * block, torch.float64, q).clone()
+    ranked_len = bufs[0].column(32 * block, 36 * block, torch.int32, q).clone()
+    ranked_idx = bufs[0].idx_all.reshape(-1, ranked_cap)[:q].clone() if ranked_cap else None
+    n_flagged = 0
+    if any_flag:
+        oflags = stats_all[:, q:2 * q].max(dim=0).values
+        flag_mask = (oflags != 0) | (bufs[0].column(36 * block, 40 * block, torch.int32, q) != 0)
+        flagged = torch.nonzero(flag_mask).reshape(-1)
+        n_flagged = int(flagged.numel())
+        fq = queries[flagged].contiguous()
+        parts = [contexts[r].similarity(shards[r][0], fq, precision, flags) for r in live]
+        rr = contexts[0].rank_and_score(torch.cat(parts, dim=1).contiguous(), labels_u8, n_classes, top_n, ranked_cap)
+        per_query[flagged] = rr["per_query"]
+        ranked_len[flagged] = rr["ranked_len"]
+        if ranked_cap:
+            ranked_idx[flagged] = rr["ranked_idx"]
+        mean = contexts[0].mean(per_query)
+    out = {"maxskew": {"eq_opp": mean[0], "dem_par": mean[1]}, "ndkl": {"eq_opp": mean[2], "dem_par": mean[3]},
+           "per_query": per_query, "ranked_len": ranked_len, "n_flagged": n_flagged, "list_len": length}
+    if ranked_cap:
+        out["ranked_idx"] = ranked_idx
+    return out
+
+
+def _evaluate_sharded_emulated_stages(contexts: Sequence, gallery: torch.Tensor, queries: torch.Tensor,
+                                      labels_u8: torch.Tensor, n_classes: int, top_n: int, opts: Optional[dict] = None,
+                                      ranked_cap: int = 0):
     """All `len(contexts)` ranks in ONE process on one GPU, stage by stage (no kernel ever waits on
     another rank): the same C-ABI stage calls as `evaluate_sharded`, with the collectives replaced
     by tensor ops.  Used by the GPU tests."""

@@ -239,9 +239,33 @@ DVL_API int dvl_shard_trim(dvl_ctx* ctx, const float* tau_bound /* dev [q] */, i
                            void* stream);
 DVL_API int dvl_shard_pack(dvl_ctx* ctx, const int32_t* cnt /* dev [q] */, int32_t q, int64_t len,
                            unsigned long long* out /* dev [q][len] */, void* stream);
+/* The same exchange with fewer launches and no host-side glue (what sharded.evaluate_sharded uses):
+ *   dvl_shard_stats      this rank's statistics record after dvl_shard_topk: [tau f32 x q][flags u32 x q]
+ *                        [label counts u64 x 17] = 2q + 34 32-bit words, written into the send buffer;
+ *      all-gather the records;
+ *   dvl_shard_reduce     all records -> tau bound (max), flags (or), label counts (sum), kept in the context
+ *                        (also on a rank that owns no rows);
+ *   dvl_shard_trim_pack  dvl_shard_trim + dvl_shard_pack in one kernel against that bound; *out_need (device)
+ *                        = the longest list prefix that can still rank, so a too-short `len` is detected;
+ *      all-gather the packed lists;  dvl_merge_topk with class_counts_global = NULL (the reduced counts),
+ *      writing straight into this rank's result record
+ *          [per_query f64 x block x 4][ranked_len i32 x block][flags u32 x block][need i32], rec_bytes % 8 == 0;
+ *      all-gather the records;
+ *   dvl_shard_finish     mean over the q queries of all records (the reduction tree of dvl_mean: bit-identical
+ *                        to the single-GPU path) -> out_mean4, and out_status3 = {any query flagged for the exact
+ *                        re-rank, a label >= n_classes seen, longest list any rank needed}; ONE host
+ *                        synchronisation for the whole exchange. */
+DVL_API int dvl_shard_stats(dvl_ctx* ctx, int32_t* out_stats /* dev [2q+34] */, int32_t q, void* stream);
+DVL_API int dvl_shard_reduce(dvl_ctx* ctx, const int32_t* stats_all /* dev [world][2q+34] */, int32_t world, int32_t q,
+                             void* stream);
+DVL_API int dvl_shard_trim_pack(dvl_ctx* ctx, int32_t q, int64_t len, unsigned long long* out /* dev [q][len] */,
+                                int32_t* out_need /* dev [1] */, void* stream);
+DVL_API int dvl_shard_finish(dvl_ctx* ctx, const void* records_all /* dev [world][rec_bytes] */, int32_t world,
+                             int32_t block, int64_t rec_bytes, int32_t q, double* out_mean4 /* host */,
+                             int64_t* out_status3 /* host */, void* stream);
 DVL_API int dvl_merge_topk(dvl_ctx* ctx, const unsigned long long* gathered /* dev [world][q_total][len] */,
                            int32_t world, int32_t q_total, int64_t len, int32_t q0, int32_t qn, int64_t n_global,
-                           const unsigned long long* class_counts_global /* dev [16] */, int32_t n_classes,
+                           const unsigned long long* class_counts_global /* dev [16], or NULL */, int32_t n_classes,
                            int64_t top_n, double* out_per_query /* dev [qn][4] */, int32_t* out_ranked_len /* dev [qn] */,
                            int32_t* out_ranked_idx /* dev [qn][ranked_cap] or NULL */, int64_t ranked_cap,
                            uint32_t* out_flags /* dev [qn] */, void* stream);

@@ -29,6 +29,8 @@ def _to_i64(v):
 
 
 class FakeCtx:
+    device = 0
+
     def __init__(self, list_cap=64):
         self.list_cap = list_cap
         self.lists = None
@@ -53,7 +55,42 @@ class FakeCtx:
         counts = torch.zeros((MAX_CLASSES + 1,), dtype=torch.int64)
         counts[:n_classes] = torch.from_numpy(np.bincount(lab, minlength=n_classes)[:n_classes].astype(np.int64))
         counts[MAX_CLASSES] = int((lab >= n_classes).any())
+        self._tau, self._oflags, self._counts = tau, oflags, counts
         return tau, oflags, counts, self.list_cap
+
+    # ---- the lean exchange (mirrors _capi.Context) ----
+    def shard_stats(self, out_stats):
+        q = len(self.lists)
+        out_stats[:q] = self._tau.view(torch.int32)
+        out_stats[q:2 * q] = self._oflags
+        out_stats[2 * q:] = self._counts.view(torch.int32)
+
+    def shard_reduce(self, stats_all, q):
+        self._tau_bound = stats_all[:, :q].contiguous().view(torch.float32).max(dim=0).values
+        self._flags_any = stats_all[:, q:2 * q].max(dim=0).values
+        self._counts_global = stats_all[:, 2 * q:].contiguous().view(torch.int64).sum(dim=0)
+
+    def shard_trim_pack(self, out_packed, out_need):
+        cnt = self.shard_trim(self._tau_bound)
+        out_packed.copy_(self.shard_pack(cnt, out_packed.shape[1]))
+        out_need[0] = int(cnt.max())
+
+    def merge_topk_into(self, gathered, q0, qn, n_global, n_classes, top_n, per_query, ranked_len, flags, ranked_idx=None):
+        cap = ranked_idx.shape[1] if ranked_idx is not None else 0
+        res = self.merge_topk(gathered, q0, qn, n_global, self._counts_global[:MAX_CLASSES], n_classes, top_n, cap)
+        per_query.copy_(res["per_query"])
+        ranked_len.copy_(res["ranked_len"])
+        flags.copy_(res["flags"])
+        if cap:
+            ranked_idx.copy_(res["ranked_idx"])
+
+    def shard_finish(self, records_all, block, q):
+        world = records_all.shape[0]
+        pq = records_all[:, :32 * block].contiguous().view(torch.float64).reshape(-1, 4)[:q]
+        mflags = records_all[:, 36 * block:40 * block].contiguous().view(torch.int32).reshape(-1)[:q]
+        need = records_all[:, 40 * block:40 * block + 4].contiguous().view(torch.int32).reshape(-1)
+        any_flag = int(bool((mflags != 0).any()) or bool((self._flags_any != 0).any()))
+        return self.mean(pq), (any_flag, int(self._counts_global[MAX_CLASSES] != 0), int(need.max()))
 
     def shard_trim(self, tau_bound):
         return torch.tensor([sum(1 for s, _ in lst if s >= float(tau_bound[i])) for i, lst in enumerate(self.lists)],

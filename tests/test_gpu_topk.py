@@ -105,12 +105,18 @@ def test_sharded_stages_match_single_gpu(world):
             n = g.shape[0]
             single = ctxs[0].eval_ranking(g, t, lab, w.n_classes, topn, _capi.PRECISION_FP32, _capi.FLAG_FULL_SORT,
                                           want_per_query=True, ranked_cap=n)
-            res = sharded.evaluate_sharded_emulated(ctxs, g, t, lab, w.n_classes, topn, ranked_cap=n)
-            assert torch.equal(res["ranked_len"], single["ranked_len"])
-            assert torch.equal(res["ranked_idx"], single["ranked_idx"])
-            assert torch.equal(res["per_query"], single["per_query"])
-            assert [res["maxskew"]["eq_opp"], res["maxskew"]["dem_par"], res["ndkl"]["eq_opp"],
-                    res["ndkl"]["dem_par"]] == single["mean"]
+            # the exchange evaluate_sharded runs (statistics record, reduce, trim+pack, merge into the result
+            # record, finish) with its speculative list length, with a hopelessly short one (second, exact
+            # round) and with a generous one; and the separate trim / pack / merge / mean stages
+            for mode in (dict(lean=True), dict(lean=True, length=8), dict(lean=True, length=2048), dict(lean=False)):
+                res = sharded.evaluate_sharded_emulated(ctxs, g, t, lab, w.n_classes, topn, ranked_cap=n, **mode)
+                assert torch.equal(res["ranked_len"], single["ranked_len"]), mode
+                assert torch.equal(res["ranked_idx"], single["ranked_idx"]), mode
+                assert torch.equal(res["per_query"], single["per_query"]), mode
+                assert [res["maxskew"]["eq_opp"], res["maxskew"]["dem_par"], res["ndkl"]["eq_opp"],
+                        res["ndkl"]["dem_par"]] == single["mean"], mode
+                if mode.get("length") == 8:
+                    assert res["list_len"] > 8
     finally:
         for c in ctxs:
             c.close()

@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Per-phase device timing of the gallery-sharded protocol (sharded.evaluate_sharded), every rank.
 
-    python -m torch.distributed.run --nproc-per-node N --master-addr 127.0.0.1 tools/shard_trace.py [--workload cfg4shard]
+    python -m torch.distributed.run --nproc-per-node N --master-addr 127.0.0.1 tools/shard_trace.py [--workload cfg4]
 
 Wraps the context's stage calls and the communicator's collectives with CUDA events (no change to the
 product code) and prints, per rank, the milliseconds between consecutive phase ends of one step, averaged
@@ -22,7 +22,8 @@ import torch.distributed as dist  # noqa: E402
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--workload", default="cfg4shard")
+    ap.add_argument("--workload", default="cfg4", choices=["cfg3", "cfg4", "cfg5"])
+    ap.add_argument("--rows", type=int, default=0, help="cut the gallery to this many rows (development)")
     ap.add_argument("--steps", type=int, default=10)
     args = ap.parse_args()
     import bench
@@ -31,17 +32,14 @@ def main():
     torch.cuda.set_device(local)
     dev = f"cuda:{local}"
     dist.init_process_group("nccl", device_id=torch.device(dev))
-    w, precision = bench.make_workload(args.workload, dev, rank)
-    lab = torch.from_numpy(w.labels.astype(np.uint8)).to(dev)
-    n = w.gallery.shape[0]
-    if precision == "bf16":
-        w.gallery, w.queries = w.gallery.bfloat16(), w.queries.bfloat16()
-    if args.workload == "cfg4shard":
-        dist.broadcast(w.queries, src=0)
-        n_global, index_base, g_local, l_local = n * world, n * rank, w.gallery, lab
-    else:
-        lo, hi = sharded.shard_bounds(n, world, rank)
-        n_global, index_base, g_local, l_local = n, lo, w.gallery[lo:hi].contiguous(), lab[lo:hi].contiguous()
+    cfg = bench.config_of(args.workload)
+    precision = cfg["precision"]
+    n_global = args.rows or cfg["n"]
+    lo, hi = sharded.shard_bounds(n_global, world, rank)
+    in_dtype = torch.bfloat16 if precision == "bf16" else torch.float32
+    w = bench.make_sharded_workload(args.workload, dev, lo, hi, n_global, cfg["q"], in_dtype)
+    g_local, index_base = w.gallery, lo
+    l_local = torch.from_numpy(w.labels.astype(np.uint8)).to(dev)
     ctx = _capi.context(local)
     comm = sharded.TorchDistComm()
     marks = []
@@ -57,9 +55,9 @@ def main():
             return out
         setattr(obj, name, inner)
 
-    for name in ("shard_topk", "shard_trim", "shard_pack", "merge_topk", "mean"):
+    for name in ("shard_topk", "shard_stats", "shard_reduce", "shard_trim_pack", "merge_topk_into", "shard_finish"):
         wrap(ctx, name, name)
-    wrap(comm, "all_gather", "all_gather")
+    wrap(comm, "all_gather_into", "all_gather")
     top_n = int(w.topn)
     opts = {"precision": precision}
 
