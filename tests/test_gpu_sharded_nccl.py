@@ -93,31 +93,29 @@ def test_two_rank_nccl_routes_match_the_oracle(tmp_path):
     for case in CASES:
         outs = [torch.load(os.path.join(str(tmp_path), f"{case['name']}.rank{r}.pt")) for r in range(world)]
         w = _workload(case)
-        # similarities: exact on the dyadic adversarial set whatever the summation order; for the bf16 case the
-        # oracle ranks OUR gathered similarities of the bf16-rounded inputs stage-isolated, so the
-        # comparison is of rankings and metrics, and the similarities are checked separately in test_gpu_parity
-        scores = np.stack([spec.similarity_f32(w.gallery, w.queries[i]) for i in range(case["q"])])
+        # similarities: exact on the dyadic adversarial set whatever the summation order.  For the bf16 case the
+        # oracle ranks the CUDA path's OWN similarities of the whole gallery (stage isolation, SURVEY H2: two
+        # rows closer than the rounding of a dot product may legitimately swap between summation orders), so
+        # the comparison of rankings and metrics is exact there as well; the similarities themselves are
+        # checked against fp64 in test_gpu_parity.
+        if case["name"].startswith("clip_like"):
+            from debias_vision_lang_b200 import _capi
+            ctx = _capi.context(0)
+            scores = ctx.similarity(w.gallery.cuda().bfloat16(), w.queries.cuda().bfloat16(),
+                                    _capi.PRECISION_BF16).cpu().numpy()
+        else:
+            scores = np.stack([spec.similarity_f32(w.gallery, w.queries[i]) for i in range(case["q"])])
         per_query, ranked = spec.eval_scores_matrix(scores, w.labels, case["topn"])
-        exact = not case["name"].startswith("clip_like")
         for r in range(world):
             got = outs[r]
             assert torch.equal(got["per_query"], outs[0]["per_query"]), (case["name"], "ranks disagree")
             lens = got["ranked_len"].numpy()
-            if exact:
-                assert np.abs(got["per_query"].numpy() - per_query).max() <= 1e-9, case["name"]
-                for qi in range(case["q"]):
-                    want = ranked[qi]
-                    assert lens[qi] == len(want), (case["name"], qi, lens[qi], len(want))
-                    shown = min(len(want), got["ranked_idx"].shape[1])
-                    assert np.array_equal(got["ranked_idx"][qi, :shown].numpy(), want[:shown]), (case["name"], qi)
-            else:
-                # near-ties of non-dyadic data may legitimately swap between summation orders: the metrics are
-                # compared at the tolerance of BASELINE.json, the ranked sets by overlap
-                assert np.abs(got["per_query"].numpy() - per_query).max() <= 1e-6, case["name"]
-                for qi in range(0, case["q"], 13):
-                    want = set(ranked[qi][:case["topn"]].tolist())
-                    have = set(got["ranked_idx"][qi, :case["topn"]].tolist())
-                    assert len(want & have) >= case["topn"] - 2, (case["name"], qi)
+            assert np.abs(got["per_query"].numpy() - per_query).max() <= 1e-9, case["name"]
+            for qi in range(case["q"]):
+                want = ranked[qi]
+                assert lens[qi] == len(want), (case["name"], qi, lens[qi], len(want))
+                shown = min(len(want), got["ranked_idx"].shape[1])
+                assert np.array_equal(got["ranked_idx"][qi, :shown].numpy(), want[:shown]), (case["name"], qi)
         if case["name"] == "adversarial":
             assert outs[0]["n_flagged"] >= 1          # the all-zero query took the exact re-rank
         if "spec" in case:
