@@ -14,7 +14,7 @@ import numpy as np
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libdvl_b200.so")
+LIB_PATH = os.environ.get("DVL_LIB_PATH") or os.path.join(_HERE, "libdvl_b200.so")   # override: A/B builds only
 
 DVL_OK = 0
 DVL_F32, DVL_BF16, DVL_F16 = 0, 1, 2

@@ -834,7 +834,7 @@ DVL_API int dvl_destroy(dvl_ctx* c) {
                          &c->log_tab, &c->per_query, &c->mean_dev, &c->scores_tmp, &c->seg_len, &c->sub_cnt, &c->partial,
                          &c->h_gallery, &c->h_queries, &c->h_labels, &c->cand, &c->cand_cnt, &c->cand_tau,
                          &c->cand_flags, &c->topk_labs, &c->topk_avail, &c->fb_queries, &c->fb_per_query, &c->fb_len,
-                         &c->fb_idx, &c->merge_sorted, &c->tab_chunks, &c->bk_store, &c->bk_cnt, &c->bk_lut,
+                         &c->fb_idx, &c->merge_sorted, &c->tab_chunks, &c->bk_store, &c->bk_cnt, &c->bk_cells, &c->bk_lut,
                          &c->bk_plan, &c->sort_flag, &c->label_info, &c->shard_tau_bound, &c->shard_flags_any,
                          &c->shard_counts, &c->shard_out, &c->merge_labs, &c->merge_avail};
   for (dvl::DevBuf* b : bufs)

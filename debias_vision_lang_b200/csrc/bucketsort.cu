@@ -30,6 +30,8 @@
 // Data that defeats the balance (massive exact ties: an all-zero query, a tiny score alphabet) overflows
 // a bucket's 4096-entry storage; the kernels then raise a flag that travels to the host with the results,
 // and the caller repeats the ranking with the radix sort of segsort.cu, which has no such limit.
+#include <type_traits>
+
 #include "dvl_common.cuh"
 #include "dvl_internal.h"
 
@@ -46,7 +48,6 @@ constexpr int kPartThreads = 256;
 constexpr int kPartItems = 16;
 constexpr int kPartTile = kPartThreads * kPartItems;     // 4096 keys per partition CTA
 constexpr int kSortThreads2 = 256;
-constexpr int kSortItems = kBucketCap / kSortThreads2;   // 16 entries per thread
 constexpr int kGroupMax = 48;                // sub-bins above this size: the CTA sorts the bucket bitonically
 
 struct SegPlan {      // per query
@@ -69,7 +70,8 @@ constexpr int kPlanThreads = 1024;
 __global__ void __launch_bounds__(kPlanThreads) bucket_plan_kernel(const uint32_t* __restrict__ keys, int64_t ldk,
                                                                    int64_t n, int n_buckets, int n_samples,
                                                                    SegPlan* __restrict__ plans, uint8_t* __restrict__ luts,
-                                                                   uint32_t* __restrict__ bucket_cnt) {
+                                                                   uint32_t* __restrict__ bucket_cnt,
+                                                                   uint32_t* __restrict__ bucket_cells) {
   __shared__ uint32_t hist[kCells];
   __shared__ float red_min[32], red_max[32];
   __shared__ uint32_t warp_tot[32];
@@ -178,6 +180,23 @@ __global__ void __launch_bounds__(kPlanThreads) bucket_plan_kernel(const uint32_
     run += local[j];
   }
   reinterpret_cast<uint32_t*>(luts + (int64_t)q * kCells)[tid] = packed;
+  // first and last cell of every bucket (first | last << 16): the bucket's score range for the second level.
+  // hist[] has been read by everyone (barrier above): its first kPlanThreads words now hold the table
+  hist[tid] = packed;
+  __syncthreads();
+  {
+    const uint32_t prev = tid > 0 ? (hist[tid - 1] >> 24) : 0xFFFFu;
+    const uint32_t next = tid < kPlanThreads - 1 ? (hist[tid + 1] & 0xFFu) : 0xFFFFu;
+    uint16_t* cells16 = reinterpret_cast<uint16_t*>(bucket_cells + (int64_t)q * kMaxBuckets);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const uint32_t b = (packed >> (8 * j)) & 0xFFu;
+      const uint32_t pb = j == 0 ? prev : ((packed >> (8 * (j - 1))) & 0xFFu);
+      const uint32_t nb = j == 3 ? next : ((packed >> (8 * (j + 1))) & 0xFFu);
+      if (b != pb) cells16[2 * b] = (uint16_t)(tid * 4 + j);
+      if (b != nb) cells16[2 * b + 1] = (uint16_t)(tid * 4 + j);
+    }
+  }
   if (tid == 0) {
     plans[q].smax = hi;
     plans[q].scale = scale;
@@ -315,20 +334,44 @@ bucket_partition_kernel(const uint32_t* __restrict__ keys, int64_t ldk, int64_t 
 struct BucketSortParams {
   const unsigned long long* store;
   const uint32_t* bucket_cnt;
+  const SegPlan* plans;
+  const uint32_t* bucket_cells;      // [q][kMaxBuckets] first | last << 16 first-level cell of the bucket
   int n_buckets;
   uint8_t* labs_out; int64_t ldl;
   int32_t* idx_out; int64_t ldi;
   uint32_t* keys_out; int64_t ldko;
 };
 
-constexpr size_t kSortSmem = (size_t)kBucketCap * 8 + (size_t)kSubBins * 4 + kBucketCap;   // list, sub-bins, ranked labels
-constexpr int kBinsPerThread = kSubBins / kSortThreads2;      // 8 consecutive sub-bins per thread
 
+// score of a (non-NaN) key, two instructions
+__device__ __forceinline__ float key_score_fast(uint32_t k) {
+  return __uint_as_float(k ^ (~(uint32_t)((int32_t)k >> 31) & 0x7FFFFFFFu));
+}
+
+// sub-bin of a key inside its bucket: (hi - s) * scale, truncated with saturation (negative and NaN -> 0),
+// capped at the last sub-bin; NaN keys (dropped rows) go last.  Non-decreasing in the key.
+__device__ __forceinline__ uint32_t subbin_of(uint32_t k, float hi, float scale) {
+  const uint32_t sb = min(__float2uint_rz((hi - key_score_fast(k)) * scale), (uint32_t)(kSubBins - 1));
+  return k == kNanKey ? (uint32_t)(kSubBins - 1) : sb;
+}
+
+constexpr int kBinsPerThread = kSubBins / kSortThreads2;      // 8 consecutive sub-bins per thread
+// sub-bin sorted entries as two 32-bit arrays, sub-bins, arrival order (u16), ranked labels
+constexpr size_t kSortSmem = (size_t)kBucketCap * 8 + (size_t)kSubBins * 4 + (size_t)kBucketCap * 2 + kBucketCap;
+
+// The kernel keeps nothing per entry in registers between its phases: every phase is a short strided loop over
+// the bucket that re-reads what it needs (the bucket's entries from L1/L2, the rest from shared memory).  An
+// earlier version held 16 entries per thread in registers across the phases; fully unrolled it executed 2.5x the
+// instructions (register shuffling, spills, one branch region per conditional) and ran no faster for it.
 __global__ void __launch_bounds__(kSortThreads2, 4) bucket_sort_kernel(const BucketSortParams p) {
   extern __shared__ __align__(16) uint8_t smem_dyn[];
-  unsigned long long* list = reinterpret_cast<unsigned long long*>(smem_dyn);        // [kBucketCap]
-  uint32_t* bins = reinterpret_cast<uint32_t*>(smem_dyn + (size_t)kBucketCap * 8);   // [kSubBins]
-  __shared__ float red_min[8], red_max[8];
+  // key | (index << 4 | label): the ranking compares keys and only looks at the index word of an equal key
+  uint32_t* s_key = reinterpret_cast<uint32_t*>(smem_dyn);                           // [kBucketCap]
+  uint32_t* s_val = s_key + kBucketCap;                                              // [kBucketCap]
+  uint32_t* bins = s_val + kBucketCap;                                               // [kSubBins]
+  uint16_t* s_arr = reinterpret_cast<uint16_t*>(bins + kSubBins);                    // [kBucketCap]
+  uint8_t* labs_s = reinterpret_cast<uint8_t*>(s_arr + kBucketCap);                  // [kBucketCap]
+  __shared__ uint32_t red_min[8], red_max[8];
   __shared__ uint32_t warp_tot[8];
   __shared__ uint32_t sh_big;
   const int q = blockIdx.y, b = blockIdx.x;
@@ -340,75 +383,61 @@ __global__ void __launch_bounds__(kSortThreads2, 4) bucket_sort_kernel(const Buc
   // ranks of this bucket's rows start after the rows of the buckets before it
   uint32_t before = 0;
   for (int i = lane; i < b; i += 32) before += cnts[i];
-#pragma unroll
-  for (int off = 16; off > 0; off >>= 1) before += __shfl_xor_sync(0xffffffffu, before, off);
-  // 8 consecutive sub-bins per thread: zeroed, scanned and fixed up by their owner
+  before = __reduce_add_sync(0xffffffffu, before);
+  // 8 consecutive sub-bins per thread: zeroed and scanned by their owner
   reinterpret_cast<uint4*>(bins)[2 * tid] = make_uint4(0u, 0u, 0u, 0u);
   reinterpret_cast<uint4*>(bins)[2 * tid + 1] = make_uint4(0u, 0u, 0u, 0u);
   if (tid == 0) sh_big = 0u;
   const unsigned long long* src = p.store + ((int64_t)q * p.n_buckets + b) * kBucketCap;
-  // entry i of this thread = position i * 256 + tid; a bucket is planned half full, so the upper rounds
-  // are usually empty and skipped by the whole CTA (uniform breaks)
-  unsigned long long e[kSortItems];
-  float lo = __int_as_float(0x7f800000), hi = __int_as_float(0xff800000);
-#pragma unroll
-  for (int i = 0; i < kSortItems; ++i) {
-    if (i * kSortThreads2 >= count) break;
-    const int pos = i * kSortThreads2 + tid;
-    e[i] = ~0ull;
-    if (pos < count) {
-      e[i] = __ldg(src + pos);
-      const uint32_t k = (uint32_t)(e[i] >> 32);
-      const float s = key_to_score(k);
-      if (k != kNanKey && fabsf(s) <= 3.4028234664e38f) {
-        lo = fminf(lo, s);
-        hi = fmaxf(hi, s);
-      }
+
+  // ---- the bucket's score range: from the first-level cells it is made of; the two end buckets (which also
+  // hold whatever lies outside the sampled range, +-inf and NaN rows) and degenerate plans measure it
+  const SegPlan plan = p.plans[q];
+  const uint32_t cw = p.bucket_cells[(int64_t)q * kMaxBuckets + b];
+  const uint32_t c0 = cw & 0xFFFFu, c1 = cw >> 16;
+  float hi = 0.0f, scale = 0.0f;
+  if (c0 == 0u || c1 >= (uint32_t)(kCells - 1) || c1 < c0 || !(plan.scale > 0.0f)) {
+    uint32_t kmin = 0xFFFFFFFFu, kmax = 0u;            // over the keys of real scores (a NaN key is 0xFFFFFFFF)
+#pragma unroll 4
+    for (int pos = tid; pos < count; pos += kSortThreads2) {
+      const uint32_t k = (uint32_t)(__ldg(src + pos) >> 32);
+      kmin = min(kmin, k);
+      kmax = max(kmax, k == kNanKey ? 0u : k);
     }
-  }
+    kmin = __reduce_min_sync(0xffffffffu, kmin);
+    kmax = __reduce_max_sync(0xffffffffu, kmax);
+    if (lane == 0) { red_min[warp] = kmin; red_max[warp] = kmax; }
+    __syncthreads();
 #pragma unroll
-  for (int off = 16; off > 0; off >>= 1) {
-    lo = fminf(lo, __shfl_xor_sync(0xffffffffu, lo, off));
-    hi = fmaxf(hi, __shfl_xor_sync(0xffffffffu, hi, off));
+    for (int w = 0; w < 8; ++w) {
+      kmin = min(kmin, red_min[w]);
+      kmax = max(kmax, red_max[w]);
+    }
+    if (kmax > kmin) {                                 // at least two distinct real scores; +-inf ends clamped
+      hi = fminf(key_score_fast(kmin), 3.4028234664e38f);
+      const float lo = fmaxf(key_score_fast(kmax), -3.4028234664e38f);
+      if (hi > lo) scale = (float)kSubBins / (hi - lo);
+    }
+  } else {
+    hi = plan.smax - (float)c0 / plan.scale;
+    scale = (float)kSubBins * plan.scale / (float)(c1 - c0 + 1u);
   }
-  if (lane == 0) { red_min[warp] = lo; red_max[warp] = hi; }
+  if (!(scale <= 3.4028234664e38f)) scale = 0.0f;
   __syncthreads();
-  lo = red_min[0];
-  hi = red_max[0];
-#pragma unroll
-  for (int w = 1; w < 8; ++w) {
-    lo = fminf(lo, red_min[w]);
-    hi = fmaxf(hi, red_max[w]);
-  }
-  float scale = 0.0f;
-  if (hi > lo) {
-    scale = (float)kSubBins / (hi - lo);
-    if (!(fabsf(scale) <= 3.4028234664e38f)) scale = 0.0f;
-  }
-  if (!(hi >= lo)) hi = 0.0f;
-  // counting sort over the sub-bins: the arrival order inside a sub-bin is arbitrary, fixed up below
-  uint32_t sub[kSortItems];                    // sub-bin << 13 | arrival
-#pragma unroll
-  for (int i = 0; i < kSortItems; ++i) {
-    if (i * kSortThreads2 >= count) break;
-    const int pos = i * kSortThreads2 + tid;
-    if (pos < count) {
-      const uint32_t k = (uint32_t)(e[i] >> 32);
-      int sb = kSubBins - 1;
-      if (k != kNanKey) {
-        const float s = key_to_score(k);
-        sb = (int)fminf(fmaxf((hi - s) * scale, 0.0f), (float)(kSubBins - 1));
-      }
-      sub[i] = ((uint32_t)sb << 13) | atomicAdd(&bins[sb], 1u);
-    }
+
+  // ---- counting sort over the sub-bins: the arrival order inside a sub-bin is arbitrary, resolved by the ranking
+#pragma unroll 2
+  for (int pos = tid; pos < count; pos += kSortThreads2) {
+    const uint32_t k = (uint32_t)(__ldg(src + pos) >> 32);
+    s_arr[pos] = (uint16_t)atomicAdd(&bins[subbin_of(k, hi, scale)], 1u);
   }
   __syncthreads();
-  // exclusive prefix over the sub-bins; the owner keeps its bins' start offsets and sizes in registers
-  uint32_t start[kBinsPerThread + 1];
   {
-    const uint4 c0 = reinterpret_cast<const uint4*>(bins)[2 * tid];
-    const uint4 c1 = reinterpret_cast<const uint4*>(bins)[2 * tid + 1];
-    const uint32_t cnt8[kBinsPerThread] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
+    // exclusive prefix over the sub-bins; written back as start | size << 16 (both <= 4096)
+    const uint4 v0 = reinterpret_cast<const uint4*>(bins)[2 * tid];
+    const uint4 v1 = reinterpret_cast<const uint4*>(bins)[2 * tid + 1];
+    const uint32_t cnt8[kBinsPerThread] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+    uint32_t start[kBinsPerThread];
     uint32_t sum = 0, mx = 0;
 #pragma unroll
     for (int j = 0; j < kBinsPerThread; ++j) {
@@ -429,49 +458,69 @@ __global__ void __launch_bounds__(kSortThreads2, 4) bucket_sort_kernel(const Buc
 #pragma unroll
     for (int w = 0; w < 8; ++w) base += (w < warp) ? warp_tot[w] : 0u;
 #pragma unroll
-    for (int j = 0; j < kBinsPerThread; ++j) start[j] += base;
-    start[kBinsPerThread] = base + sum;
+    for (int j = 0; j < kBinsPerThread; ++j) start[j] = (start[j] + base) | (cnt8[j] << 16);
     reinterpret_cast<uint4*>(bins)[2 * tid] = make_uint4(start[0], start[1], start[2], start[3]);
     reinterpret_cast<uint4*>(bins)[2 * tid + 1] = make_uint4(start[4], start[5], start[6], start[7]);
   }
   __syncthreads();
-#pragma unroll
-  for (int i = 0; i < kSortItems; ++i) {
-    if (i * kSortThreads2 >= count) break;
-    const int pos = i * kSortThreads2 + tid;
-    if (pos < count) list[bins[sub[i] >> 13] + (sub[i] & 0x1FFFu)] = e[i];
+#pragma unroll 2
+  for (int pos = tid; pos < count; pos += kSortThreads2) {
+    const unsigned long long e = __ldg(src + pos);     // second read: L1 / L2
+    const uint32_t k = (uint32_t)(e >> 32);
+    const uint32_t dst = (bins[subbin_of(k, hi, scale)] & 0xFFFFu) + s_arr[pos];
+    s_key[dst] = k;
+    s_val[dst] = (uint32_t)e;
   }
   __syncthreads();
   uint8_t* labs = p.labs_out + (int64_t)q * p.ldl + before;
   if (sh_big == 0u) {
-    // Entry-parallel: every entry counts the entries of its own sub-bin that rank before it (~1 entry per
-    // sub-bin: the loop is one or two iterations, and every lane works on an entry of its own).  That count
-    // is its final position; the ranked labels are collected in shared memory and written out in order.
-    uint8_t* labs_s = reinterpret_cast<uint8_t*>(bins + kSubBins);                   // [kBucketCap]
+    // Entry-parallel ranking over the sub-bin sorted list: every entry counts the entries of its own sub-bin
+    // that rank before it (a sub-bin holds ~1 entry).  The first four candidates are compared without a loop
+    // (indices clamped into the sub-bin, results masked), a lane only loops for a sub-bin of more than four.
+    const bool want_idx = p.idx_out != nullptr, want_keys = p.keys_out != nullptr;
+#pragma unroll 2
+    for (int d = tid; d < count; d += kSortThreads2) {
+      const uint32_t k = s_key[d], v = s_val[d];
+      const uint32_t w = bins[subbin_of(k, hi, scale)];
+      const uint32_t s0 = w & 0xFFFFu, g = w >> 16, last = s0 + g - 1u;
+      uint32_t rank = s0;
 #pragma unroll
-    for (int i = 0; i < kSortItems; ++i) {
-      if (i * kSortThreads2 >= count) break;
-      const int pos = i * kSortThreads2 + tid;
-      if (pos < count) {
-        const uint32_t sb = sub[i] >> 13;
-        const uint32_t s0 = bins[sb];
-        const uint32_t s1 = (sb + 1 < (uint32_t)kSubBins) ? bins[sb + 1] : (uint32_t)count;
-        uint32_t rank = s0;
-        for (uint32_t j = s0; j < s1; ++j) rank += (list[j] < e[i]);
-        labs_s[rank] = (uint8_t)(e[i] & 0xFull);
-        if (p.idx_out != nullptr) p.idx_out[(int64_t)q * p.ldi + before + rank] = (int32_t)((e[i] >> 4) & 0x0FFFFFFFull);
-        if (p.keys_out != nullptr) p.keys_out[(int64_t)q * p.ldko + before + rank] = (uint32_t)(e[i] >> 32);
+      for (uint32_t j = 0; j < 4u; ++j) {
+        const uint32_t at = min(s0 + j, last);
+        const uint32_t kk = s_key[at];
+        bool first = kk < k;
+        if (kk == k) first = s_val[at] < v;            // itself, or an exact tie: the gallery index decides
+        rank += (j < g && first) ? 1u : 0u;
       }
+      for (uint32_t j = 4u; j < g; ++j) {
+        const uint32_t kk = s_key[s0 + j];
+        rank += (kk < k || (kk == k && s_val[s0 + j] < v)) ? 1u : 0u;
+      }
+      labs_s[rank] = (uint8_t)(v & 0xFu);
+      if (want_idx) p.idx_out[(int64_t)q * p.ldi + before + rank] = (int32_t)(v >> 4);
+      if (want_keys) p.keys_out[(int64_t)q * p.ldko + before + rank] = k;
     }
     __syncthreads();
-    for (int i = tid; i < count; i += kSortThreads2) labs[i] = labs_s[i];
+    // ranked labels out: 4 bytes per store where the destination allows it
+    const int head = (int)((4u - (uint32_t)(reinterpret_cast<uintptr_t>(labs) & 3u)) & 3u);
+    for (int i = tid; i < head && i < count; i += kSortThreads2) labs[i] = labs_s[i];
+    const int words = count > head ? (count - head) >> 2 : 0;
+    for (int i = tid; i < words; i += kSortThreads2) {
+      const uint8_t* sp = labs_s + head + 4 * i;
+      reinterpret_cast<uint32_t*>(labs + head)[i] =
+          (uint32_t)sp[0] | ((uint32_t)sp[1] << 8) | ((uint32_t)sp[2] << 16) | ((uint32_t)sp[3] << 24);
+    }
+    for (int i = head + 4 * words + tid; i < count; i += kSortThreads2) labs[i] = labs_s[i];
     return;
   }
   {
-    // a sub-bin is crowded (heavy ties inside the bucket): bitonic sort of the whole bucket
+    // a sub-bin is crowded (heavy ties inside the bucket): bitonic sort of the whole bucket by (key, index word)
     int pow2 = 1;
     while (pow2 < count) pow2 <<= 1;
-    for (int i = count + tid; i < pow2; i += kSortThreads2) list[i] = ~0ull;
+    for (int i = count + tid; i < pow2; i += kSortThreads2) {
+      s_key[i] = 0xFFFFFFFFu;
+      s_val[i] = 0xFFFFFFFFu;
+    }
     __syncthreads();
     for (int size = 2; size <= pow2; size <<= 1) {
       for (int stride = size >> 1; stride > 0; stride >>= 1) {
@@ -479,10 +528,11 @@ __global__ void __launch_bounds__(kSortThreads2, 4) bucket_sort_kernel(const Buc
           const int i = 2 * t - (t & (stride - 1));
           const int j = i + stride;
           const bool up = (i & size) == 0;
-          const unsigned long long a = list[i], c = list[j];
-          if ((a > c) == up) {
-            list[i] = c;
-            list[j] = a;
+          const unsigned long long x = ((unsigned long long)s_key[i] << 32) | s_val[i];
+          const unsigned long long y = ((unsigned long long)s_key[j] << 32) | s_val[j];
+          if ((x > y) == up) {
+            s_key[i] = (uint32_t)(y >> 32); s_val[i] = (uint32_t)y;
+            s_key[j] = (uint32_t)(x >> 32); s_val[j] = (uint32_t)x;
           }
         }
         __syncthreads();
@@ -490,10 +540,10 @@ __global__ void __launch_bounds__(kSortThreads2, 4) bucket_sort_kernel(const Buc
     }
   }
   for (int i = tid; i < count; i += kSortThreads2) {
-    const unsigned long long v = list[i];
-    labs[i] = (uint8_t)(v & 0xFull);
-    if (p.idx_out != nullptr) p.idx_out[(int64_t)q * p.ldi + before + i] = (int32_t)((v >> 4) & 0x0FFFFFFFull);
-    if (p.keys_out != nullptr) p.keys_out[(int64_t)q * p.ldko + before + i] = (uint32_t)(v >> 32);
+    const uint32_t v = s_val[i];
+    labs[i] = (uint8_t)(v & 0xFu);
+    if (p.idx_out != nullptr) p.idx_out[(int64_t)q * p.ldi + before + i] = (int32_t)(v >> 4);
+    if (p.keys_out != nullptr) p.keys_out[(int64_t)q * p.ldko + before + i] = s_key[i];
   }
 }
 
@@ -513,7 +563,7 @@ static int buckets_for(int64_t n) {
 }
 
 size_t bucket_sort_workspace_per_query(int64_t n) {
-  return (size_t)buckets_for(n) * kBucketCap * 8 + kCells + kMaxBuckets * 4 + sizeof(SegPlan);
+  return (size_t)buckets_for(n) * kBucketCap * 8 + kCells + kMaxBuckets * 8 + sizeof(SegPlan);
 }
 
 int launch_bucket_sort(Ctx* c, const BucketSortArgs& a, cudaStream_t st) {
@@ -524,6 +574,7 @@ int launch_bucket_sort(Ctx* c, const BucketSortArgs& a, cudaStream_t st) {
   if (n_samples < 1024) n_samples = 1024;
   DVL_TRY(ensure(c, c->bk_store, (size_t)a.q * nb * kBucketCap * 8));
   DVL_TRY(ensure(c, c->bk_cnt, (size_t)a.q * kMaxBuckets * 4));
+  DVL_TRY(ensure(c, c->bk_cells, (size_t)a.q * kMaxBuckets * 4));
   DVL_TRY(ensure(c, c->bk_lut, (size_t)a.q * kCells));
   DVL_TRY(ensure(c, c->bk_plan, (size_t)a.q * sizeof(SegPlan)));
   if (!c->bucket_attr_set) {
@@ -538,10 +589,11 @@ int launch_bucket_sort(Ctx* c, const BucketSortArgs& a, cudaStream_t st) {
     SegPlan* plans = (SegPlan*)c->bk_plan.ptr + q0;
     uint8_t* luts = (uint8_t*)c->bk_lut.ptr + (int64_t)q0 * kCells;
     uint32_t* cnt = (uint32_t*)c->bk_cnt.ptr + (int64_t)q0 * kMaxBuckets;
+    uint32_t* cells = (uint32_t*)c->bk_cells.ptr + (int64_t)q0 * kMaxBuckets;
     unsigned long long* store = (unsigned long long*)c->bk_store.ptr + (int64_t)q0 * nb * kBucketCap;
     {
       StageScope scope(c, DVL_STAGE_SORT_HIST, st);
-      bucket_plan_kernel<<<(unsigned)qn, kPlanThreads, 0, st>>>(keys, a.ldk, a.n, nb, n_samples, plans, luts, cnt);
+      bucket_plan_kernel<<<(unsigned)qn, kPlanThreads, 0, st>>>(keys, a.ldk, a.n, nb, n_samples, plans, luts, cnt, cells);
       DVL_LAUNCH_CHECK(c, "bucket_plan_kernel");
     }
     {
@@ -556,6 +608,8 @@ int launch_bucket_sort(Ctx* c, const BucketSortArgs& a, cudaStream_t st) {
       BucketSortParams p;
       p.store = store;
       p.bucket_cnt = cnt;
+      p.plans = plans;
+      p.bucket_cells = cells;
       p.n_buckets = nb;
       p.labs_out = a.labs_out + (int64_t)q0 * a.ldl;
       p.ldl = a.ldl;

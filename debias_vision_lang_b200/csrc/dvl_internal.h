@@ -37,7 +37,7 @@ struct Ctx {
   DevBuf merge_sorted, merge_labs, merge_avail, tab_chunks;
   // bucket sort (bucketsort.cu): bucket storage, per-bucket counts, cell -> bucket tables, per-query plans,
   // and the device word a bucket overflow raises
-  DevBuf bk_store, bk_cnt, bk_lut, bk_plan, sort_flag, label_info;
+  DevBuf bk_store, bk_cnt, bk_cells, bk_lut, bk_plan, sort_flag, label_info;
   DevBuf shard_tau_bound, shard_flags_any, shard_counts, shard_out;   // reduced over the ranks (dvl_shard_reduce)
   int shard_reduced_q = 0;
   bool bucket_attr_set = false;

@@ -133,7 +133,7 @@ __global__ void __launch_bounds__(kSelThreads) select_kernel(const SelectParams 
   __shared__ uint32_t sh_prefix, sh_remaining, sh_kept;
   const int q = blockIdx.x + p.q_offset;
   const int tid = threadIdx.x;
-  if (p.flags[q] != 0u) {                              // already handed to the full-sort route
+  if ((p.flags[q] & 1u) != 0u) {                       // already handed to the full-sort route
     if (p.final_pass && tid == 0 && p.avail != nullptr) p.avail[q] = 0;
     return;
   }
@@ -219,6 +219,15 @@ __global__ void __launch_bounds__(kSelThreads) select_kernel(const SelectParams 
     kth = sh_prefix;
   }
 
+  if (p.cnt == nullptr && tid < p.segs) {
+    // Merge of per-shard lists that were packed to a speculative common length: a list without padding may
+    // have been cut short.  The merge is still exact if what was cut cannot rank: the list's last entry must
+    // rank strictly behind the k-th of the union.  Otherwise the query is marked "short" (bit 1) and the
+    // exchange is repeated with the length the shards reported.
+    const unsigned long long last = load_entry(p, q, (int64_t)tid * p.seg_len + p.seg_len - 1);
+    if (last != ~0ull && (uint32_t)(last >> 32) <= kth) atomicOr(&p.flags[q], 2u);
+  }
+
   if (p.pilot_pass) {
     // pilot sample: its k-th best score becomes the (optimistic) threshold of the main pass; the
     // sample's own entries are dropped -- the main pass sees those rows again
@@ -243,7 +252,7 @@ __global__ void __launch_bounds__(kSelThreads) select_kernel(const SelectParams 
   const uint32_t kept = sh_kept;
   if (kept > (uint32_t)p.sort_cap) {
     if (tid == 0) {
-      p.flags[q] = 1u;
+      atomicOr(&p.flags[q], 1u);
       if (p.cnt != nullptr) p.cnt[q] = 0u;
       if (p.tau != nullptr) p.tau[q] = __int_as_float(0x7f800000);   // stop collecting for this query
       if (p.final_pass && p.avail != nullptr) p.avail[q] = 0;
@@ -420,7 +429,8 @@ __global__ void __launch_bounds__(128) trim_pack_kernel(const unsigned long long
 
 // Every rank's result record: [per_query f64 x block x 4][ranked_len i32 x block][flags u32 x block][need i32].
 // Mean over the q queries with the reduction tree of mean_kernel (metrics.cu) -- so the numbers are
-// bit-identical to the single-GPU path --, any merge / overflow flag, the longest list any rank needed.
+// bit-identical to the single-GPU path --, any tie-overflow flag, and -- only if a merge found a list cut
+// short -- the longest list any rank would have sent untruncated.
 __global__ void __launch_bounds__(1024) shard_finish_kernel(const uint8_t* __restrict__ rec_all, int world, int block,
                                                             int64_t rec_bytes, int q,
                                                             const uint32_t* __restrict__ local_flags,
@@ -438,7 +448,8 @@ __global__ void __launch_bounds__(1024) shard_finish_kernel(const uint8_t* __res
     const double* pq = reinterpret_cast<const double*>(rec) + (int64_t)j * 4;
 #pragma unroll
     for (int k = 0; k < 4; ++k) acc[k] += pq[k];
-    flag |= reinterpret_cast<const uint32_t*>(rec + (int64_t)block * 36)[j] | local_flags[i];
+    const uint32_t mf = reinterpret_cast<const uint32_t*>(rec + (int64_t)block * 36)[j];
+    flag |= (mf & 1u) | (local_flags[i] != 0u ? 1u : 0u) | (mf & 2u);   // bit 0: exact re-rank; bit 1: a list was cut short
   }
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
@@ -449,7 +460,7 @@ __global__ void __launch_bounds__(1024) shard_finish_kernel(const uint8_t* __res
 #pragma unroll
     for (int k = 0; k < 4; ++k) sh[threadIdx.x >> 5][k] = acc[k];
   }
-  if (flag != 0u) atomicOr(&sh_flag, 1u);
+  if (flag != 0u) atomicOr(&sh_flag, flag);
   __syncthreads();
   if (threadIdx.x < 4) {
     double v = 0.0;
@@ -460,9 +471,9 @@ __global__ void __launch_bounds__(1024) shard_finish_kernel(const uint8_t* __res
     int need = 0;
     for (int w = 0; w < world; ++w)
       need = max(need, *reinterpret_cast<const int32_t*>(rec_all + (int64_t)w * rec_bytes + (int64_t)block * 40));
-    out[4] = (double)(sh_flag != 0u);
+    out[4] = (double)((sh_flag & 1u) != 0u);
     out[5] = (double)(counts[kMaxClasses] != 0ull);
-    out[6] = (double)need;
+    out[6] = (sh_flag & 2u) != 0u ? (double)need : 0.0;   // the length to repeat the exchange with, if it must be
   }
 }
 

@@ -215,7 +215,10 @@ def evaluate_sharded(ctx, comm, gallery_local: torch.Tensor, queries: torch.Tens
     1. all-gather of the per-shard statistics record (thresholds, overflow flags, label histogram),
        reduced by one kernel on every rank: tau = max over shards, histogram = sum;
     2. all-gather of the candidate lists, cut at tau and packed (one kernel) to a *speculative* common
-       length (the exact one would need a host round trip in the middle of the pipeline);
+       length: the rows of a shard expected among the global top_n plus six sigmas (224 entries instead of
+       ~1000 at top-1000 on 8 GPUs -- the list gather is the one bandwidth-bound collective of the path).
+       The merge verifies the guess per query: a list that was cut must end strictly behind the k-th entry
+       of the union, else the query is marked and the exchange repeated with the untruncated length;
     3. all-gather of every rank's result record: the per-query results of its query slice, written there
        directly by the merge kernels, and the list length it really needed.
     ``dvl_shard_finish`` then reduces the records to the four means and a status word in one kernel and one
@@ -285,7 +288,7 @@ def evaluate_sharded(ctx, comm, gallery_local: torch.Tensor, queries: torch.Tens
     if any_flag:
         oflags = bufs.stats_all[:, q:2 * q].max(dim=0).values
         merge_flags = bufs.column(36 * block, 40 * block, torch.int32, q)
-        flag_mask = (oflags != 0) | (merge_flags != 0)
+        flag_mask = (oflags != 0) | ((merge_flags & 1) != 0)
         if host_inputs:      # rare path: the dense scores of the flagged queries need the shard on the device
             gallery_local, queries, labels_local_u8 = gallery_local.to(dev), queries.to(dev), labels_local_u8.to(dev)
         flagged = torch.nonzero(flag_mask).reshape(-1)
@@ -375,7 +378,7 @@ def evaluate_sharded_emulated(contexts: Sequence, gallery: torch.Tensor, queries
     n_flagged = 0
     if any_flag:
         oflags = stats_all[:, q:2 * q].max(dim=0).values
-        flag_mask = (oflags != 0) | (bufs[0].column(36 * block, 40 * block, torch.int32, q) != 0)
+        flag_mask = (oflags != 0) | ((bufs[0].column(36 * block, 40 * block, torch.int32, q) & 1) != 0)
         flagged = torch.nonzero(flag_mask).reshape(-1)
         n_flagged = int(flagged.numel())
         fq = queries[flagged].contiguous()
@@ -431,7 +434,7 @@ def _evaluate_sharded_emulated_stages(contexts: Sequence, gallery: torch.Tensor,
         merge_flags[q0:q0 + qn] = res["flags"]
         if ranked_cap:
             ranked_idx[q0:q0 + qn] = res["ranked_idx"]
-    flagged = torch.nonzero((oflags != 0) | (merge_flags != 0)).reshape(-1)
+    flagged = torch.nonzero((oflags != 0) | ((merge_flags & 1) != 0)).reshape(-1)   # bit 1 (list cut short) cannot be set: exact lengths
     if flagged.numel():
         fq = queries[flagged].contiguous()
         parts = [contexts[r].similarity(shards[r][0], fq, precision, flags) for r in live]

@@ -211,8 +211,10 @@ DVL_API int dvl_similarity(dvl_ctx* ctx,
  *   4. dvl_merge_topk   for queries [q0, q0+qn): deterministic merge of the world lists (a u64
  *                       entry is key<<32 | global index<<4 | label, so the merge is a sort of
  *                       integers), m_q with boundary ties, MaxSkew + NDKL against the GLOBAL
- *                       label histogram.  out_flags[q] != 0: tie run too long, re-rank that query
- *                       with dvl_similarity + dvl_rank_and_score.
+ *                       label histogram.  out_flags[q] bit 0: tie run too long, re-rank that query
+ *                       with dvl_similarity + dvl_rank_and_score.  Bit 1: a list that arrived without padding
+ *                       (possibly cut to `len`) does not end strictly behind the k-th entry of the union, so
+ *                       rows that could rank may be missing: repeat the exchange with longer lists.
  *      all-gather the per-query results;  5. dvl_mean gives the four means (same reduction
  *      tree as the single-GPU path, so the numbers are bit-identical to it).
  */
