@@ -30,12 +30,12 @@ FAIRFACE_DATA_PATH = DATA_PATH / "fairface"
 PROMPT_DATA_PATH = DATA_PATH / "prompt_templates.csv"   # not read: the prompt array is built in
 
 from .measuring_bias import (  # noqa: E402
-    DEFAULT_OPTS, clip_logits, compute_skew_metrics, eval_ranking, evaluate, gen_prompts, get_labels_img_embeddings,
+    DEFAULT_OPTS, adversary_input, clip_logits, compute_skew_metrics, eval_ranking, evaluate, gen_prompts, get_labels_img_embeddings,
     get_prompt_embeddings, measure_bias, normalized_discounted_KL,
 )
 
 __all__ = [
     "Dotdict", "DATA_PATH", "FAIRFACE_DATA_PATH", "PROMPT_DATA_PATH", "measure_bias", "eval_ranking", "evaluate",
     "compute_skew_metrics", "normalized_discounted_KL", "gen_prompts", "get_labels_img_embeddings",
-    "get_prompt_embeddings", "DEFAULT_OPTS", "clip_logits",
+    "get_prompt_embeddings", "DEFAULT_OPTS", "clip_logits", "adversary_input",
 ]

@@ -287,6 +287,14 @@ int ensure_sort_flag(Ctx* c, cudaStream_t st) {
   return DVL_OK;
 }
 
+bool fuse_metrics_enabled() {
+  static const bool on = [] {
+    const char* e = getenv("DVL_FUSE_METRICS");
+    return !(e != nullptr && e[0] == '0');
+  }();
+  return on;
+}
+
 constexpr int kRetryLsd = 1;      // internal: a bucket of the bucket sort overflowed, rank again with the radix sort
 
 // Full-sort route.  keys [q][ldk] already in c->keys[0] -> stable segmented sort -> metrics.
@@ -310,6 +318,7 @@ int rank_full(Ctx* c, const uint8_t* labels, int64_t n, int64_t n_gallery, int q
   const uint32_t* sorted_keys = nullptr;
   const uint8_t* ranked_labs = nullptr;
   const int32_t* ranked_idx = nullptr;
+  bool fused = false;
   if (bucket) {
     // two-level score-linear bucket sort (bucketsort.cu); a bucket overflow (tie-heavy data) raises
     // c->sort_flag, which finish_wait turns into one retry of the call with the radix sort
@@ -320,7 +329,6 @@ int rank_full(Ctx* c, const uint8_t* labels, int64_t n, int64_t n_gallery, int q
     b.n = n;
     b.q = q;
     b.gallery_labels = labels;
-    b.labs_out = (uint8_t*)c->labs[0].ptr;
     b.ldl = ldk;
     b.idx_out = want_idx ? (int32_t*)c->idxs[0].ptr : nullptr;
     b.ldi = ldk;
@@ -328,6 +336,18 @@ int rank_full(Ctx* c, const uint8_t* labels, int64_t n, int64_t n_gallery, int q
     b.ldko = ldk;
     b.nan_cnt = whole ? (uint32_t*)c->nan_cnt.ptr : nullptr;
     b.overflow = (uint32_t*)c->sort_flag.ptr;
+    // the whole segment is ranked: the NDKL partial sums come out of the sort itself (per bucket, from the ranked
+    // labels while they are in shared memory) and the labels never go to HBM; DVL_FUSE_METRICS=0 keeps the stages apart
+    fused = whole && fuse_metrics_enabled();
+    if (fused) {
+      DVL_TRY(fused_metric_buffers(c, q, bucket_sort_buckets(n), &b.partial, &b.ranked_cls));
+      metric_tables(c, &b.dxl, &b.pwi);
+      b.class_counts = (const unsigned long long*)c->class_counts.ptr;
+      b.n_gallery = n_gallery;
+      b.n_classes = n_classes;
+    } else {
+      b.labs_out = (uint8_t*)c->labs[0].ptr;
+    }
     DVL_TRY(launch_bucket_sort(c, b, st));
     c->bucket_used = true;
     sorted_keys = b.keys_out;
@@ -369,7 +389,8 @@ int rank_full(Ctx* c, const uint8_t* labels, int64_t n, int64_t n_gallery, int q
   m.ranked_len = ranked_len;
   {
     StageScope scope(c, DVL_STAGE_METRICS, st);
-    DVL_TRY(launch_metrics(c, m, st));
+    if (fused) DVL_TRY(launch_metrics_fused(c, m, bucket_sort_buckets(n), st));
+    else DVL_TRY(launch_metrics(c, m, st));
   }
   if (want_idx) {
     StageScope scope(c, DVL_STAGE_COPY, st);
@@ -432,7 +453,7 @@ struct StreamPlan {
   int64_t pilot_rank;  // rank of the pilot sample's entry that becomes the threshold
 };
 
-// Pilot sample: ~16k rows cost <= 6 % of the main pass (the gallery has >= 16x as many rows) and leave
+// Pilot sample: ~16k rows cost <= 6 % of the main pass on galleries of >= 16x as many rows (25 % at 4x) and leave
 // ~2.8 top_n survivors per query at top_n = 1000 of 1.25 M rows; 65536 rows left ~1.7 top_n but cost
 // 5 % of the similarity work on config 4.
 constexpr int64_t kPilotRows = 16384;
@@ -460,7 +481,10 @@ bool plan_stream(int64_t n, int q, int64_t top_n, uint32_t flags, StreamPlan* pl
   plan->cap = s + chunk_max;
   plan->pilot_step = 1;
   plan->pilot_rank = 0;
-  if (!(flags & DVL_FLAG_NO_PILOT) && n >= 16 * kPilotRows && top_n < n / 8) {
+  // From 65,536 rows on (every 4th row is sampled there, every n/16384-th from 262,144 rows on): below that the
+  // progressive scheme's few chunks are cheaper than a pilot pass.  The mid range matters for shards: 125 k rows
+  // per GPU (config 3 on 8 GPUs) took five GEMM launches and five selects progressively, three of each with a pilot.
+  if (!(flags & DVL_FLAG_NO_PILOT) && n >= 4 * kPilotRows && top_n < n / 8) {
     const int64_t step = n / kPilotRows;
     const int64_t n_view = (n + step - 1) / step;
     const double mu = (double)top_n * (double)n_view / (double)n;     // expected pilot rank of the top_n-th best
@@ -834,7 +858,7 @@ DVL_API int dvl_destroy(dvl_ctx* c) {
                          &c->log_tab, &c->per_query, &c->mean_dev, &c->scores_tmp, &c->seg_len, &c->sub_cnt, &c->partial,
                          &c->h_gallery, &c->h_queries, &c->h_labels, &c->cand, &c->cand_cnt, &c->cand_tau,
                          &c->cand_flags, &c->topk_labs, &c->topk_avail, &c->fb_queries, &c->fb_per_query, &c->fb_len,
-                         &c->fb_idx, &c->merge_sorted, &c->tab_chunks, &c->bk_store, &c->bk_cnt, &c->bk_cells, &c->bk_lut,
+                         &c->fb_idx, &c->merge_sorted, &c->tab_chunks, &c->bk_store, &c->bk_cnt, &c->bk_cells, &c->bk_cls, &c->bk_lut,
                          &c->bk_plan, &c->sort_flag, &c->label_info, &c->shard_tau_bound, &c->shard_flags_any,
                          &c->shard_counts, &c->shard_out, &c->merge_labs, &c->merge_avail};
   for (dvl::DevBuf* b : bufs)

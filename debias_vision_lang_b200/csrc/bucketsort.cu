@@ -71,7 +71,8 @@ __global__ void __launch_bounds__(kPlanThreads) bucket_plan_kernel(const uint32_
                                                                    int64_t n, int n_buckets, int n_samples,
                                                                    SegPlan* __restrict__ plans, uint8_t* __restrict__ luts,
                                                                    uint32_t* __restrict__ bucket_cnt,
-                                                                   uint32_t* __restrict__ bucket_cells) {
+                                                                   uint32_t* __restrict__ bucket_cells,
+                                                                   uint32_t* __restrict__ bucket_cls) {
   __shared__ uint32_t hist[kCells];
   __shared__ float red_min[32], red_max[32];
   __shared__ uint32_t warp_tot[32];
@@ -83,6 +84,8 @@ __global__ void __launch_bounds__(kPlanThreads) bucket_plan_kernel(const uint32_
 #pragma unroll
   for (int i = 0; i < kCells / kPlanThreads; ++i) hist[i * kPlanThreads + tid] = 0u;
   if (tid < n_buckets) bucket_cnt[(int64_t)q * kMaxBuckets + tid] = 0u;
+  if (bucket_cls != nullptr)       // per-bucket class counts, accumulated by the partition pass (fused metrics)
+    for (int i = tid; i < n_buckets * kMaxClasses; i += kPlanThreads) bucket_cls[(int64_t)q * kMaxBuckets * kMaxClasses + i] = 0u;
   // The sample: groups of 8 consecutive keys (one 32-byte sector) spread evenly over the segment, read twice
   // (range, then histogram; the second read hits L2).  Single keys at a stride below 32 would touch every
   // 128-byte line of the segment -- the whole key matrix from DRAM, twice (measured: 271 MB for config 2).
@@ -211,6 +214,7 @@ struct PartSmem {          // the partition CTA's shared memory (one copy for bo
   unsigned long long* stage;   // [kPartTile] the tile grouped by bucket
   uint8_t* stage_b;        // [kPartTile] bucket of the staged entry
   uint32_t* warp_tot;
+  uint32_t* cls;           // [kMaxBuckets][8] rows of this tile per (bucket, class), two 16-bit counts per word
 };
 
 template <bool kFull>
@@ -218,7 +222,7 @@ __device__ __forceinline__ void
 partition_body(const uint32_t* __restrict__ keys, int64_t ldk, int64_t n, const uint8_t* __restrict__ gallery_labels,
                const SegPlan* __restrict__ plans, const uint8_t* __restrict__ luts, uint32_t* __restrict__ bucket_cnt,
                int n_buckets, unsigned long long* __restrict__ store, uint32_t* __restrict__ nan_cnt,
-               uint32_t* __restrict__ overflow, const PartSmem& sm) {
+               uint32_t* __restrict__ overflow, uint32_t* __restrict__ bucket_cls, const PartSmem& sm) {
   uint8_t* lut = sm.lut;
   uint32_t* hist = sm.hist;
   uint32_t* gbase = sm.gbase;
@@ -229,6 +233,11 @@ partition_body(const uint32_t* __restrict__ keys, int64_t ldk, int64_t n, const 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   reinterpret_cast<uint4*>(lut)[tid] = __ldg(reinterpret_cast<const uint4*>(luts + (int64_t)q * kCells) + tid);
   hist[tid] = 0u;                              // kPartThreads == kMaxBuckets
+  const bool count_cls = bucket_cls != nullptr;
+  if (count_cls) {
+    reinterpret_cast<uint4*>(sm.cls)[2 * tid] = make_uint4(0u, 0u, 0u, 0u);
+    reinterpret_cast<uint4*>(sm.cls)[2 * tid + 1] = make_uint4(0u, 0u, 0u, 0u);
+  }
   const float smax = plans[q].smax, scale = plans[q].scale;
   const uint32_t* seg = keys + (int64_t)q * ldk;
   const int64_t base = (int64_t)blockIdx.x * kPartTile;
@@ -265,6 +274,10 @@ partition_body(const uint32_t* __restrict__ keys, int64_t ldk, int64_t n, const 
       const uint32_t b = lut[cell_of(key[i], smax, scale)];
       nans += (key[i] == kNanKey);
       slot[i] = (b << 16) | atomicAdd(&hist[b], 1u);
+      if (count_cls) {
+        const uint32_t lab = (lab4[i >> 2] >> (8 * (i & 3))) & 0xFu;
+        atomicAdd(&sm.cls[b * 8 + (lab >> 1)], 1u << (16 * (lab & 1u)));     // a tile holds 4096 rows: 16 bits do
+      }
     }
   }
   if (nan_cnt != nullptr && nans != 0u) atomicAdd(nan_cnt + q, nans);      // NaN scores are rare
@@ -288,6 +301,15 @@ partition_body(const uint32_t* __restrict__ keys, int64_t ldk, int64_t n, const 
     if (mine != 0u && g + mine > (uint32_t)kBucketCap) atomicOr(overflow, 1u);
     gbase[tid] = g - excl;                     // storage position = gbase[b] + staging position
     hist[tid] = excl;
+    if (count_cls && mine != 0u) {             // this tile's rows of bucket `tid`, per class
+      uint32_t* dst = bucket_cls + ((int64_t)q * kMaxBuckets + tid) * kMaxClasses;
+#pragma unroll
+      for (int w = 0; w < 8; ++w) {
+        const uint32_t v = sm.cls[tid * 8 + w];
+        if ((v & 0xFFFFu) != 0u) atomicAdd(dst + 2 * w, v & 0xFFFFu);
+        if ((v >> 16) != 0u) atomicAdd(dst + 2 * w + 1, v >> 16);
+      }
+    }
   }
   __syncthreads();
 #pragma unroll
@@ -316,18 +338,21 @@ bucket_partition_kernel(const uint32_t* __restrict__ keys, int64_t ldk, int64_t 
                         const uint8_t* __restrict__ gallery_labels, const SegPlan* __restrict__ plans,
                         const uint8_t* __restrict__ luts, uint32_t* __restrict__ bucket_cnt, int n_buckets,
                         unsigned long long* __restrict__ store, uint32_t* __restrict__ nan_cnt,
-                        uint32_t* __restrict__ overflow) {
+                        uint32_t* __restrict__ overflow, uint32_t* __restrict__ bucket_cls) {
   __shared__ __align__(16) uint8_t lut[kCells];
   __shared__ uint32_t hist[kMaxBuckets];
   __shared__ uint32_t gbase[kMaxBuckets];
-  __shared__ unsigned long long stage[kPartTile];
+  __shared__ __align__(16) unsigned long long stage[kPartTile];
   __shared__ uint8_t stage_b[kPartTile];
   __shared__ uint32_t warp_tot[kPartThreads / 32];
-  const PartSmem sm = {lut, hist, gbase, stage, stage_b, warp_tot};
+  // the per-(bucket, class) counters live in the staging buffer: they are flushed before the first entry is staged
+  const PartSmem sm = {lut, hist, gbase, stage, stage_b, warp_tot, reinterpret_cast<uint32_t*>(stage)};
   if ((int64_t)(blockIdx.x + 1) * kPartTile <= n)     // all tiles of a segment but (at most) the last
-    partition_body<true>(keys, ldk, n, gallery_labels, plans, luts, bucket_cnt, n_buckets, store, nan_cnt, overflow, sm);
+    partition_body<true>(keys, ldk, n, gallery_labels, plans, luts, bucket_cnt, n_buckets, store, nan_cnt, overflow,
+                         bucket_cls, sm);
   else
-    partition_body<false>(keys, ldk, n, gallery_labels, plans, luts, bucket_cnt, n_buckets, store, nan_cnt, overflow, sm);
+    partition_body<false>(keys, ldk, n, gallery_labels, plans, luts, bucket_cnt, n_buckets, store, nan_cnt, overflow,
+                          bucket_cls, sm);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -337,9 +362,19 @@ struct BucketSortParams {
   const SegPlan* plans;
   const uint32_t* bucket_cells;      // [q][kMaxBuckets] first | last << 16 first-level cell of the bucket
   int n_buckets;
-  uint8_t* labs_out; int64_t ldl;
+  uint8_t* labs_out; int64_t ldl;     // null when the metrics are fused (nobody reads the ranked labels then)
   int32_t* idx_out; int64_t ldi;
   uint32_t* keys_out; int64_t ldko;
+  // fused NDKL partial sums + class counts of the ranked rows (whole-segment ranking only; see FusedMetrics)
+  const uint32_t* bucket_cls;        // [q][kMaxBuckets][16] rows per class in each bucket (partition pass)
+  const uint32_t* nan_cnt;           // [q]
+  const unsigned long long* class_counts;   // [16] global label histogram
+  const double* dxl;                 // metric tables (metrics.cu)
+  const double* pwi;
+  double* partial;                   // [q][n_buckets][2]
+  uint32_t* ranked_cls;              // [q][n_buckets + 1][16] class counts of each bucket's ranked rows
+  int64_t n, n_gallery;
+  int n_classes;
 };
 
 
@@ -363,6 +398,133 @@ constexpr size_t kSortSmem = (size_t)kBucketCap * 8 + (size_t)kSubBins * 4 + (si
 // the bucket that re-reads what it needs (the bucket's entries from L1/L2, the rest from shared memory).  An
 // earlier version held 16 entries per thread in registers across the phases; fully unrolled it executed 2.5x the
 // instructions (register shuffling, spills, one branch region per conditional) and ran no faster for it.
+// ---- NDKL partial sums of one bucket, fused into its sort (measuring_bias.py:17-44) ----
+// Same arithmetic as metrics.cu's ndkl_partial_kernel (summation by parts over fp64 tables), on the bucket's
+// ranked labels while they are still in shared memory: the labels never travel to HBM and back, and the
+// sub_counts / sub_scan / ndkl_partial launches disappear.  Needs, per class, the number of rows ranked in
+// earlier buckets (the partition pass counted rows per bucket and class) and the global ranked length
+// m = n - #NaN rows (whole-segment ranking only).  A thread owns 16 consecutive ranks; class counts travel as
+// 16-bit fields of W 64-bit words (W = ceil(C / 4)) through one block-wide exclusive scan.  Fixed reduction
+// order: the result does not depend on scheduling.
+template <int W>
+__device__ __forceinline__ void fused_metrics(const BucketSortParams& p, int q, int b, int count, uint32_t before,
+                                              const uint8_t* labs_s, unsigned long long* scratch, int tid) {
+  __shared__ double ln_d[kMaxClasses];
+  __shared__ uint32_t cbase[kMaxClasses];
+  __shared__ double red[8][2];
+  const int lane = tid & 31, warp = tid >> 5;
+  unsigned long long* warp_scan = scratch;                      // [8][W]   (the sorted keys are dead by now)
+  uint32_t* cpart = reinterpret_cast<uint32_t*>(scratch + 8 * 4);   // [16 groups][16 classes]
+  // rows of each class ranked before this bucket: 16 groups of threads stride over the earlier buckets
+  {
+    const int c = tid & 15, g = tid >> 4;
+    uint32_t acc = 0;
+    const uint32_t* cls = p.bucket_cls + (int64_t)q * kMaxBuckets * kMaxClasses;
+    for (int bb = g; bb < b; bb += 16) acc += __ldg(cls + bb * kMaxClasses + c);
+    cpart[g * 16 + c] = acc;
+  }
+  if (tid < kMaxClasses) {
+    double v = 0.0;
+    if (tid < p.n_classes) {
+      const unsigned long long nc = p.class_counts[tid];
+      v = log((double)(nc > 0 ? nc : 1ull) / (double)p.n_gallery);      // dem_par: max(count, 1) / N  (:27)
+    }
+    ln_d[tid] = v;
+  }
+  __syncthreads();
+  if (tid < kMaxClasses) {
+    uint32_t acc = 0;
+#pragma unroll
+    for (int g = 0; g < 16; ++g) acc += cpart[g * 16 + tid];
+    cbase[tid] = acc;
+  }
+  const long long m = (long long)p.n - (long long)p.nan_cnt[q];          // ranked rows of the query
+  long long valid_ll = m - (long long)before;
+  const int valid = valid_ll < 0 ? 0 : (valid_ll > count ? count : (int)valid_ll);   // NaN rows sit at the very end
+  const int r0 = tid * 16;                                                // this thread's first local rank
+  const uint4 l16 = reinterpret_cast<const uint4*>(labs_s)[tid];         // 16 labels
+  const uint32_t lw[4] = {l16.x, l16.y, l16.z, l16.w};
+  unsigned long long own[W];
+#pragma unroll
+  for (int w = 0; w < W; ++w) own[w] = 0ull;
+#pragma unroll
+  for (int j = 0; j < 16; ++j) {
+    const uint32_t l = (lw[j >> 2] >> (8 * (j & 3))) & 0xFu;
+    const unsigned long long inc = (r0 + j < valid) ? (1ull << (16 * (l & 3u))) : 0ull;
+#pragma unroll
+    for (int w = 0; w < W; ++w) own[w] += ((l >> 2) == (uint32_t)w) ? inc : 0ull;   // labels >= C are rejected by the caller
+  }
+  unsigned long long incl[W];
+#pragma unroll
+  for (int w = 0; w < W; ++w) {
+    incl[w] = own[w];
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+      const unsigned long long o = __shfl_up_sync(0xffffffffu, incl[w], off);
+      if (lane >= off) incl[w] += o;
+    }
+    if (lane == 31) warp_scan[warp * W + w] = incl[w];
+  }
+  __syncthreads();
+  unsigned long long run[W];                     // rows of each class among this bucket's ranks before r0
+#pragma unroll
+  for (int w = 0; w < W; ++w) {
+    run[w] = incl[w] - own[w];
+#pragma unroll
+    for (int ww = 0; ww < 8; ++ww) run[w] += (ww < warp) ? warp_scan[ww * W + w] : 0ull;
+  }
+  if (tid == kSortThreads2 - 1) {                // inclusive total of the last thread = class counts of the ranked rows
+    uint32_t* out = p.ranked_cls + ((int64_t)q * (p.n_buckets + 1) + b) * kMaxClasses;
+#pragma unroll
+    for (int c = 0; c < kMaxClasses; ++c) out[c] = 0u;
+#pragma unroll
+    for (int w = 0; w < W; ++w) {
+      const unsigned long long tot = run[w] + own[w];
+#pragma unroll
+      for (int f = 0; f < 4; ++f) out[4 * w + f] = (uint32_t)(tot >> (16 * f)) & 0xFFFFu;
+    }
+  }
+  double acc_eq = 0.0, acc_d = 0.0;
+  if (r0 < valid) {
+    const double pwi_m = __ldg(p.pwi + m);
+    const double* pw = p.pwi + before + r0;      // PWI[j - 1] of rank j = before + r0 + jj + 1
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      if (r0 + j < valid) {
+        const uint32_t l = (lw[j >> 2] >> (8 * (j & 3))) & 0xFu;
+        const int sh = 16 * (int)(l & 3u);
+        unsigned long long mine = 0ull;
+#pragma unroll
+        for (int w = 0; w < W; ++w) {
+          const bool here = (l >> 2) == (uint32_t)w;
+          mine = here ? run[w] : mine;
+          run[w] += here ? (1ull << sh) : 0ull;
+        }
+        const uint32_t t = cbase[l] + ((uint32_t)(mine >> sh) & 0xFFFFu) + 1u;   // this row is the t-th of its class
+        const double tj = pwi_m - __ldg(pw + j);
+        acc_eq = fma(tj, __ldg(p.dxl + t), acc_eq);
+        acc_d = fma(tj, ln_d[l], acc_d);
+      }
+    }
+  }
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) {
+    acc_eq += __shfl_xor_sync(0xffffffffu, acc_eq, off);
+    acc_d += __shfl_xor_sync(0xffffffffu, acc_d, off);
+  }
+  if (lane == 0) { red[warp][0] = acc_eq; red[warp][1] = acc_d; }
+  __syncthreads();
+  if (tid == 0) {
+    double e = 0.0, d = 0.0;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) { e += red[w][0]; d += red[w][1]; }
+    double* out = p.partial + ((int64_t)q * p.n_buckets + b) * 2;
+    out[0] = e;
+    out[1] = e - d;
+  }
+}
+
+template <int W>
 __global__ void __launch_bounds__(kSortThreads2, 4) bucket_sort_kernel(const BucketSortParams p) {
   extern __shared__ __align__(16) uint8_t smem_dyn[];
   // key | (index << 4 | label): the ranking compares keys and only looks at the index word of an equal key
@@ -379,7 +541,13 @@ __global__ void __launch_bounds__(kSortThreads2, 4) bucket_sort_kernel(const Buc
   const uint32_t* cnts = p.bucket_cnt + (int64_t)q * kMaxBuckets;
   const uint32_t raw = cnts[b];
   const int count = raw > (uint32_t)kBucketCap ? kBucketCap : (int)raw;   // overflowed: the caller falls back
-  if (count == 0) return;
+  if (count == 0) {
+    if constexpr (W > 0) {                             // an empty bucket still owns its slots of the fused outputs
+      if (tid < kMaxClasses) p.ranked_cls[((int64_t)q * (p.n_buckets + 1) + b) * kMaxClasses + tid] = 0u;
+      if (tid < 2) p.partial[((int64_t)q * p.n_buckets + b) * 2 + tid] = 0.0;
+    }
+    return;
+  }
   // ranks of this bucket's rows start after the rows of the buckets before it
   uint32_t before = 0;
   for (int i = lane; i < b; i += 32) before += cnts[i];
@@ -398,7 +566,7 @@ __global__ void __launch_bounds__(kSortThreads2, 4) bucket_sort_kernel(const Buc
   float hi = 0.0f, scale = 0.0f;
   if (c0 == 0u || c1 >= (uint32_t)(kCells - 1) || c1 < c0 || !(plan.scale > 0.0f)) {
     uint32_t kmin = 0xFFFFFFFFu, kmax = 0u;            // over the keys of real scores (a NaN key is 0xFFFFFFFF)
-#pragma unroll 4
+#pragma unroll 8
     for (int pos = tid; pos < count; pos += kSortThreads2) {
       const uint32_t k = (uint32_t)(__ldg(src + pos) >> 32);
       kmin = min(kmin, k);
@@ -426,7 +594,9 @@ __global__ void __launch_bounds__(kSortThreads2, 4) bucket_sort_kernel(const Buc
   __syncthreads();
 
   // ---- counting sort over the sub-bins: the arrival order inside a sub-bin is arbitrary, resolved by the ranking
-#pragma unroll 2
+  // (a planned bucket is 8 rounds of 256 entries: all its loads are in flight together -- the CTA's lifetime is
+  // a chain of memory round trips, and with two loads in flight this loop alone was four of them)
+#pragma unroll 8
   for (int pos = tid; pos < count; pos += kSortThreads2) {
     const uint32_t k = (uint32_t)(__ldg(src + pos) >> 32);
     s_arr[pos] = (uint16_t)atomicAdd(&bins[subbin_of(k, hi, scale)], 1u);
@@ -463,7 +633,7 @@ __global__ void __launch_bounds__(kSortThreads2, 4) bucket_sort_kernel(const Buc
     reinterpret_cast<uint4*>(bins)[2 * tid + 1] = make_uint4(start[4], start[5], start[6], start[7]);
   }
   __syncthreads();
-#pragma unroll 2
+#pragma unroll 4
   for (int pos = tid; pos < count; pos += kSortThreads2) {
     const unsigned long long e = __ldg(src + pos);     // second read: L1 / L2
     const uint32_t k = (uint32_t)(e >> 32);
@@ -472,7 +642,6 @@ __global__ void __launch_bounds__(kSortThreads2, 4) bucket_sort_kernel(const Buc
     s_val[dst] = (uint32_t)e;
   }
   __syncthreads();
-  uint8_t* labs = p.labs_out + (int64_t)q * p.ldl + before;
   if (sh_big == 0u) {
     // Entry-parallel ranking over the sub-bin sorted list: every entry counts the entries of its own sub-bin
     // that rank before it (a sub-bin holds ~1 entry).  The first four candidates are compared without a loop
@@ -500,20 +669,7 @@ __global__ void __launch_bounds__(kSortThreads2, 4) bucket_sort_kernel(const Buc
       if (want_idx) p.idx_out[(int64_t)q * p.ldi + before + rank] = (int32_t)(v >> 4);
       if (want_keys) p.keys_out[(int64_t)q * p.ldko + before + rank] = k;
     }
-    __syncthreads();
-    // ranked labels out: 4 bytes per store where the destination allows it
-    const int head = (int)((4u - (uint32_t)(reinterpret_cast<uintptr_t>(labs) & 3u)) & 3u);
-    for (int i = tid; i < head && i < count; i += kSortThreads2) labs[i] = labs_s[i];
-    const int words = count > head ? (count - head) >> 2 : 0;
-    for (int i = tid; i < words; i += kSortThreads2) {
-      const uint8_t* sp = labs_s + head + 4 * i;
-      reinterpret_cast<uint32_t*>(labs + head)[i] =
-          (uint32_t)sp[0] | ((uint32_t)sp[1] << 8) | ((uint32_t)sp[2] << 16) | ((uint32_t)sp[3] << 24);
-    }
-    for (int i = head + 4 * words + tid; i < count; i += kSortThreads2) labs[i] = labs_s[i];
-    return;
-  }
-  {
+  } else {
     // a sub-bin is crowded (heavy ties inside the bucket): bitonic sort of the whole bucket by (key, index word)
     int pow2 = 1;
     while (pow2 < count) pow2 <<= 1;
@@ -538,13 +694,30 @@ __global__ void __launch_bounds__(kSortThreads2, 4) bucket_sort_kernel(const Buc
         __syncthreads();
       }
     }
+    for (int i = tid; i < count; i += kSortThreads2) {
+      const uint32_t v = s_val[i];
+      labs_s[i] = (uint8_t)(v & 0xFu);
+      if (p.idx_out != nullptr) p.idx_out[(int64_t)q * p.ldi + before + i] = (int32_t)(v >> 4);
+      if (p.keys_out != nullptr) p.keys_out[(int64_t)q * p.ldko + before + i] = s_key[i];
+    }
   }
-  for (int i = tid; i < count; i += kSortThreads2) {
-    const uint32_t v = s_val[i];
-    labs[i] = (uint8_t)(v & 0xFu);
-    if (p.idx_out != nullptr) p.idx_out[(int64_t)q * p.ldi + before + i] = (int32_t)(v >> 4);
-    if (p.keys_out != nullptr) p.keys_out[(int64_t)q * p.ldko + before + i] = s_key[i];
+  __syncthreads();
+  // ---- the bucket's ranked labels are in shared memory: fused NDKL partial sums, and / or the labels themselves
+  if constexpr (W > 0) {
+    fused_metrics<W>(p, q, b, count, before, labs_s, reinterpret_cast<unsigned long long*>(s_key), tid);
+    if (p.labs_out == nullptr) return;
   }
+  uint8_t* labs = p.labs_out + (int64_t)q * p.ldl + before;
+  // 4 bytes per store where the destination allows it
+  const int head = (int)((4u - (uint32_t)(reinterpret_cast<uintptr_t>(labs) & 3u)) & 3u);
+  for (int i = tid; i < head && i < count; i += kSortThreads2) labs[i] = labs_s[i];
+  const int words = count > head ? (count - head) >> 2 : 0;
+  for (int i = tid; i < words; i += kSortThreads2) {
+    const uint8_t* sp = labs_s + head + 4 * i;
+    reinterpret_cast<uint32_t*>(labs + head)[i] =
+        (uint32_t)sp[0] | ((uint32_t)sp[1] << 8) | ((uint32_t)sp[2] << 16) | ((uint32_t)sp[3] << 24);
+  }
+  for (int i = head + 4 * words + tid; i < count; i += kSortThreads2) labs[i] = labs_s[i];
 }
 
 }  // namespace
@@ -562,6 +735,8 @@ static int buckets_for(int64_t n) {
   return b < 1 ? 1 : (b > kMaxBuckets ? kMaxBuckets : b);
 }
 
+int bucket_sort_buckets(int64_t n) { return buckets_for(n); }
+
 size_t bucket_sort_workspace_per_query(int64_t n) {
   return (size_t)buckets_for(n) * kBucketCap * 8 + kCells + kMaxBuckets * 8 + sizeof(SegPlan);
 }
@@ -577,8 +752,18 @@ int launch_bucket_sort(Ctx* c, const BucketSortArgs& a, cudaStream_t st) {
   DVL_TRY(ensure(c, c->bk_cells, (size_t)a.q * kMaxBuckets * 4));
   DVL_TRY(ensure(c, c->bk_lut, (size_t)a.q * kCells));
   DVL_TRY(ensure(c, c->bk_plan, (size_t)a.q * sizeof(SegPlan)));
+  const bool fused = a.partial != nullptr;
+  if (fused && (a.ranked_cls == nullptr || a.nan_cnt == nullptr || a.class_counts == nullptr || a.dxl == nullptr ||
+                a.pwi == nullptr || a.n_classes < 1 || a.n_classes > kMaxClasses))
+    return set_error(c, DVL_ERR_INVALID, "fused metrics need the label statistics, tables and output buffers");
+  if (!fused && a.labs_out == nullptr) return set_error(c, DVL_ERR_INVALID, "no output for the ranked labels");
+  if (fused) DVL_TRY(ensure(c, c->bk_cls, (size_t)a.q * kMaxBuckets * kMaxClasses * 4));
   if (!c->bucket_attr_set) {
-    DVL_CUDA(c, cudaFuncSetAttribute(bucket_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSortSmem));
+    DVL_CUDA(c, cudaFuncSetAttribute(bucket_sort_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSortSmem));
+    DVL_CUDA(c, cudaFuncSetAttribute(bucket_sort_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSortSmem));
+    DVL_CUDA(c, cudaFuncSetAttribute(bucket_sort_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSortSmem));
+    DVL_CUDA(c, cudaFuncSetAttribute(bucket_sort_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSortSmem));
+    DVL_CUDA(c, cudaFuncSetAttribute(bucket_sort_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSortSmem));
     c->bucket_attr_set = true;
   }
   if (a.nan_cnt != nullptr) DVL_CUDA(c, cudaMemsetAsync(a.nan_cnt, 0, (size_t)a.q * sizeof(uint32_t), st));
@@ -590,17 +775,18 @@ int launch_bucket_sort(Ctx* c, const BucketSortArgs& a, cudaStream_t st) {
     uint8_t* luts = (uint8_t*)c->bk_lut.ptr + (int64_t)q0 * kCells;
     uint32_t* cnt = (uint32_t*)c->bk_cnt.ptr + (int64_t)q0 * kMaxBuckets;
     uint32_t* cells = (uint32_t*)c->bk_cells.ptr + (int64_t)q0 * kMaxBuckets;
+    uint32_t* cls = fused ? (uint32_t*)c->bk_cls.ptr + (int64_t)q0 * kMaxBuckets * kMaxClasses : nullptr;
     unsigned long long* store = (unsigned long long*)c->bk_store.ptr + (int64_t)q0 * nb * kBucketCap;
     {
       StageScope scope(c, DVL_STAGE_SORT_HIST, st);
-      bucket_plan_kernel<<<(unsigned)qn, kPlanThreads, 0, st>>>(keys, a.ldk, a.n, nb, n_samples, plans, luts, cnt, cells);
+      bucket_plan_kernel<<<(unsigned)qn, kPlanThreads, 0, st>>>(keys, a.ldk, a.n, nb, n_samples, plans, luts, cnt, cells, cls);
       DVL_LAUNCH_CHECK(c, "bucket_plan_kernel");
     }
     {
       StageScope scope(c, DVL_STAGE_SORT_SCATTER, st);
       dim3 grid((unsigned)tiles, (unsigned)qn);
       bucket_partition_kernel<<<grid, kPartThreads, 0, st>>>(keys, a.ldk, a.n, a.gallery_labels, plans, luts, cnt, nb, store,
-                                                            a.nan_cnt != nullptr ? a.nan_cnt + q0 : nullptr, a.overflow);
+                                                            a.nan_cnt != nullptr ? a.nan_cnt + q0 : nullptr, a.overflow, cls);
       DVL_LAUNCH_CHECK(c, "bucket_partition_kernel");
     }
     {
@@ -611,14 +797,30 @@ int launch_bucket_sort(Ctx* c, const BucketSortArgs& a, cudaStream_t st) {
       p.plans = plans;
       p.bucket_cells = cells;
       p.n_buckets = nb;
-      p.labs_out = a.labs_out + (int64_t)q0 * a.ldl;
+      p.labs_out = a.labs_out != nullptr ? a.labs_out + (int64_t)q0 * a.ldl : nullptr;
       p.ldl = a.ldl;
+      p.bucket_cls = cls;
+      p.nan_cnt = a.nan_cnt != nullptr ? a.nan_cnt + q0 : nullptr;
+      p.class_counts = a.class_counts;
+      p.dxl = a.dxl;
+      p.pwi = a.pwi;
+      p.partial = fused ? a.partial + (int64_t)q0 * nb * 2 : nullptr;
+      p.ranked_cls = fused ? a.ranked_cls + (int64_t)q0 * (nb + 1) * kMaxClasses : nullptr;
+      p.n = a.n;
+      p.n_gallery = a.n_gallery;
+      p.n_classes = a.n_classes;
       p.idx_out = a.idx_out != nullptr ? a.idx_out + (int64_t)q0 * a.ldi : nullptr;
       p.ldi = a.ldi;
       p.keys_out = a.keys_out != nullptr ? a.keys_out + (int64_t)q0 * a.ldko : nullptr;
       p.ldko = a.ldko;
       dim3 grid((unsigned)nb, (unsigned)qn);
-      bucket_sort_kernel<<<grid, kSortThreads2, kSortSmem, st>>>(p);
+      switch (fused ? (a.n_classes + 3) / 4 : 0) {
+        case 0: bucket_sort_kernel<0><<<grid, kSortThreads2, kSortSmem, st>>>(p); break;
+        case 1: bucket_sort_kernel<1><<<grid, kSortThreads2, kSortSmem, st>>>(p); break;
+        case 2: bucket_sort_kernel<2><<<grid, kSortThreads2, kSortSmem, st>>>(p); break;
+        case 3: bucket_sort_kernel<3><<<grid, kSortThreads2, kSortSmem, st>>>(p); break;
+        default: bucket_sort_kernel<4><<<grid, kSortThreads2, kSortSmem, st>>>(p); break;
+      }
       DVL_LAUNCH_CHECK(c, "bucket_sort_kernel");
     }
   }

@@ -37,7 +37,7 @@ struct Ctx {
   DevBuf merge_sorted, merge_labs, merge_avail, tab_chunks;
   // bucket sort (bucketsort.cu): bucket storage, per-bucket counts, cell -> bucket tables, per-query plans,
   // and the device word a bucket overflow raises
-  DevBuf bk_store, bk_cnt, bk_cells, bk_lut, bk_plan, sort_flag, label_info;
+  DevBuf bk_store, bk_cnt, bk_cells, bk_cls, bk_lut, bk_plan, sort_flag, label_info;
   DevBuf shard_tau_bound, shard_flags_any, shard_counts, shard_out;   // reduced over the ranks (dvl_shard_reduce)
   int shard_reduced_q = 0;
   bool bucket_attr_set = false;
@@ -194,8 +194,20 @@ struct BucketSortArgs {
   int64_t ldko = 0;
   uint32_t* nan_cnt = nullptr;         // [q] or null: number of NaN-keyed rows per segment
   uint32_t* overflow = nullptr;        // device word
+  // Fused metrics (whole-segment ranking, top_n >= n): when `partial` is set the sort also emits, per bucket,
+  // the NDKL partial sums [q][B][2] (the layout finalize reads, B = bucket_sort_buckets(n)) and the class
+  // counts of its ranked rows [q][B + 1][16]; labs_out may then be null.  Needs nan_cnt, the global label
+  // histogram and the DXL / PWI tables of metrics.cu.
+  double* partial = nullptr;
+  uint32_t* ranked_cls = nullptr;
+  const unsigned long long* class_counts = nullptr;
+  const double* dxl = nullptr;
+  const double* pwi = nullptr;
+  int64_t n_gallery = 0;
+  int n_classes = 0;
 };
 bool bucket_sort_eligible(int64_t n);
+int bucket_sort_buckets(int64_t n);
 size_t bucket_sort_workspace_per_query(int64_t n);
 int launch_bucket_sort(Ctx* c, const BucketSortArgs& a, cudaStream_t st);
 
@@ -265,6 +277,12 @@ struct MetricArgs {
 // fp64 tables XL, WI, PW, PWL of metrics.cu for indices < len
 int ensure_metric_tables(Ctx* c, int64_t len, cudaStream_t st);
 int launch_metrics(Ctx* c, const MetricArgs& a, cudaStream_t st);
+// metrics of a ranking whose NDKL partial sums and ranked class counts were already produced per bucket by the
+// bucket sort (fused): ranked lengths + finalize only.  Sizes and hands out the two buffers the sort writes.
+int fused_metric_buffers(Ctx* c, int q, int buckets, double** partial, uint32_t** ranked_cls);
+int launch_metrics_fused(Ctx* c, const MetricArgs& a, int buckets, cudaStream_t st);
+// DXL / PWI tables (device pointers) for kernels outside metrics.cu
+void metric_tables(const Ctx* c, const double** dxl, const double** pwi);
 int launch_mean(Ctx* c, const double* per_query, int q, double* mean_dev, cudaStream_t st);
 int launch_copy_ranked(Ctx* c, const int32_t* idx_sorted, int64_t ldi, const int32_t* ranked_len, int q,
                        int32_t* out, int64_t cap, cudaStream_t st);

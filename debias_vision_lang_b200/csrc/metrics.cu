@@ -435,6 +435,7 @@ struct FinalParams {
   const double* pw;
   const double* pwl;
   double* per_query;
+  int sum_counts;       // sub_pref holds per-slice COUNTS (fused bucket sort): total them into slot `subs` first
 };
 
 __global__ void __launch_bounds__(128) finalize_kernel(const FinalParams p) {
@@ -455,6 +456,15 @@ __global__ void __launch_bounds__(128) finalize_kernel(const FinalParams p) {
   for (int off = 16; off > 0; off >>= 1) {
     s_eq += __shfl_xor_sync(0xffffffffu, s_eq, off);
     s_dp += __shfl_xor_sync(0xffffffffu, s_dp, off);
+  }
+  if (p.sum_counts) {
+    uint32_t* cnt = const_cast<uint32_t*>(p.sub_pref) + (int64_t)qi * (p.subs + 1) * kMaxClasses;
+    if (lane < kMaxClasses) {
+      uint32_t tot = 0;
+      for (int s = 0; s < p.subs; ++s) tot += cnt[(int64_t)s * kMaxClasses + lane];
+      cnt[(int64_t)p.subs * kMaxClasses + lane] = tot;
+    }
+    __syncwarp();
   }
   if (lane != 0) return;
   int c_present = 0;
@@ -599,6 +609,46 @@ int launch_metrics(Ctx* c, const MetricArgs& a, cudaStream_t st) {
   f.pw = pw;
   f.pwl = pwl;
   f.per_query = a.per_query;
+  f.sum_counts = 0;
+  finalize_kernel<<<(a.q + 3) / 4, 128, 0, st>>>(f);
+  DVL_LAUNCH_CHECK(c, "finalize_kernel");
+  return DVL_OK;
+}
+
+void metric_tables(const Ctx* c, const double** dxl, const double** pwi) {
+  *dxl = (const double*)c->log_tab.ptr;
+  *pwi = *dxl + c->log_tab_len;
+}
+
+int fused_metric_buffers(Ctx* c, int q, int buckets, double** partial, uint32_t** ranked_cls) {
+  DVL_TRY(ensure(c, c->sub_cnt, (size_t)q * (buckets + 1) * kMaxClasses * sizeof(uint32_t)));
+  DVL_TRY(ensure(c, c->partial, (size_t)q * buckets * 2 * sizeof(double)));
+  *partial = (double*)c->partial.ptr;
+  *ranked_cls = (uint32_t*)c->sub_cnt.ptr;
+  return DVL_OK;
+}
+
+int launch_metrics_fused(Ctx* c, const MetricArgs& a, int buckets, cudaStream_t st) {
+  if (a.nan_cnt == nullptr || a.top_n < a.n_avail) return set_error(c, DVL_ERR_INVALID, "fused metrics rank whole segments");
+  const int64_t tab = c->log_tab_len;
+  if (a.top_n + 6 > tab || a.n_avail + 6 > tab) return set_error(c, DVL_ERR_INVALID, "metric tables too short");
+  const double* dxl = (const double*)c->log_tab.ptr;
+  ranked_len_kernel<<<(a.q + 3) / 4, 128, 0, st>>>(nullptr, 0, nullptr, a.n_avail, a.top_n, a.q, a.ranked_len, a.nan_cnt);
+  DVL_LAUNCH_CHECK(c, "ranked_len_kernel");
+  FinalParams f;
+  f.ranked_len = a.ranked_len;
+  f.q = a.q;
+  f.n_classes = a.n_classes;
+  f.subs = buckets;
+  f.n_gallery = a.n_gallery;
+  f.top_n = a.top_n;
+  f.sub_pref = (const uint32_t*)c->sub_cnt.ptr;
+  f.class_counts = a.class_counts;
+  f.partial = (const double*)c->partial.ptr;
+  f.pw = dxl + 2 * tab;
+  f.pwl = dxl + 3 * tab;
+  f.per_query = a.per_query;
+  f.sum_counts = 1;
   finalize_kernel<<<(a.q + 3) / 4, 128, 0, st>>>(f);
   DVL_LAUNCH_CHECK(c, "finalize_kernel");
   return DVL_OK;

@@ -29,7 +29,7 @@ import torch
 from . import _capi
 
 __all__ = [
-    "clip_logits", "normalized_discounted_KL", "compute_skew_metrics", "get_prompt_embeddings", "get_labels_img_embeddings",
+    "clip_logits", "adversary_input", "normalized_discounted_KL", "compute_skew_metrics", "get_prompt_embeddings", "get_labels_img_embeddings",
     "eval_ranking", "gen_prompts", "measure_bias", "evaluate", "DEFAULT_OPTS", "PROMPT_TEMPLATES", "PROMPT_CONCEPTS",
 ]
 
@@ -300,6 +300,27 @@ def clip_logits(image_features: torch.Tensor, text_features: torch.Tensor, logit
                                                    _capi.FLAG_NORMALIZE_GALLERY | _capi.FLAG_NORMALIZE_QUERIES)
     logits_per_text = sims * float(logit_scale)
     return logits_per_text.t(), logits_per_text
+
+
+def adversary_input(image_features: torch.Tensor, text_features: torch.Tensor, logit_scale: float = 1.0,
+                    opts: Optional[dict] = None) -> torch.Tensor:
+    """The input of the reference's ``Adversary`` (model/model.py:337-361; ``ADV_N_INPUT`` = number of prompts):
+    ``logits_per_image`` of ``DebiasCLIP.forward`` (model/model.py:276-289) as a CONTIGUOUS ``[N, Q]`` fp32
+    matrix -- one row of prompt-array logits per image, what ``nn.Linear(n_input, hidden)`` reads.
+    ``clip_logits`` returns that matrix as a transposed view of the query-major GEMM output; here the roles
+    of the operands are swapped (images on the tensor-core M side, prompts on the N side), so the same
+    tcgen05 GEMM with both L2 normalisations fused into its epilogue writes the image-major layout
+    directly and no transpose pass over N x Q floats is needed."""
+    dev = _device_of(image_features)
+    g = _as_device_matrix(image_features, dev)
+    t = _as_device_matrix(text_features, dev)
+    precision = _PRECISIONS[(opts or {}).get("precision", "fp32")]
+    with torch.cuda.device(dev):
+        logits = _capi.context(dev.index).similarity(t, g, precision,
+                                                     _capi.FLAG_NORMALIZE_GALLERY | _capi.FLAG_NORMALIZE_QUERIES)
+    if float(logit_scale) != 1.0:
+        logits *= float(logit_scale)
+    return logits
 
 
 def measure_bias(cliplike, img_preproc: Optional[Callable] = None, tokenizer: Optional[Callable] = None,

@@ -137,6 +137,7 @@ def _query_slice(q: int, world: int, rank: int) -> Tuple[int, int]:
 # Packed list length learnt by a (world, Q, top_n, shard size) configuration whose speculative length
 # was once too short (tie-heavy or label-sorted galleries): later calls start from it.
 _learnt_list_len: Dict[tuple, int] = {}
+MAX_STREAM_TOP_N = 8192      # dvl_shard_topk keeps lists of up to this many entries (csrc/api.cu plan_stream)
 # exchange buffers of evaluate_query_sharded, per (context, device, queries per rank)
 _query_shard_bufs: Dict[tuple, tuple] = {}
 
@@ -147,6 +148,41 @@ def speculative_list_len(top_n: int, rows_per_shard: int, n_global: int) -> int:
     travels with the results and a too-short guess is repaired by a second exchange."""
     mu = top_n * min(1.0, rows_per_shard / max(1, n_global))
     return int(-(-math.ceil(mu + 6.0 * math.sqrt(mu) + 32.0) // 8) * 8)
+
+
+def _dense_rerank(ctx, comm, gallery_local: torch.Tensor, labels_local_u8: torch.Tensor, queries_sel: torch.Tensor,
+                  n_global: int, n_classes: int, top_n: int, precision: int, flags: int, ranked_cap: int):
+    """Exact ranking of a (small) set of queries over the whole sharded gallery by the full-sort route: every rank
+    computes the dense scores of its shard, the score rows and the labels are all-gathered (contiguous row blocks,
+    so concatenating the shards IS the gallery order) and ranked with ``dvl_rank_and_score``.  Used for the queries
+    the streaming route flags (tie run longer than a candidate list) and for ``top_n`` beyond its 8192-entry lists;
+    batched so that the gathered score matrix stays below ~2 GB."""
+    world = comm.world
+    dev = queries_sel.device
+    n_local = gallery_local.shape[0]
+    rows_blk = shard_bounds(n_global, world, 0)[1]
+    lab_blk = torch.zeros((rows_blk,), dtype=torch.uint8, device=dev)
+    lab_blk[:n_local] = labels_local_u8
+    all_labels = comm.all_gather(lab_blk).reshape(-1)[:n_global].contiguous()
+    f_total = queries_sel.shape[0]
+    batch = max(1, min(f_total, int(2.0e9 // (4 * world * rows_blk))))
+    out = {"per_query": torch.empty((f_total, 4), dtype=torch.float64, device=dev),
+           "ranked_len": torch.empty((f_total,), dtype=torch.int32, device=dev),
+           "ranked_idx": torch.full((f_total, ranked_cap), -1, dtype=torch.int32, device=dev) if ranked_cap else None}
+    for b0 in range(0, f_total, batch):
+        fq = queries_sel[b0:b0 + batch].contiguous()
+        f = fq.shape[0]
+        local_scores = torch.zeros((f, rows_blk), dtype=torch.float32, device=dev)
+        if n_local:
+            local_scores[:, :n_local] = ctx.similarity(gallery_local, fq, precision, flags)
+        all_scores = comm.all_gather(local_scores)          # [world, F, rows_blk]
+        full = all_scores.permute(1, 0, 2).reshape(f, -1)[:, :n_global].contiguous()
+        rr = ctx.rank_and_score(full, all_labels, n_classes, top_n, ranked_cap)
+        out["per_query"][b0:b0 + f] = rr["per_query"]
+        out["ranked_len"][b0:b0 + f] = rr["ranked_len"]
+        if ranked_cap:
+            out["ranked_idx"][b0:b0 + f] = rr["ranked_idx"]
+    return out
 
 
 def evaluate_sharded_host(ctx, comm, gallery_local: torch.Tensor, queries: torch.Tensor, labels_local_u8: torch.Tensor,
@@ -230,6 +266,19 @@ def evaluate_sharded(ctx, comm, gallery_local: torch.Tensor, queries: torch.Tens
     if top_n < 1:
         raise ZeroDivisionError("top_n must be >= 1")
     dev = torch.device("cuda", ctx.device) if host_inputs else queries.device
+    if top_n > MAX_STREAM_TOP_N:
+        # beyond the streaming top-k's shared-memory lists: every query is ranked exactly from gathered dense scores
+        # (the reference takes any topn, measuring_bias.py:109-110; so does this, at full-sort cost)
+        if host_inputs:
+            gallery_local, queries, labels_local_u8 = gallery_local.to(dev), queries.to(dev), labels_local_u8.to(dev)
+        rr = _dense_rerank(ctx, comm, gallery_local, labels_local_u8, queries, n_global, n_classes, top_n, precision,
+                           flags, ranked_cap)
+        mean = ctx.mean(rr["per_query"])
+        out = {"maxskew": {"eq_opp": mean[0], "dem_par": mean[1]}, "ndkl": {"eq_opp": mean[2], "dem_par": mean[3]},
+               "per_query": rr["per_query"], "ranked_len": rr["ranked_len"], "n_flagged": q, "list_len": 0}
+        if ranked_cap:
+            out["ranked_idx"] = rr["ranked_idx"]
+        return out
     rows_per_shard = shard_bounds(n_global, world, 0)[1]
     key = (world, q, int(top_n), rows_per_shard, n_global)
     length = _learnt_list_len.get(key) or speculative_list_len(top_n, rows_per_shard, n_global)
@@ -293,18 +342,8 @@ def evaluate_sharded(ctx, comm, gallery_local: torch.Tensor, queries: torch.Tens
             gallery_local, queries, labels_local_u8 = gallery_local.to(dev), queries.to(dev), labels_local_u8.to(dev)
         flagged = torch.nonzero(flag_mask).reshape(-1)
         n_flagged = int(flagged.numel())
-        n_local = gallery_local.shape[0]
-        rows_blk = shard_bounds(n_global, world, 0)[1]
-        fq = queries[flagged].contiguous()
-        local_scores = torch.zeros((n_flagged, rows_blk), dtype=torch.float32, device=queries.device)
-        if n_local:
-            local_scores[:, :n_local] = ctx.similarity(gallery_local, fq, precision, flags)
-        lab_blk = torch.zeros((rows_blk,), dtype=torch.uint8, device=queries.device)
-        lab_blk[:n_local] = labels_local_u8
-        all_scores = comm.all_gather(local_scores)          # [world, F, rows_blk]
-        all_labels = comm.all_gather(lab_blk).reshape(-1)[:n_global].contiguous()
-        full = all_scores.permute(1, 0, 2).reshape(n_flagged, -1)[:, :n_global].contiguous()
-        rr = ctx.rank_and_score(full, all_labels, n_classes, top_n, ranked_cap)
+        rr = _dense_rerank(ctx, comm, gallery_local, labels_local_u8, queries[flagged].contiguous(), n_global, n_classes,
+                           top_n, precision, flags, ranked_cap)
         per_query[flagged] = rr["per_query"]
         ranked_len[flagged] = rr["ranked_len"]
         if ranked_cap:

@@ -102,8 +102,8 @@ def test_bucket_sort_segment_lengths(ctx, n):
 
 def test_bucket_sort_equals_radix_sort_on_config2_shape(ctx):
     """BASELINE config 2's shape end to end (108,501 x 512 x 40 queries, C = 7, top_n = N): the default route
-    (bucket sort) and the radix sort (DVL_FLAG_RADIX_SORT) give bit-identical per-query results and ranked
-    index lists, in direct launches and in the CUDA-graph replays of either."""
+    (bucket sort with the NDKL sums fused in) and the radix sort (DVL_FLAG_RADIX_SORT) give identical ranked
+    index lists and per-query results equal to 1e-12, in direct launches and in the CUDA-graph replays of either."""
     w = synthetic.baseline_workload("cfg2", device="cuda", q_override=40)
     lab = torch.from_numpy(w.labels.astype(np.uint8)).cuda()
     n = w.gallery.shape[0]
@@ -115,8 +115,14 @@ def test_bucket_sort_equals_radix_sort_on_config2_shape(ctx):
             assert torch.equal(o["per_query"], outs[0]["per_query"]) and torch.equal(o["ranked_idx"], outs[0]["ranked_idx"])
         runs[name] = outs[0]
     assert torch.equal(runs["bucket"]["ranked_idx"], runs["radix"]["ranked_idx"])
-    assert torch.equal(runs["bucket"]["per_query"], runs["radix"]["per_query"])
-    assert runs["bucket"]["mean"] == runs["radix"]["mean"]
+    assert torch.equal(runs["bucket"]["ranked_len"], runs["radix"]["ranked_len"])
+    # the bucket sort sums the NDKL terms per bucket (fused into the sort), the radix route per 1024-row slice:
+    # same fp64 terms, different grouping
+    assert (runs["bucket"]["per_query"] - runs["radix"]["per_query"]).abs().max().item() <= 1e-12
+    assert max(abs(a - b) for a, b in zip(runs["bucket"]["mean"], runs["radix"]["mean"])) <= 1e-12
+    want = spec.measure(w.labels, w.gallery.cpu()[:, :], w.queries.cpu()[:3], 1.0)    # three queries through the oracle
+    got3 = runs["bucket"]["per_query"][:3].cpu().numpy().mean(axis=0)
+    assert abs(got3[2] - want["ndkl"]["eq_opp"]) <= 1e-6 and abs(got3[3] - want["ndkl"]["dem_par"]) <= 1e-6
 
 
 def test_bucket_overflow_falls_back_inside_graph_replays(ctx):

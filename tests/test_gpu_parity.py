@@ -356,6 +356,25 @@ def test_clip_logits_both_sides_normalised():
     assert torch.equal(per_text, per_image.t())
 
 
+def test_adversary_input_is_contiguous_logits_per_image():
+    """the adversary's input (model/model.py:337-361) = logits_per_image of DebiasCLIP.forward
+    (model/model.py:276-289), image-major and contiguous, against the reference formula in float64."""
+    torch.manual_seed(5)
+    img = torch.randn(3001, 512, device="cuda") * 3.0
+    txt = torch.randn(319, 512, device="cuda")
+    scale = float(np.exp(4.6052))
+    x = measuring_bias.adversary_input(img, txt, scale)
+    assert x.shape == (3001, 319) and x.is_contiguous() and x.dtype == torch.float32
+    i64, t64 = img.double(), txt.double()
+    want = scale * (i64 / i64.norm(dim=-1, keepdim=True)) @ (t64 / t64.norm(dim=-1, keepdim=True)).t()
+    assert (x.double() - want).abs().max().item() <= scale * 1e-5
+    per_image, _ = measuring_bias.clip_logits(img, txt, scale)
+    assert (x - per_image).abs().max().item() <= scale * 2e-6          # same numbers as the query-major GEMM
+    # it feeds an Adversary-shaped MLP as is
+    mlp = torch.nn.Sequential(torch.nn.Linear(319, 32), torch.nn.ReLU(), torch.nn.Linear(32, 1)).cuda()
+    assert torch.sigmoid(mlp(x)).shape == (3001, 1)
+
+
 def test_graph_replay_matches_direct_launches(ctx):
     """The full-sort route replays a captured CUDA graph from the third identical call on.  Replays must
     see new contents of the same buffers, survive a differently shaped call in between (workspace

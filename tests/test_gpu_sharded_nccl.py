@@ -29,6 +29,7 @@ CASES = [
     dict(name="adversarial_short_guess", n=40_000, d=64, q=24, c=2, topn=300, seed=22, spec=8),
     dict(name="clip_like_bf16", n=300_000, d=128, q=130, c=7, topn=1000, seed=23, precision="bf16"),
     dict(name="host_inputs", n=40_000, d=64, q=24, c=2, topn=300, seed=24, host=True),
+    dict(name="large_top_n_dense_route", n=20_000, d=64, q=5, c=2, topn=9_000, seed=26),
     dict(name="query_sharded_top_n_is_N", n=9_000, d=64, q=9, c=3, topn=9_000, seed=25, route="query"),
 ]
 

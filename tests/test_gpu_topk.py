@@ -148,7 +148,17 @@ def test_million_row_topk_properties(ctx):
 def test_pilot_threshold_route_is_exact(ctx):
     """Galleries >= 262,144 rows take their first threshold from a strided pilot sample (optimistic, then
     verified).  Same ranked lists and metrics as the full-sort route and as the progressive scheme."""
-    w = synthetic.clip_like(300_000, 64, 40, 7, seed=41, device="cuda")
+    _pilot_route_case(ctx, 300_000)
+
+
+def test_pilot_threshold_route_on_a_shard_sized_gallery(ctx):
+    """The pilot also serves mid-size galleries (65,536 rows on; every 4th..16th row sampled): one GPU's shard of
+    a million-row gallery on 8 GPUs."""
+    _pilot_route_case(ctx, 125_000)
+
+
+def _pilot_route_case(ctx, n):
+    w = synthetic.clip_like(n, 64, 40, 7, seed=41, device="cuda")
     lab = torch.from_numpy(w.labels.astype(np.uint8)).cuda()
     # every precision mode (the fp32 mode's per-row scale must follow the strided pilot view), with and
     # without the fused gallery normalisation

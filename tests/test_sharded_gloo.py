@@ -50,6 +50,7 @@ def _worker(rank, world, port, case, out_dir):
     (2, dict(n=1500, q=6, c=2, topn=40, seed=8, cap=4096, spec=8)),   # guess too short -> re-exchange
     (2, dict(n=400, q=5, c=3, topn=400, seed=9, cap=4096, route="query")),   # whole gallery ranked, query slices
     (3, dict(n=300, q=2, c=2, topn=300, seed=10, cap=4096, route="query")),  # a rank without queries
+    (2, dict(n=8600, q=2, c=2, topn=8300, seed=12, cap=4096)),   # top_n beyond the streaming lists: dense route
 ])
 def test_sharded_protocol_gloo(tmp_path, world, case):
     port = 29500 + (os.getpid() % 2000)
