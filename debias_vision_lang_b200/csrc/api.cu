@@ -287,10 +287,16 @@ int ensure_sort_flag(Ctx* c, cudaStream_t st) {
   return DVL_OK;
 }
 
+// Opt-in (DVL_FUSE_METRICS=1), off by default -- measured on config 2 and rejected: with the NDKL partial sums
+// computed inside bucket_sort_kernel (fused_metrics in bucketsort.cu) the sort takes 0.90 instead of 0.28 ms and
+// the partition 0.16 instead of 0.126, against 0.12 ms saved in the metrics stage (1.10 vs 0.57 ms in total).
+// The metrics are bound by their fp64 table gathers, not by the one byte per ranked row they read from HBM, and
+// inside the sort CTA those gathers sit on a per-thread chain of 16 rows with half the threads idle.  Kept
+// because it is exact and tested (it documents what the label round trip through HBM costs: nothing).
 bool fuse_metrics_enabled() {
   static const bool on = [] {
     const char* e = getenv("DVL_FUSE_METRICS");
-    return !(e != nullptr && e[0] == '0');
+    return e != nullptr && e[0] == '1';
   }();
   return on;
 }
@@ -336,8 +342,7 @@ int rank_full(Ctx* c, const uint8_t* labels, int64_t n, int64_t n_gallery, int q
     b.ldko = ldk;
     b.nan_cnt = whole ? (uint32_t*)c->nan_cnt.ptr : nullptr;
     b.overflow = (uint32_t*)c->sort_flag.ptr;
-    // the whole segment is ranked: the NDKL partial sums come out of the sort itself (per bucket, from the ranked
-    // labels while they are in shared memory) and the labels never go to HBM; DVL_FUSE_METRICS=0 keeps the stages apart
+    // opt-in variant (see fuse_metrics_enabled): the NDKL partial sums come out of the sort itself, per bucket
     fused = whole && fuse_metrics_enabled();
     if (fused) {
       DVL_TRY(fused_metric_buffers(c, q, bucket_sort_buckets(n), &b.partial, &b.ranked_cls));
