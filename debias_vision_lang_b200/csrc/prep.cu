@@ -80,10 +80,16 @@ __global__ void __launch_bounds__(256) split_rows_kernel(const T* __restrict__ s
         for (int j = 0; j < 4; ++j) {
           ss = fmaf(x[u][j], x[u][j], ss);
           float r = x[u][j];
+          // A +-inf / NaN element lives in the LAST plane alone (the residual inf - inf would be NaN, and every
+          // product term that pairs an inf with the other operand's small residual planes could flip its sign):
+          // the last plane only multiplies the other operand's leading plane, so the similarity comes out as the
+          // +-inf / NaN an fp32 mat-vec produces (measuring_bias.py:114).
+          const bool fin = fabsf(r) <= 3.4028234664e38f;
 #pragma unroll
           for (int p = 0; p < PLANES; ++p) {
-            b[p][j] = __float2bfloat16_rn(r);
-            r = r - __bfloat162float(b[p][j]);   // exact: the residual of a round-to-8-bits fits fp32
+            const bool last = p == PLANES - 1;
+            b[p][j] = (fin || last) ? __float2bfloat16_rn(r) : __float2bfloat16_rn(0.0f);
+            r = fin ? r - __bfloat162float(b[p][j]) : r;   // exact: the residual of a round-to-8-bits fits fp32
           }
         }
 #pragma unroll
@@ -115,7 +121,6 @@ __global__ void __launch_bounds__(256) split_rows_f16x2_kernel(const T* __restri
     const T* s = src + row * (int64_t)d;
     __half* o = dst + row * (int64_t)dp;
     float ss = 0.f, amax = 0.f;
-    bool finite = true;
     float x[kUnroll][4];
     for (int c0 = lane * 4; c0 < dp; c0 += 128 * kUnroll) {
 #pragma unroll
@@ -126,8 +131,7 @@ __global__ void __launch_bounds__(256) split_rows_f16x2_kernel(const T* __restri
         for (int j = 0; j < 4; ++j) {
           ss = fmaf(x[u][j], x[u][j], ss);
           const float a = fabsf(x[u][j]);
-          finite &= (a <= 3.4028234664e38f);     // false for inf and NaN
-          amax = fmaxf(amax, a);
+          amax = fmaxf(amax, (a <= 3.4028234664e38f) ? a : 0.f);   // the scale comes from the finite elements
         }
       }
     }
@@ -136,11 +140,9 @@ __global__ void __launch_bounds__(256) split_rows_f16x2_kernel(const T* __restri
       ss += __shfl_xor_sync(0xffffffffu, ss, off);
       amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, off));
     }
-    finite = __all_sync(0xffffffffu, finite);
-    // e = 14 - floor(log2(amax)), clamped so that 2^e and 2^-e are normal floats; an all-zero or
-    // non-finite row keeps scale 1 (inf/NaN then propagate into the scores like in an fp32 product)
+    // e = 14 - floor(log2(amax)), clamped so that 2^e and 2^-e are normal floats; an all-zero row keeps scale 1
     int e = 0;
-    if (finite && amax > 0.f) {
+    if (amax > 0.f) {
       const int be = (int)((__float_as_uint(amax) >> 23) & 0xFFu);   // biased exponent; 0 for subnormals
       e = 14 - (be - 127);
       e = e > 126 ? 126 : (e < -126 ? -126 : e);
@@ -160,8 +162,12 @@ __global__ void __launch_bounds__(256) split_rows_f16x2_kernel(const T* __restri
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           const float xs = x[u][j] * up;            // exact (power of two; |xs| < 2^15)
-          h0[j] = __float2half_rn(xs);
-          h1[j] = __float2half_rn(xs - __half2float(h0[j]));   // the residual is exact in fp32
+          // a +-inf / NaN element goes to the second plane alone: that plane only meets the other operand's
+          // leading plane (terms h1*h0', h0*h1', h0*h0'), so the similarity is the +-inf / NaN of an fp32
+          // product instead of inf - inf from a residual, or an inf whose sign a tiny residual decides
+          const bool fin = fabsf(x[u][j]) <= 3.4028234664e38f;
+          h0[j] = __float2half_rn(fin ? xs : 0.f);
+          h1[j] = __float2half_rn(fin ? xs - __half2float(h0[j]) : x[u][j]);   // the residual is exact in fp32
         }
         *reinterpret_cast<uint2*>(o + c) = *reinterpret_cast<const uint2*>(h0);
         *reinterpret_cast<uint2*>(o + plane_stride + c) = *reinterpret_cast<const uint2*>(h1);

@@ -227,8 +227,31 @@ def eval_ranking(labels_list: np.ndarray, image_embeddings: torch.Tensor, prompt
     return dict(both[evaluation])
 
 
+def _scores_as_f32(col) -> np.ndarray:
+    """The ``score`` column as the float32 keys the kernels rank.  The reference builds the column as float32
+    (measuring_bias.py:114-115), but ``compute_skew_metrics`` / ``normalized_discounted_KL`` take any DataFrame:
+    float64 scores that differ below float32 resolution must not become ties (they would change the keep="all"
+    cut-off and the tie order), so such a column is replaced by its dense ranks -- an order- and tie-preserving
+    float32 surrogate (exact for up to 2^24 distinct values)."""
+    a = np.asarray(col)
+    if a.dtype == np.float32:
+        return np.ascontiguousarray(a)
+    a64 = a.astype(np.float64)
+    a32 = a64.astype(np.float32)
+    with np.errstate(invalid="ignore"):
+        exact = bool(np.all((a32.astype(np.float64) == a64) | np.isnan(a64)))
+    if exact:
+        return np.ascontiguousarray(a32)
+    values, inverse = np.unique(a64, return_inverse=True)         # ascending; NaN (if any) last, as one value
+    if len(values) > (1 << 24):
+        raise ValueError("more than 2^24 distinct float64 scores: pass float32 scores")
+    surrogate = inverse.astype(np.float32)
+    surrogate[np.isnan(a64)] = np.nan
+    return np.ascontiguousarray(surrogate)
+
+
 def _single_query(df, top_n: int, need_contiguous: bool) -> List[float]:
-    scores = np.ascontiguousarray(np.asarray(df["score"], dtype=np.float32))
+    scores = _scores_as_f32(df["score"])
     codes, n_classes = _encode_labels(np.asarray(df["label"]), need_contiguous)
     if int(top_n) < 1:
         raise ZeroDivisionError("division by zero")

@@ -548,7 +548,11 @@ def measure_sharded(labels_local, gallery_local: torch.Tensor, queries: torch.Te
                     topn: Union[int, float] = 1000, opts: Optional[dict] = None, group=None):
     """Convenience wrapper under torchrun: labels (ints, local rows) -> the measure_bias dict."""
     lab = np.asarray(labels_local)
-    n_classes = int(opts.get("n_classes")) if opts and "n_classes" in opts else int(lab.max()) + 1
+    if lab.size and (int(lab.min()) < 0 or int(lab.max()) >= _capi.MAX_CLASSES):
+        raise ValueError(f"labels must be class codes 0..{_capi.MAX_CLASSES - 1} (datasets.gen_labels); "
+                         "re-encode them before sharding")
+    # a rank may own no rows (tiny gallery): its class count is whatever the other ranks see
+    n_classes = int(opts.get("n_classes")) if opts and "n_classes" in opts else (int(lab.max()) + 1 if lab.size else 1)
     top_n = math.ceil(n_global * topn) if isinstance(topn, float) else int(topn)
     dev = gallery_local.device
     comm = TorchDistComm(group)

@@ -229,6 +229,61 @@ def test_dataframe_entry_points_match_golden(stage_cases):
             assert abs(nd["ndkl_dem_par"] - case["ndkl_dem_par"]) <= TIGHT
 
 
+def test_dataframe_entry_points_rank_float64_scores_exactly():
+    """float64 scores that differ below float32 resolution are NOT ties (the reference's nlargest compares the
+    column as it is): the drop-in ranks them through an order- and tie-preserving surrogate."""
+    import pandas as pd
+    rng = np.random.RandomState(3)
+    n, top_n = 400, 50
+    base = rng.randint(0, 40, size=n).astype(np.float64) / 8.0           # heavy float32-level ties ...
+    scores = base + rng.randint(0, 3, size=n) * 1e-12                      # ... split (or not) far below fp32 resolution
+    labels = synthetic.make_labels(n, 3, 4)
+    df = pd.DataFrame({"score": scores, "label": labels})
+    ms = dvl.compute_skew_metrics(df, top_n)
+    nd = dvl.normalized_discounted_KL(df, top_n)
+    want_ms = spec.eval_query(scores, labels, "maxskew", top_n)
+    want_nd = spec.eval_query(scores, labels, "ndkl", top_n)
+    assert abs(ms["maxskew_eq_opp"] - want_ms["eq_opp"]) <= TIGHT and abs(ms["maxskew_dem_par"] - want_ms["dem_par"]) <= TIGHT
+    assert abs(nd["ndkl_eq_opp"] - want_nd["eq_opp"]) <= TIGHT and abs(nd["ndkl_dem_par"] - want_nd["dem_par"]) <= TIGHT
+    # and the float32 view of the same column would have been a different ranking
+    as32 = spec.eval_query(scores.astype(np.float32), labels, "ndkl", top_n)
+    assert abs(as32["eq_opp"] - want_nd["eq_opp"]) > 1e-6
+
+
+def test_non_finite_embedding_elements_behave_like_an_fp32_product(ctx):
+    """A gallery row with a +-inf element scores +-inf (by the sign of the query's component; NaN where it is 0 or
+    where +inf and -inf meet), a NaN element scores NaN -- what the reference's fp32 mat-vec gives
+    (measuring_bias.py:114) -- in every precision mode, and such rows rank first / last / are dropped."""
+    torch.manual_seed(9)
+    n, d, q = 600, 96, 5
+    g = torch.randn(n, d, device="cuda")
+    t = torch.randn(q, d, device="cuda")
+    t[:, 7] = torch.tensor([1.5, -0.5, 0.0, 2.0, -3.0], device="cuda")
+    t[:, 11] = torch.tensor([1.0, 1.0, 1.0, -1.0, 0.25], device="cuda")
+    g[5, 7] = float("inf")
+    g[6, 7] = float("-inf")
+    g[9, 7] = float("inf"); g[9, 11] = float("-inf")
+    g[12, 3] = float("nan")
+    want = t @ g.t()                                   # fp32 reference semantics for the special rows
+    rows = [5, 6, 9, 12]
+    for prec in (_capi.PRECISION_FP32, _capi.PRECISION_FP32X3, _capi.PRECISION_BF16):
+        got = ctx.similarity(g, t, prec)
+        for r in rows:
+            w, h = want[:, r], got[:, r]
+            assert torch.equal(torch.isnan(w), torch.isnan(h)), (prec, r, w, h)
+            fin = ~torch.isnan(w)
+            assert torch.equal(w[fin], h[fin]), (prec, r, w, h)      # +-inf with the right sign
+        others = [i for i in range(n) if i not in rows]
+        tol = 2e-2 if prec == _capi.PRECISION_BF16 else 1e-5
+        scale = g[others].norm(dim=-1)[None, :] * t.norm(dim=-1)[:, None]
+        assert ((got[:, others] - want[:, others]).abs() / scale).max().item() <= tol
+    lab = torch.from_numpy(synthetic.make_labels(n, 2, 1).astype(np.uint8)).cuda()
+    res = ctx.eval_ranking(g, t, lab, 2, n, _capi.PRECISION_FP32, want_per_query=True, ranked_cap=n)
+    order0 = res["ranked_idx"][0].cpu().numpy()         # query 0: t[0,7] = 1.5 > 0
+    assert order0[0] == 5 and int(res["ranked_len"][0]) == n - 2        # +inf first; rows 9 and 12 are NaN: dropped
+    assert order0[n - 3] == 6                                            # -inf last
+
+
 def test_edge_cases_and_errors(ctx):
     w = synthetic.dyadic_grid(300, 64, 3, 2, seed=1)
     g, t = w.gallery.cuda(), w.queries.cuda()

@@ -140,3 +140,13 @@ def test_gallery_cache_round_trip_and_shards(tmp_path, dtype):
     assert torch.equal(torch.cat(rows), emb) and np.array_equal(np.concatenate(labs), w.labels)
     item = whole[5]
     assert torch.equal(item["img"], emb[5]) and item["iat_label"] == int(w.labels[5])
+
+
+def test_float64_scores_get_an_order_and_tie_preserving_float32_surrogate():
+    from debias_vision_lang_b200.measuring_bias import _scores_as_f32
+    exact = np.array([0.5, 0.25, -1.0, 3.0], dtype=np.float64)
+    assert _scores_as_f32(exact).dtype == np.float32 and np.array_equal(_scores_as_f32(exact), exact.astype(np.float32))
+    close = np.array([1.0, 1.0 + 1e-12, 1.0, 1.0 - 1e-12, np.nan, 2.0])
+    s = _scores_as_f32(close)
+    assert s[1] > s[0] == s[2] > s[3] and s[5] > s[1] and np.isnan(s[4])
+    assert np.array_equal(_scores_as_f32(np.array([3, 1, 2])), np.array([3, 1, 2], dtype=np.float32))
