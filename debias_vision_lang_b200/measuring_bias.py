@@ -258,7 +258,7 @@ def _single_query(df, top_n: int, need_contiguous: bool) -> List[float]:
     if not torch.cuda.is_available():
         raise RuntimeError("no CUDA device: the bias-measurement path has no CPU fallback")
     dev = torch.device("cuda", torch.cuda.current_device())
-    s = torch.from_numpy(scores).to(dev)[None, :]
+    s = torch.from_numpy(np.array(scores, copy=True)).to(dev)[None, :]
     lab = torch.from_numpy(codes).to(dev)
     return _capi.context(dev.index).rank_and_score(s, lab, n_classes, int(top_n))["mean"]
 

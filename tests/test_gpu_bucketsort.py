@@ -136,3 +136,40 @@ def test_bucket_overflow_falls_back_inside_graph_replays(ctx):
         m = ctx.eval_ranking(g, t, lab, 2, 20_000, _capi.PRECISION_FP32)["mean"]
         assert abs(m[2] - want["ndkl"]["eq_opp"]) <= 1e-9 and abs(m[3] - want["ndkl"]["dem_par"]) <= 1e-9
         assert abs(m[0] - want["maxskew"]["eq_opp"]) <= 1e-9
+
+
+def test_query_batching_of_the_full_sort_route_matches_one_batch(tmp_path):
+    """The full-sort route ranks queries in batches bounded by a workspace budget (DVL_WS_BUDGET_MB, read once per
+    process): a run squeezed into ~10 queries per batch -- bucket sort and radix sort, with ranked indices and
+    scores on request -- must equal the unbatched run bit for bit."""
+    import json
+    import os
+    import subprocess
+    import sys
+    from conftest import ROOT
+    script = r'''
+import json, sys, numpy as np, torch
+sys.path.insert(0, %r)
+from debias_vision_lang_b200 import _capi, synthetic
+w = synthetic.clip_like(30_011, 64, 47, 7, seed=5, device="cuda")
+lab = torch.from_numpy(w.labels.astype(np.uint8)).cuda()
+ctx = _capi.Context(0)
+out = {}
+for name, flags, topn in (("bucket", 0, 30_011), ("radix", _capi.FLAG_RADIX_SORT, 30_011), ("cut", _capi.FLAG_FULL_SORT, 700)):
+    r = ctx.eval_ranking(w.gallery, w.queries, lab, 7, topn, _capi.PRECISION_FP32, flags, want_per_query=True,
+                         ranked_cap=1500, want_scores=(name == "bucket"))
+    out[name] = dict(mean=r["mean"], pq=r["per_query"].cpu().numpy().tobytes().hex(),
+                     idx=r["ranked_idx"].cpu().numpy().tobytes().hex(), len=r["ranked_len"].cpu().tolist(),
+                     scores=(r["scores"].double().sum().item() if r["scores"] is not None else None))
+print("RESULT" + json.dumps(out))
+''' % ROOT
+    results = []
+    for budget in (None, "8"):
+        env = dict(os.environ)
+        env.pop("DVL_WS_BUDGET_MB", None)
+        if budget:
+            env["DVL_WS_BUDGET_MB"] = budget
+        p = subprocess.run([sys.executable, "-c", script], env=env, capture_output=True, text=True, timeout=600)
+        assert p.returncode == 0, p.stderr[-2000:]
+        results.append(json.loads([ln for ln in p.stdout.splitlines() if ln.startswith("RESULT")][0][6:]))
+    assert results[0] == results[1]
