@@ -125,7 +125,7 @@ int launch_encode_labels(Ctx* c, const void* labels, int label_dtype, int64_t n,
                          unsigned long long* info, cudaStream_t st);
 
 // ---- gemm.cu ---------------------------------------------------------------------------
-enum { kGemmStore = 0, kGemmSeed = 1, kGemmFilter = 2 };
+enum { kGemmStore = 0, kGemmSeed = 1, kGemmFilter = 2, kGemmProbe = 3, kGemmProbeLd = 4 /* measurement only: no epilogue / TMEM reads only */ };
 struct GemmArgs {
   int mode = kGemmStore;
   int64_t row0 = 0, row1 = 0;       // gallery rows [row0, row1) handled by this launch

@@ -98,12 +98,30 @@ struct KernelParams {
   int64_t cap;
   const uint8_t* labels;       // [n] labels of this gallery shard
   int64_t index_base;          // global index of local row 0
+  int probe_pass1_only;        // measurement only
 };
 
 // The label nibble is filled in by the final select pass (topk.cu): looking it up here would put a
 // dependent global load on the epilogue's slow path.
 __device__ __forceinline__ unsigned long long make_entry(float s, int64_t gidx) {
   return (static_cast<unsigned long long>(score_to_key(s)) << 32) | (static_cast<unsigned long long>(gidx) << 4);
+}
+
+// v[j] for a runtime j without touching memory: a five-level select tree (31 selects).  The FILTER epilogue
+// needs it for its rare survivors; staging the 32 values of a chunk in shared memory instead (indexable, the
+// first version) cost ~120 KB of shared-memory traffic per tile -- on the port the tensor cores' operand reads
+// and the TMA writes already saturate.
+__device__ __forceinline__ uint32_t pick32(const uint32_t (&v)[32], int j) {
+  uint32_t a[16], b[8], c[4], d[2];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) a[i] = (j & 16) ? v[16 + i] : v[i];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) b[i] = (j & 8) ? a[8 + i] : a[i];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) c[i] = (j & 4) ? b[4 + i] : b[i];
+#pragma unroll
+  for (int i = 0; i < 2; ++i) d[i] = (j & 2) ? c[2 + i] : c[i];
+  return (j & 1) ? d[1] : d[0];
 }
 
 // kPair: the kernel runs as clusters of two CTAs (one TPC) that drive tcgen05.mma.cta_group::2 together: the
@@ -287,29 +305,51 @@ sim_gemm_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
       if (p.mode == kGemmFilter && row_ok) tau = __ldg(p.tau + qrow);
       mbar_wait(tfull_bar(as), aphase);
       tc_fence_after();
+      if (p.mode == kGemmProbe || p.mode == kGemmProbeLd) {   // measurement only (DVL_GEMM_PROBE=1 / 2): the MMA/TMA
+        if (p.mode == kGemmProbeLd) {                          // pipeline without an epilogue / with its TMEM reads only
+          uint32_t v[32];
+          const uint32_t ta = tmem_base + (uint32_t)(as * BN) + ((uint32_t)((warp & 3) * 32) << 16);
+          uint32_t acc = 0;
+#pragma unroll
+          for (int ci = 0; ci < BN / 64; ++ci) {
+            tmem_ld_32x32(ta + (uint32_t)((((warp - 2) >> 2) * (BN / 64) + ci) * 32), v);
+            tmem_ld_wait_regs(v);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) acc |= v[j];
+          }
+          if (acc == 0x12345678u) p.cand_cnt[0] = acc;         // keeps the reads alive
+        }
+        tc_fence_before();
+        if (kPair) mbar_arrive_cluster(tempty_bar(as) & kPeerBitMask);
+        else mbar_arrive(tempty_bar(as));
+        as ^= 1;
+        if (as == 0) aphase ^= 1u;
+        continue;
+      }
       const uint32_t taddr = tmem_base + (uint32_t)(as * BN) + ((uint32_t)(quarter * 32) << 16);
       const bool scaled = p.qry_scale != nullptr || p.gal_scale != nullptr;
       if (p.mode == kGemmFilter) {
         // ---- streaming top-k: one compare per similarity against tau.  Survivors (rare once tau has
-        // tightened) are appended to the query's list: ONE atomic per 32-column chunk reserves their
-        // slots, the values go through a 32-word shared-memory row so that the bit loop can index them.
-        uint32_t* mine = epi_scratch + (threadIdx.x - 64) * 33;
+        // tightened) are appended to the query's list.  Two passes over the thread's four 32-column chunks:
+        //   pass 1  accumulator read + fused scale + compare -> a 32-bit survivor mask per chunk;
+        //   one global atomic per TILE reserves the slots of all the thread's survivors;
+        //   pass 2  the chunks that hold a survivor in any lane are read from TMEM again (reads cost nothing
+        //           next to the MMAs) and the survivors are picked out of the registers (pick32) and written.
+        // One atomic per chunk (the first version) put ~four global round trips of ~2000 cycles on every tile of
+        // every epilogue warp -- about the time the tensor cores need for the tile -- and the kernel ran 11 %
+        // below its own MMA/TMA pipeline (tools/gemm_probe.py: 1268 vs 1404 TFLOP/s without the epilogue).
         unsigned long long* list = p.cand + (int64_t)qrow * p.cap;
-        // software pipeline over the warp's four 32-column chunks: the accumulator read of chunk c+1 is
-        // in flight while chunk c is processed
-        uint32_t vbuf[2][32];
-        tmem_ld_32x32(taddr + (uint32_t)(chunk0 * 32), vbuf[0]);
-#pragma unroll
-        for (int ci = 0; ci < BN / 64; ++ci) {
+        uint32_t masks[BN / 64];
+        uint32_t total = 0;
+        auto load_scaled = [&](int ci, uint32_t (&v)[32], bool prefetch_next, uint32_t (&vnext)[32]) {
           const int chunk = chunk0 + ci;
-          uint32_t (&v)[32] = vbuf[ci & 1];
           const int64_t col0 = p.row0 + gb * BN + chunk * 32;
           // the chunk's 32 gallery-row factors: lane j fetches column j's (one coalesced load), the element
           // loop gets them by shuffle
           float gs_lane = 1.0f;
           if (p.gal_scale != nullptr) gs_lane = (col0 + lane < p.n) ? __ldg(p.gal_scale + (col0 + lane) * p.gal_step) : 0.f;
           tmem_ld_wait_regs(v);
-          if (ci + 1 < BN / 64) tmem_ld_32x32(taddr + (uint32_t)((chunk + 1) * 32), vbuf[(ci + 1) & 1]);
+          if (prefetch_next) tmem_ld_32x32(taddr + (uint32_t)((chunk + 1) * 32), vnext);
           // uniform branches, outside the element loops (a shuffle under a per-element branch is neither
           // if-converted nor pipelined by the compiler)
           if (p.gal_scale != nullptr) {
@@ -320,21 +360,40 @@ sim_gemm_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) * qs);
           }
-          uint32_t mask = 0;
+        };
+        {
+          uint32_t vbuf[2][32];
+          tmem_ld_32x32(taddr + (uint32_t)(chunk0 * 32), vbuf[0]);
 #pragma unroll
-          for (int j = 0; j < 32; ++j) mask |= (__uint_as_float(v[j]) >= tau ? 1u : 0u) << j;
-          const int64_t left = p.n - col0;
-          if (left < 32) mask &= (left <= 0) ? 0u : ((1u << left) - 1u);
-          if (mask != 0u) {
+          for (int ci = 0; ci < BN / 64; ++ci) {
+            uint32_t (&v)[32] = vbuf[ci & 1];
+            load_scaled(ci, v, ci + 1 < BN / 64, vbuf[(ci + 1) & 1]);
+            uint32_t mask = 0;
 #pragma unroll
-            for (int j = 0; j < 32; ++j) mine[j] = v[j];
-            uint32_t slot = atomicAdd(p.cand_cnt + qrow, (uint32_t)__popc(mask));
+            for (int j = 0; j < 32; ++j) mask |= (__uint_as_float(v[j]) >= tau ? 1u : 0u) << j;
+            const int64_t left = p.n - (p.row0 + gb * BN + (chunk0 + ci) * 32);
+            if (left < 32) mask &= (left <= 0) ? 0u : ((1u << left) - 1u);
+            masks[ci] = mask;
+            total += (uint32_t)__popc(mask);
+          }
+        }
+        if (p.probe_pass1_only) {                  // measurement only (DVL_GEMM_PROBE=3): thresholds, no appends
+          if (total == 0xFFFFFFFFu) p.cand_cnt[qrow] = total;
+        } else if (__any_sync(0xffffffffu, total != 0u)) {
+          uint32_t slot = 0;
+          if (total != 0u) slot = atomicAdd(p.cand_cnt + qrow, total);
+#pragma unroll
+          for (int ci = 0; ci < BN / 64; ++ci) {
+            if (!__any_sync(0xffffffffu, masks[ci] != 0u)) continue;     // warp-uniform: tcgen05.ld is warp-wide
+            uint32_t v[32];
+            tmem_ld_32x32(taddr + (uint32_t)((chunk0 + ci) * 32), v);
+            load_scaled(ci, v, false, v);
+            uint32_t mask = masks[ci];
+            const int64_t col0 = p.row0 + gb * BN + (chunk0 + ci) * 32;
             while (mask != 0u) {
               const int j = __ffs(mask) - 1;
               mask &= mask - 1u;
-              const int64_t col = col0 + j;
-              if ((int64_t)slot < p.cap)
-                list[slot] = make_entry(__uint_as_float(mine[j]), p.index_base + col);
+              if ((int64_t)slot < p.cap) list[slot] = make_entry(__uint_as_float(pick32(v, j)), p.index_base + col0 + j);
               ++slot;
             }
           }
@@ -500,6 +559,12 @@ int launch_sim_gemm(Ctx* c, const GemmArgs& a, cudaStream_t st) {
                    a.gal_row_step));
   KernelParams p;
   p.mode = a.mode;
+  {
+    // DVL_GEMM_PROBE=1: FILTER launches run without their epilogue (results are garbage; tools/gemm_probe.py)
+    static const int probe = [] { const char* e = getenv("DVL_GEMM_PROBE"); return e != nullptr ? atoi(e) : 0; }();
+    if ((probe == 1 || probe == 2) && a.mode == kGemmFilter) p.mode = probe == 2 ? kGemmProbeLd : kGemmProbe;
+    p.probe_pass1_only = probe == 3 ? 1 : 0;
+  }
   p.row0 = a.row0;
   p.n = a.row1;
   p.q = a.q;

@@ -150,3 +150,43 @@ def test_float64_scores_get_an_order_and_tie_preserving_float32_surrogate():
     s = _scores_as_f32(close)
     assert s[1] > s[0] == s[2] > s[3] and s[5] > s[1] and np.isnan(s[4])
     assert np.array_equal(_scores_as_f32(np.array([3, 1, 2])), np.array([3, 1, 2], dtype=np.float32))
+
+
+def test_header_is_plain_c_and_the_library_binds_from_c(tmp_path):
+    """include/dvl_b200.h compiles as C99 (no C++, no torch types) and a C program can bind the library the way
+    any FFI would: dlopen, version, context creation (DVL_ERR_NO_DEVICE without a B200 -- never a silent fallback)."""
+    import shutil
+    import subprocess
+    from conftest import ROOT
+    from debias_vision_lang_b200 import _capi
+    if shutil.which("gcc") is None or not os.path.exists(_capi.LIB_PATH):
+        pytest.skip("needs gcc and the built library")
+    src = tmp_path / "bind.c"
+    src.write_text(r'''
+#include <dlfcn.h>
+#include <stdio.h>
+#include "dvl_b200.h"
+typedef int (*version_fn)(void);
+typedef int (*create_fn)(dvl_ctx**, int);
+typedef int (*destroy_fn)(dvl_ctx*);
+int main(int argc, char** argv) {
+  void* lib = dlopen(argv[1], RTLD_NOW);
+  if (!lib) { printf("dlopen failed: %s\n", dlerror()); return 2; }
+  version_fn version; create_fn create; destroy_fn destroy;
+  *(void**)(&version) = dlsym(lib, "dvl_abi_version");     /* the POSIX idiom: ISO C has no object -> function cast */
+  *(void**)(&create) = dlsym(lib, "dvl_create");
+  *(void**)(&destroy) = dlsym(lib, "dvl_destroy");
+  if (!version || !create || !destroy || !dlsym(lib, "dvl_eval_ranking") || !dlsym(lib, "dvl_shard_topk_host")) return 3;
+  dvl_ctx* ctx = 0;
+  int rc = create(&ctx, 0);
+  printf("abi=%d create=%d\n", version(), rc);
+  if (rc == DVL_OK) destroy(ctx);
+  return (version() == DVL_B200_ABI_VERSION && (rc == DVL_OK || rc == DVL_ERR_NO_DEVICE)) ? 0 : 4;
+}
+''')
+    exe = tmp_path / "bind"
+    subprocess.check_call(["gcc", "-std=c99", "-pedantic", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"),
+                           str(src), "-o", str(exe), "-ldl"])
+    out = subprocess.run([str(exe), _capi.LIB_PATH], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert "abi=1" in out.stdout
