@@ -21,6 +21,7 @@ DVL_F32, DVL_BF16, DVL_F16 = 0, 1, 2
 PRECISION_FP32, PRECISION_BF16, PRECISION_FP32X3 = 0, 1, 2
 FLAG_NORMALIZE_QUERIES, FLAG_NORMALIZE_GALLERY, FLAG_FULL_SORT, FLAG_STREAM_TOPK, FLAG_NO_PILOT = 1, 2, 4, 8, 16
 FLAG_RADIX_SORT = 32
+FLAG_REUSE_GALLERY = 64
 MAX_CLASSES = 16
 STAGES = ("prep", "gemm", "sort_hist", "sort_scan", "sort_scatter", "metrics", "select", "copy")
 NUM_STAGES = len(STAGES)

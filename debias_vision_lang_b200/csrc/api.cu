@@ -102,14 +102,6 @@ int check_common(Ctx* c, int64_t n, int32_t d, int32_t q, int32_t n_classes, int
   return DVL_OK;
 }
 
-struct Operands {
-  const void* qry_planes;
-  const void* gal_planes;
-  int planes;
-  int dp;
-  const float* qry_scale;
-  const float* gal_scale;
-};
 
 // bf16 embeddings in bf16 mode are already the operand TMA wants (K-major rows, 16-byte aligned
 // pitch): the caller's memory is used in place and the conversion pass is skipped
@@ -949,8 +941,20 @@ DVL_API int dvl_similarity(dvl_ctx* c, const void* gallery, int gdt, const void*
   cudaStream_t st = (cudaStream_t)stream;
   const int64_t lds = dvl::round_up(n, 256);
   DVL_TRY(dvl::ensure(c, c->scores_tmp, (size_t)q * lds * 4));
-  DVL_TRY(dvl::run_similarity(c, gallery, gdt, queries, qdt, n, d, q, precision, flags, nullptr, 0,
-                              (float*)c->scores_tmp.ptr, lds, st));
+  if ((flags & DVL_FLAG_REUSE_GALLERY) != 0u) {
+    // the caller vouches that `gallery` is the matrix the preceding dvl_shard_topk on this context prepared and
+    // that it has not changed since: only the queries are prepared, the gallery's conversion pass is skipped
+    if (!c->prepared_valid || c->prepared_n != n || c->prepared_d != d || c->prepared_precision != precision ||
+        c->prepared_flags != (flags & DVL_FLAG_NORMALIZE_GALLERY))
+      return dvl::set_error(c, DVL_ERR_INVALID, "DVL_FLAG_REUSE_GALLERY: no matching gallery prepared by dvl_shard_topk");
+    dvl::Operands op = c->prepared_gallery;
+    DVL_TRY(dvl::prepare_queries(c, queries, qdt, d, q, precision, flags, &op, st));
+    DVL_TRY(dvl::run_similarity_prepared(c, op, n, d, q, nullptr, 0, (float*)c->scores_tmp.ptr, lds, st));
+  } else {
+    c->prepared_valid = false;        // this call prepares another gallery into the same workspace
+    DVL_TRY(dvl::run_similarity(c, gallery, gdt, queries, qdt, n, d, q, precision, flags, nullptr, 0,
+                                (float*)c->scores_tmp.ptr, lds, st));
+  }
   DVL_CUDA(c, cudaMemcpy2DAsync(out, (size_t)ld_out * 4, c->scores_tmp.ptr, (size_t)lds * 4, (size_t)n * 4, q,
                                 cudaMemcpyDeviceToDevice, st));
   DVL_CUDA(c, cudaStreamSynchronize(st));
@@ -1062,6 +1066,7 @@ int eval_ranking_impl(dvl_ctx* c, const void* gallery, int gdt, const void* quer
   c->radix_only = false;      // per-call state a failed earlier call may have left behind
   c->force_lsd = false;
   c->bucket_used = false;
+  c->prepared_valid = false;  // this call prepares its own gallery into the shared workspace
   dvl::DeviceGuard guard(c->device);
   cudaStream_t st = (cudaStream_t)stream;
   DVL_TRY(dvl::ensure(c, c->per_query, (size_t)q * 4 * sizeof(double)));
@@ -1188,6 +1193,14 @@ int shard_topk_impl(dvl_ctx* c, const void* gallery, int gdt, const void* querie
   c->shard_plan_cap = plan.cap;
   c->shard_sort_cap = plan.sort_cap;
   c->shard_q = q;
+  // what DVL_FLAG_REUSE_GALLERY may pick up: the gallery operand this call prepared (planes + row factors in the
+  // workspace, or the caller's bf16 rows in place), valid until the next call that prepares a gallery
+  c->prepared_gallery = op;
+  c->prepared_n = n_local;
+  c->prepared_d = d;
+  c->prepared_precision = precision;
+  c->prepared_flags = flags & DVL_FLAG_NORMALIZE_GALLERY;
+  c->prepared_valid = true;
   DVL_CUDA(c, cudaMemcpyAsync(out_tau, c->cand_tau.ptr, (size_t)q * 4, cudaMemcpyDeviceToDevice, st));
   DVL_CUDA(c, cudaMemcpyAsync(out_flags, c->cand_flags.ptr, (size_t)q * 4, cudaMemcpyDeviceToDevice, st));
   DVL_CUDA(c, cudaMemcpyAsync(out_class_counts, c->class_counts.ptr, sizeof(unsigned long long) * (kMaxClasses + 1),

@@ -20,6 +20,16 @@ struct DevBuf {
   size_t bytes = 0;
 };
 
+// one prepared similarity problem: 16-bit operand planes (+ row factors) of both sides
+struct Operands {
+  const void* qry_planes;
+  const void* gal_planes;
+  int planes;
+  int dp;
+  const float* qry_scale;
+  const float* gal_scale;
+};
+
 struct Ctx {
   int device = 0;
   int num_sms = 0;
@@ -43,6 +53,12 @@ struct Ctx {
   bool bucket_attr_set = false;
   bool bucket_used = false;                // a ranking of the current call went through the bucket sort
   bool force_lsd = false;                  // retry after an overflow: radix sort only
+  // the gallery operand the last dvl_shard_topk prepared (DVL_FLAG_REUSE_GALLERY)
+  Operands prepared_gallery = {};
+  int64_t prepared_n = 0;
+  int prepared_d = 0, prepared_precision = 0;
+  uint32_t prepared_flags = 0;
+  bool prepared_valid = false;
   bool radix_only = false;                 // DVL_FLAG_RADIX_SORT of the current call
   bool graph_bucket = false;               // the captured graph contains bucket-sort kernels
   bool select_attr_set = false;

@@ -151,7 +151,8 @@ def speculative_list_len(top_n: int, rows_per_shard: int, n_global: int) -> int:
 
 
 def _dense_rerank(ctx, comm, gallery_local: torch.Tensor, labels_local_u8: torch.Tensor, queries_sel: torch.Tensor,
-                  n_global: int, n_classes: int, top_n: int, precision: int, flags: int, ranked_cap: int):
+                  n_global: int, n_classes: int, top_n: int, precision: int, flags: int, ranked_cap: int,
+                  gallery_prepared: bool = False):
     """Exact ranking of a (small) set of queries over the whole sharded gallery by the full-sort route: every rank
     computes the dense scores of its shard, the score rows and the labels are all-gathered (contiguous row blocks,
     so concatenating the shards IS the gallery order) and ranked with ``dvl_rank_and_score``.  Used for the queries
@@ -174,7 +175,9 @@ def _dense_rerank(ctx, comm, gallery_local: torch.Tensor, labels_local_u8: torch
         f = fq.shape[0]
         local_scores = torch.zeros((f, rows_blk), dtype=torch.float32, device=dev)
         if n_local:
-            local_scores[:, :n_local] = ctx.similarity(gallery_local, fq, precision, flags)
+            # right after shard_topk on the same, untouched shard its operand planes are still in the context
+            reuse = _capi.FLAG_REUSE_GALLERY if (gallery_prepared and b0 == 0) else 0
+            local_scores[:, :n_local] = ctx.similarity(gallery_local, fq, precision, flags | reuse)
         all_scores = comm.all_gather(local_scores)          # [world, F, rows_blk]
         full = all_scores.permute(1, 0, 2).reshape(f, -1)[:, :n_global].contiguous()
         rr = ctx.rank_and_score(full, all_labels, n_classes, top_n, ranked_cap)
@@ -343,7 +346,7 @@ def evaluate_sharded(ctx, comm, gallery_local: torch.Tensor, queries: torch.Tens
         flagged = torch.nonzero(flag_mask).reshape(-1)
         n_flagged = int(flagged.numel())
         rr = _dense_rerank(ctx, comm, gallery_local, labels_local_u8, queries[flagged].contiguous(), n_global, n_classes,
-                           top_n, precision, flags, ranked_cap)
+                           top_n, precision, flags, ranked_cap, gallery_prepared=have_rows and not host_inputs)
         per_query[flagged] = rr["per_query"]
         ranked_len[flagged] = rr["ranked_len"]
         if ranked_cap:

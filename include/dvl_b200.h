@@ -76,6 +76,10 @@ typedef enum dvl_precision { DVL_PRECISION_FP32 = 0, DVL_PRECISION_BF16 = 1, DVL
 #define DVL_FLAG_RADIX_SORT        0x20u /* full-sort route: rank with the stable LSD radix sort (segsort.cu) instead
                                            of the score-linear bucket sort (bucketsort.cu) that is tried first;
                                            same results, used for A/B measurements and tests */
+#define DVL_FLAG_REUSE_GALLERY     0x40u /* dvl_similarity only: `gallery` is the matrix the preceding dvl_shard_topk on this
+                                           context prepared, unchanged since (the caller vouches for it): its
+                                           conversion into tensor-core operands is not repeated.  Used by the exact
+                                           re-rank of flagged queries on the sharded path */
 #define DVL_FLAG_STREAM_TOPK       0x8u /* force the streaming top-k route even on a small gallery
                                            (chunks of N/4 rows); needs top_n < N and top_n <= 8192 */
 
