@@ -173,3 +173,23 @@ print("RESULT" + json.dumps(out))
         assert p.returncode == 0, p.stderr[-2000:]
         results.append(json.loads([ln for ln in p.stdout.splitlines() if ln.startswith("RESULT")][0][6:]))
     assert results[0] == results[1]
+
+
+def test_more_segments_than_one_grid_dimension_holds(ctx):
+    """70,000 queries (more than the 65,535 a grid's y dimension takes: the launches are split): every query is one
+    of seven score rows, so its result must equal that row's -- which is checked against the oracle."""
+    n, q, c = 300, 70_000, 3
+    rng = np.random.RandomState(12)
+    base = (rng.standard_normal((7, n)) * 0.5).astype(np.float32)
+    base[3, ::4] = 0.25                                   # some exact ties
+    which = rng.randint(0, 7, size=q)
+    which[:7] = np.arange(7)
+    scores = torch.from_numpy(base).cuda()[torch.from_numpy(which).cuda()].contiguous()
+    labels = synthetic.make_labels(n, c, 8)
+    lab = torch.from_numpy(labels.astype(np.uint8)).cuda()
+    for top_n in (n, 40):
+        want, _ = spec.eval_scores_matrix(base, labels, top_n)
+        res = ctx.rank_and_score(scores, lab, c, top_n)
+        got = res["per_query"]
+        assert np.abs(got[:7].cpu().numpy() - want).max() <= 1e-12
+        assert torch.equal(got, got[:7][torch.from_numpy(which).cuda()])
