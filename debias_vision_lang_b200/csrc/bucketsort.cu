@@ -324,6 +324,9 @@ partition_body(const uint32_t* __restrict__ keys, int64_t ldk, int64_t n, const 
     }
   }
   __syncthreads();
+  // (Copying whole runs, one warp per bucket, so that the bucket and its storage offset are warp-uniform and the
+  // bucket byte per staged entry disappears, was measured: 0.1325 instead of 0.125 ms -- runs of ~77 entries leave
+  // 40 % of the lanes idle in their last iteration.)
   unsigned long long* out = store + (int64_t)q * n_buckets * kBucketCap;
 #pragma unroll 4
   for (int p = tid; p < count; p += kPartThreads) {
