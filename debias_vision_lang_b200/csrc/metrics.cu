@@ -35,6 +35,7 @@ namespace {
 
 constexpr int kSub = 1024;            // ranked rows per warp-sized sub-slice
 constexpr int kWarpsPerCta = 4;
+constexpr int kQueriesPerCta = 8;     // ndkl_partial_kernel: the warps of a CTA take the SAME sub-slice of different queries
 constexpr double kLn2 = 0.693147180559945309417232121458176568;
 
 // ---- tables ------------------------------------------------------------------------------
@@ -240,6 +241,7 @@ struct PartialParams {
   int64_t ldl;
   const int32_t* ranked_len;
   int subs;
+  int qn;                                 // queries of this launch
   int64_t n_gallery;
   const uint32_t* sub_pref;               // [q][subs+1][16] exclusive prefixes (+ totals)
   const unsigned long long* class_counts; // global n_c
@@ -255,11 +257,14 @@ struct PartialParams {
 // own-class prefix count of a row -- the only thing NDKL needs from the ranking -- costs a field
 // extract instead of a ballot per class.  The running per-class base of the warp lives in shared
 // memory (it is indexed by the label).
+// The warps of a CTA work on the same sub-slice of kQueriesPerCta consecutive queries: their PWI rows are
+// the same addresses and their DXL gathers (t ~ rank x class share) cluster, so both tables are served
+// from L1 instead of once per warp from L2.
 template <int C>
-__global__ void __launch_bounds__(32 * kWarpsPerCta) ndkl_partial_kernel(const PartialParams p) {
+__global__ void __launch_bounds__(32 * kQueriesPerCta) ndkl_partial_kernel(const PartialParams p) {
   constexpr int W = (C + 7) / 8;
   __shared__ double ln_d[kMaxClasses];
-  __shared__ uint32_t s_base[kWarpsPerCta][kMaxClasses];
+  __shared__ uint32_t s_base[kQueriesPerCta][kMaxClasses];
   if (threadIdx.x < kMaxClasses) {
     double v = 0.0;
     if (threadIdx.x < C) {
@@ -270,11 +275,11 @@ __global__ void __launch_bounds__(32 * kWarpsPerCta) ndkl_partial_kernel(const P
     ln_d[threadIdx.x] = v;
   }
   __syncthreads();
-  const int q = blockIdx.y;
   const int warp = threadIdx.x >> 5;
-  const int sub = blockIdx.x * kWarpsPerCta + warp;
+  const int q = blockIdx.y * kQueriesPerCta + warp;
+  const int sub = blockIdx.x;
   const int lane = threadIdx.x & 31;
-  if (sub >= p.subs) return;
+  if (q >= p.qn) return;
   const long long m = p.ranked_len[q];
   const long long begin = (long long)sub * kSub;
   long long end = begin + kSub;
@@ -409,7 +414,8 @@ void launch_counts_and_partials(const PartialParams& p, dim3 grid, int stride, u
   if (counts)
     sub_counts_kernel<C><<<grid, 32 * kWarpsPerCta, 0, st>>>(p.labs, p.ldl, p.ranked_len, p.subs, stride, sub_cnt_q);
   else
-    ndkl_partial_kernel<C><<<grid, 32 * kWarpsPerCta, 0, st>>>(p);
+    ndkl_partial_kernel<C><<<dim3((unsigned)p.subs, (unsigned)((p.qn + kQueriesPerCta - 1) / kQueriesPerCta)),
+                             32 * kQueriesPerCta, 0, st>>>(p);
 }
 
 void dispatch_classes(int n_classes, const PartialParams& p, dim3 grid, int stride, uint32_t* sub_cnt_q, bool counts,
@@ -580,6 +586,7 @@ int launch_metrics(Ctx* c, const MetricArgs& a, cudaStream_t st) {
       p.ldl = a.ldl;
       p.ranked_len = a.ranked_len + q0;
       p.subs = subs;
+      p.qn = qn;
       p.n_gallery = a.n_gallery;
       p.sub_pref = sub_cnt + (int64_t)q0 * (subs + 1) * kMaxClasses;
       p.class_counts = a.class_counts;
