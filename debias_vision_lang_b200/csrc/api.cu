@@ -454,6 +454,7 @@ struct StreamPlan {
 // ~2.8 top_n survivors per query at top_n = 1000 of 1.25 M rows; 65536 rows left ~1.7 top_n but cost
 // 5 % of the similarity work on config 4.
 constexpr int64_t kPilotRows = 16384;
+constexpr int64_t kPilotRowsMin = 4096;     // a sample this small is scored densely: no seed / filter split
 
 bool plan_stream(int64_t n, int q, int64_t top_n, uint32_t flags, StreamPlan* plan, bool shard = false) {
   if (top_n > 8192) return false;
@@ -482,7 +483,14 @@ bool plan_stream(int64_t n, int q, int64_t top_n, uint32_t flags, StreamPlan* pl
   // progressive scheme's few chunks are cheaper than a pilot pass.  The mid range matters for shards: 125 k rows
   // per GPU (config 3 on 8 GPUs) took five GEMM launches and five selects progressively, three of each with a pilot.
   if (!(flags & DVL_FLAG_NO_PILOT) && n >= 4 * kPilotRows && top_n < n / 8) {
-    const int64_t step = n / kPilotRows;
+    // sample size: 1/32 of the gallery between kPilotRowsMin and kPilotRows.  A 125 k-row shard (config 3 on 8
+    // GPUs) spent a third of its local time on a 16 k-row pilot (seed GEMM, select, filter GEMM, select: 121 us
+    // next to the 192 us main pass); 4 k rows are one dense seed launch + one select and leave ~2.0 top_n
+    // survivors instead of ~1.4.
+    int64_t sample = n / 32;
+    if (sample < kPilotRowsMin) sample = kPilotRowsMin;
+    if (sample > kPilotRows) sample = kPilotRows;
+    const int64_t step = (n + sample - 1) / sample;
     const int64_t n_view = (n + step - 1) / step;
     const double mu = (double)top_n * (double)n_view / (double)n;     // expected pilot rank of the top_n-th best
     const int64_t rank = (int64_t)ceil(mu + 4.0 * sqrt(mu + 4.0) + 8.0);
@@ -572,7 +580,7 @@ int stream_topk(Ctx* c, const Operands& op, const uint8_t* labels, int64_t n, in
     // 0.35 ms of candidate writes + 0.29 ms of selection at Q = 10^4; 512 rows a tenth of that).
     int64_t seed_rows = round_up(4 * plan.pilot_rank > 512 ? 4 * plan.pilot_rank : 512, 256);
     if (seed_rows > plan.chunk0) seed_rows = plan.chunk0;
-    if (seed_rows > n_view) seed_rows = n_view;
+    if (seed_rows > n_view || n_view <= kPilotRowsMin) seed_rows = n_view;
     DVL_TRY(launch_topk_reset(c, cnt, tau, cflags, q, (uint32_t)seed_rows, true, st));
     DVL_TRY(gemm_launch(kGemmSeed, 0, seed_rows, n_view, plan.pilot_step));
     if (seed_rows < n_view) {

@@ -48,6 +48,7 @@ struct SelectParams {
   int64_t trigger;          // skip (non-final) while the list is shorter than this
   int final_pass;
   int pilot_pass;
+  int rank_sort;            // final pass: the launch carries the shared memory of counting_rank_sort
   int64_t rows_total;
   // final outputs
   unsigned long long* sorted_out;   // [q][sort_cap] or null (defaults to in place for segs == 1)
@@ -125,6 +126,128 @@ __device__ __forceinline__ void bitonic_sort_regs(unsigned long long* buf, int t
 #pragma unroll
   for (int j = 0; j < E; ++j) buf[tid * E + j] = v[j];
   __syncthreads();
+}
+
+// ---- final ordering of a kept list without the bitonic network ----
+// The kept entries of a query are a few thousand scores from one smooth tail.  Like the second level of
+// bucketsort.cu: a score-linear split of [best, worst] into kSelBins sub-bins (counting sort, ~1 entry per
+// sub-bin), then every entry ranks itself among the entries of its own sub-bin by its full (key, index) value.
+// ~1/3 of the instructions of the 55..66-stage bitonic sort of 1024..2048 u64 entries.  Exact for the same
+// reason: score -> sub-bin is monotone, so entries of different sub-bins are ordered by the sub-bin, and equal
+// keys share one.  Returns false (list untouched) when a sub-bin is crowded -- heavy exact ties, e.g. scores
+// on a coarse grid -- and the caller sorts bitonically as before.
+constexpr int kSelBins = 2048;               // 8 consecutive sub-bins per thread
+constexpr int kSelGroupMax = 48;
+
+__device__ __forceinline__ float sel_key_score(uint32_t k) {   // score of a non-NaN key
+  return __uint_as_float(k ^ (~(uint32_t)((int32_t)k >> 31) & 0x7FFFFFFFu));
+}
+
+__device__ __forceinline__ uint32_t sel_subbin(uint32_t k, float hi, float scale) {
+  // (hi - s) * scale truncated with saturation (negative, NaN -> 0), capped; NaN keys (dropped rows) go last
+  const uint32_t sb = min(__float2uint_rz((hi - sel_key_score(k)) * scale), (uint32_t)(kSelBins - 1));
+  return k == kNanKey ? (uint32_t)(kSelBins - 1) : sb;
+}
+
+__device__ bool counting_rank_sort(unsigned long long* list, uint32_t kept, uint8_t* extra, int sort_cap, int tid) {
+  uint32_t* s_key = reinterpret_cast<uint32_t*>(extra);           // [sort_cap]
+  uint32_t* s_val = s_key + sort_cap;                             // [sort_cap]
+  uint32_t* bins = s_val + sort_cap;                              // [kSelBins]
+  uint16_t* arr = reinterpret_cast<uint16_t*>(bins + kSelBins);   // [sort_cap] arrival order inside the sub-bin
+  __shared__ uint32_t red_min[kSelThreads / 32], red_max[kSelThreads / 32], warp_tot[kSelThreads / 32];
+  __shared__ uint32_t sh_big;
+  const int lane = tid & 31, warp = tid >> 5;
+  reinterpret_cast<uint4*>(bins)[2 * tid] = make_uint4(0u, 0u, 0u, 0u);
+  reinterpret_cast<uint4*>(bins)[2 * tid + 1] = make_uint4(0u, 0u, 0u, 0u);
+  if (tid == 0) sh_big = 0u;
+  uint32_t kmin = 0xFFFFFFFFu, kmax = 0u;                         // over the keys of real scores
+  for (uint32_t i = tid; i < kept; i += kSelThreads) {
+    const uint32_t k = (uint32_t)(list[i] >> 32);
+    kmin = min(kmin, k);
+    kmax = max(kmax, k == kNanKey ? 0u : k);
+  }
+  kmin = __reduce_min_sync(0xffffffffu, kmin);
+  kmax = __reduce_max_sync(0xffffffffu, kmax);
+  if (lane == 0) { red_min[warp] = kmin; red_max[warp] = kmax; }
+  __syncthreads();
+#pragma unroll
+  for (int w = 0; w < kSelThreads / 32; ++w) {
+    kmin = min(kmin, red_min[w]);
+    kmax = max(kmax, red_max[w]);
+  }
+  float hi = 0.0f, scale = 0.0f;
+  if (kmax > kmin) {                                              // two distinct real scores; +-inf ends clamped
+    hi = fminf(sel_key_score(kmin), 3.4028234664e38f);
+    const float lo = fmaxf(sel_key_score(kmax), -3.4028234664e38f);
+    if (hi > lo) scale = (float)kSelBins / (hi - lo);
+  }
+  if (!(scale <= 3.4028234664e38f)) scale = 0.0f;
+  for (uint32_t i = tid; i < kept; i += kSelThreads) {
+    const uint32_t k = (uint32_t)(list[i] >> 32);
+    arr[i] = (uint16_t)atomicAdd(&bins[sel_subbin(k, hi, scale)], 1u);
+  }
+  __syncthreads();
+  {
+    // exclusive prefix over the sub-bins, written back as start | size << 16 (both <= 4096)
+    const uint4 v0 = reinterpret_cast<const uint4*>(bins)[2 * tid];
+    const uint4 v1 = reinterpret_cast<const uint4*>(bins)[2 * tid + 1];
+    const uint32_t cnt8[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+    uint32_t start[8];
+    uint32_t sum = 0, mx = 0;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      start[j] = sum;
+      sum += cnt8[j];
+      mx = max(mx, cnt8[j]);
+    }
+    uint32_t incl = sum;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+      const uint32_t o = __shfl_up_sync(0xffffffffu, incl, off);
+      if (lane >= off) incl += o;
+    }
+    if (lane == 31) warp_tot[warp] = incl;
+    if (mx > (uint32_t)kSelGroupMax) sh_big = 1u;
+    __syncthreads();
+    if (sh_big != 0u) return false;                               // uniform: every thread reads it after the barrier
+    uint32_t base = incl - sum;
+#pragma unroll
+    for (int w = 0; w < kSelThreads / 32; ++w) base += (w < warp) ? warp_tot[w] : 0u;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) start[j] = (start[j] + base) | (cnt8[j] << 16);
+    reinterpret_cast<uint4*>(bins)[2 * tid] = make_uint4(start[0], start[1], start[2], start[3]);
+    reinterpret_cast<uint4*>(bins)[2 * tid + 1] = make_uint4(start[4], start[5], start[6], start[7]);
+  }
+  __syncthreads();
+  for (uint32_t i = tid; i < kept; i += kSelThreads) {
+    const unsigned long long e = list[i];
+    const uint32_t k = (uint32_t)(e >> 32);
+    const uint32_t dst = (bins[sel_subbin(k, hi, scale)] & 0xFFFFu) + arr[i];
+    s_key[dst] = k;
+    s_val[dst] = (uint32_t)e;
+  }
+  __syncthreads();
+  for (uint32_t d = tid; d < kept; d += kSelThreads) {
+    const uint32_t k = s_key[d], v = s_val[d];
+    const uint32_t w = bins[sel_subbin(k, hi, scale)];
+    const uint32_t s0 = w & 0xFFFFu, g = w >> 16, last = s0 + g - 1u;
+    uint32_t rank = s0;
+#pragma unroll
+    for (uint32_t j = 0; j < 4u; ++j) {                           // the first four candidates without a loop
+      const uint32_t at = min(s0 + j, last);
+      const uint32_t kk = s_key[at];
+      bool first = kk < k;
+      if (kk == k) first = s_val[at] < v;                         // itself, or an exact tie: the gallery index decides
+      rank += (j < g && first) ? 1u : 0u;
+    }
+    for (uint32_t j = 4u; j < g; ++j) {
+      const uint32_t kk = s_key[s0 + j];
+      rank += (kk < k || (kk == k && s_val[s0 + j] < v)) ? 1u : 0u;
+    }
+    list[rank] = ((unsigned long long)k << 32) | v;
+  }
+  __syncthreads();
+  return true;
 }
 
 __global__ void __launch_bounds__(kSelThreads) select_kernel(const SelectParams p) {
@@ -278,7 +401,9 @@ __global__ void __launch_bounds__(kSelThreads) select_kernel(const SelectParams 
   uint32_t pow2 = 1;
   while (pow2 < kept) pow2 <<= 1;
   const uint32_t n_sort = pow2 <= 4u * kSelThreads ? 4u * kSelThreads : 8u * kSelThreads;
-  if (pow2 <= n_sort && (uint32_t)p.sort_cap >= n_sort) {
+  if (p.rank_sort && counting_rank_sort(sm_list, kept, reinterpret_cast<uint8_t*>(sm_list + p.sort_cap), p.sort_cap, tid)) {
+    // ordered by sub-bin + in-bin rank
+  } else if (pow2 <= n_sort && (uint32_t)p.sort_cap >= n_sort) {
     // up to 2048 entries (top_n <= ~1000 with its ties, the usual case): registers + warp shuffles
     for (uint32_t i = kept + tid; i < n_sort; i += kSelThreads) sm_list[i] = ~0ull;
     __syncthreads();
@@ -545,8 +670,15 @@ int launch_select(Ctx* c, const SelectArgs& a, cudaStream_t st) {
   p.q_offset = a.q_offset;
   p.labels = a.labels;
   p.index_base = a.index_base;
-  const size_t smem = (size_t)a.sort_cap * sizeof(unsigned long long);
-  if (smem > 48 * 1024 && !c->select_attr_set) {
+  size_t smem = (size_t)a.sort_cap * sizeof(unsigned long long);
+  // final pass of a list of <= 4096 entries: ordered by counting_rank_sort, which needs a second list + its sub-bins
+  static const bool bitonic_only = [] {
+    const char* e = getenv("DVL_SELECT_BITONIC");
+    return e != nullptr && e[0] == '1';
+  }();
+  p.rank_sort = (a.final_pass && a.sort_cap <= 4096 && !bitonic_only) ? 1 : 0;
+  if (p.rank_sort) smem += (size_t)a.sort_cap * 8 + (size_t)kSelBins * 4 + (size_t)a.sort_cap * 2;
+  if (!c->select_attr_set) {
     DVL_CUDA(c, cudaFuncSetAttribute(select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 16384 * 8));
     c->select_attr_set = true;
   }
