@@ -292,14 +292,13 @@ class Context:
 
     # ---- gallery-sharded stages (see sharded.py) -------------------------------------------
     def shard_topk(self, gallery: torch.Tensor, queries: torch.Tensor, labels_u8: torch.Tensor, index_base: int,
-                   n_classes: int, top_n: int, precision: int = PRECISION_FP32, flags: int = 0):
+                   n_classes: int, top_n: int, precision: int = PRECISION_FP32, flags: int = 0, outputs: bool = True):
+        """``outputs=False``: no copies of tau / flags / label counts (the lean exchange reads them from the
+        context with ``shard_stats``); returns ``(None, None, None, list_cap)``."""
         assert gallery.is_cuda and gallery.is_contiguous() and queries.is_contiguous() and labels_u8.dtype == torch.uint8
         n_local, d = gallery.shape
         q = queries.shape[0]
-        dev = gallery.device
-        tau = torch.empty((q,), dtype=torch.float32, device=dev)
-        oflags = torch.empty((q,), dtype=torch.int32, device=dev)
-        counts = torch.empty((MAX_CLASSES + 1,), dtype=torch.int64, device=dev)
+        tau, oflags, counts = self._shard_outputs(q, gallery.device, outputs)
         cap = ctypes.c_int32(0)
         rc = lib().dvl_shard_topk(self._h, self._ptr(gallery), _dtype_code(gallery.dtype), self._ptr(queries),
                                   _dtype_code(queries.dtype), self._ptr(labels_u8), n_local, int(index_base), d, q,
@@ -309,8 +308,16 @@ class Context:
         self._check(rc)
         return tau, oflags, counts, int(cap.value)
 
+    @staticmethod
+    def _shard_outputs(q: int, dev, outputs: bool):
+        if not outputs:
+            return None, None, None
+        return (torch.empty((q,), dtype=torch.float32, device=dev), torch.empty((q,), dtype=torch.int32, device=dev),
+                torch.empty((MAX_CLASSES + 1,), dtype=torch.int64, device=dev))
+
     def shard_topk_host(self, gallery: torch.Tensor, queries: torch.Tensor, labels_u8: torch.Tensor, index_base: int,
-                        n_classes: int, top_n: int, precision: int = PRECISION_FP32, flags: int = 0):
+                        n_classes: int, top_n: int, precision: int = PRECISION_FP32, flags: int = 0,
+                        outputs: bool = True):
         """``shard_topk`` with HOST tensors (pinned for an asynchronous, overlapped upload): the gallery shard
         travels in row blocks on the context's copy stream while the blocks that have landed are already
         being scored and filtered."""
@@ -319,10 +326,7 @@ class Context:
         assert labels_u8.dtype == torch.uint8
         n_local, d = gallery.shape
         q = queries.shape[0]
-        dev = torch.device("cuda", self.device)
-        tau = torch.empty((q,), dtype=torch.float32, device=dev)
-        oflags = torch.empty((q,), dtype=torch.int32, device=dev)
-        counts = torch.empty((MAX_CLASSES + 1,), dtype=torch.int64, device=dev)
+        tau, oflags, counts = self._shard_outputs(q, torch.device("cuda", self.device), outputs)
         cap = ctypes.c_int32(0)
         rc = lib().dvl_shard_topk_host(self._h, self._ptr(gallery), _dtype_code(gallery.dtype), self._ptr(queries),
                                        _dtype_code(queries.dtype), self._ptr(labels_u8), n_local, int(index_base), d, q,

@@ -1209,10 +1209,13 @@ int shard_topk_impl(dvl_ctx* c, const void* gallery, int gdt, const void* querie
   c->prepared_precision = precision;
   c->prepared_flags = flags & DVL_FLAG_NORMALIZE_GALLERY;
   c->prepared_valid = true;
-  DVL_CUDA(c, cudaMemcpyAsync(out_tau, c->cand_tau.ptr, (size_t)q * 4, cudaMemcpyDeviceToDevice, st));
-  DVL_CUDA(c, cudaMemcpyAsync(out_flags, c->cand_flags.ptr, (size_t)q * 4, cudaMemcpyDeviceToDevice, st));
-  DVL_CUDA(c, cudaMemcpyAsync(out_class_counts, c->class_counts.ptr, sizeof(unsigned long long) * (kMaxClasses + 1),
-                              cudaMemcpyDeviceToDevice, st));
+  // optional: the lean exchange reads the same three things from the context (dvl_shard_stats)
+  if (out_tau != nullptr) DVL_CUDA(c, cudaMemcpyAsync(out_tau, c->cand_tau.ptr, (size_t)q * 4, cudaMemcpyDeviceToDevice, st));
+  if (out_flags != nullptr)
+    DVL_CUDA(c, cudaMemcpyAsync(out_flags, c->cand_flags.ptr, (size_t)q * 4, cudaMemcpyDeviceToDevice, st));
+  if (out_class_counts != nullptr)
+    DVL_CUDA(c, cudaMemcpyAsync(out_class_counts, c->class_counts.ptr, sizeof(unsigned long long) * (kMaxClasses + 1),
+                                cudaMemcpyDeviceToDevice, st));
   if (out_list_cap != nullptr) *out_list_cap = plan.sort_cap;
   return DVL_OK;    // stream-ordered: the outputs are consumed by collectives enqueued after this call
 }
@@ -1225,9 +1228,7 @@ DVL_API int dvl_shard_topk(dvl_ctx* c, const void* gallery, int gdt, const void*
                    int precision, uint32_t flags, float* out_tau, uint32_t* out_flags,
                    unsigned long long* out_class_counts, int32_t* out_list_cap, void* stream) {
   DVL_TRY(dvl::check_common(c, n_local, d, q, n_classes, top_n, precision, gdt, qdt));
-  if (gallery == nullptr || queries == nullptr || labels == nullptr || out_tau == nullptr || out_flags == nullptr ||
-      out_class_counts == nullptr)
-    return dvl::set_error(c, DVL_ERR_INVALID, "null pointer");
+  if (gallery == nullptr || queries == nullptr || labels == nullptr) return dvl::set_error(c, DVL_ERR_INVALID, "null pointer");
   dvl::DeviceGuard guard(c->device);
   return dvl::shard_topk_impl(c, gallery, gdt, queries, qdt, labels, n_local, index_base, d, q, n_classes, top_n,
                               precision, flags, out_tau, out_flags, out_class_counts, out_list_cap, (cudaStream_t)stream,
@@ -1241,8 +1242,7 @@ DVL_API int dvl_shard_topk_host(dvl_ctx* c, const void* gallery_host, int gdt, c
                         const void** out_gallery_dev, const void** out_queries_dev, const uint8_t** out_labels_dev,
                         void* stream) {
   DVL_TRY(dvl::check_common(c, n_local, d, q, n_classes, top_n, precision, gdt, qdt));
-  if (gallery_host == nullptr || queries_host == nullptr || labels_host == nullptr || out_tau == nullptr ||
-      out_flags == nullptr || out_class_counts == nullptr)
+  if (gallery_host == nullptr || queries_host == nullptr || labels_host == nullptr)
     return dvl::set_error(c, DVL_ERR_INVALID, "null pointer");
   dvl::DeviceGuard guard(c->device);
   cudaStream_t st = (cudaStream_t)stream;

@@ -292,7 +292,7 @@ def evaluate_sharded(ctx, comm, gallery_local: torch.Tensor, queries: torch.Tens
     # 1. local streaming top-k -> this rank's statistics record -> reduced over the ranks
     if have_rows:
         local_topk = ctx.shard_topk_host if host_inputs else ctx.shard_topk
-        local_topk(gallery_local, queries, labels_local_u8, index_base, n_classes, top_n, precision, flags)
+        local_topk(gallery_local, queries, labels_local_u8, index_base, n_classes, top_n, precision, flags, outputs=False)
         ctx.shard_stats(bufs.stats_send)
     else:
         bufs.stats_send.zero_()
@@ -317,9 +317,16 @@ def evaluate_sharded(ctx, comm, gallery_local: torch.Tensor, queries: torch.Tens
         comm.all_gather_into(bufs.rec_all, bufs.rec_send)          # [world, rec_bytes]
         if ranked_cap:
             comm.all_gather_into(bufs.idx_all, bufs.idx_send)
-        return ctx.shard_finish(bufs.rec_all, bufs.block, q)       # the path's host synchronisation
+        # the caller's copies of the per-query results (the buffers are reused by the next call) are enqueued
+        # BEFORE the synchronisation: the host prepares them while the device is still busy, instead of after
+        # it has gone idle
+        block = bufs.block
+        copies = (bufs.column(0, 32 * block, torch.float64, q).clone(),
+                  bufs.column(32 * block, 36 * block, torch.int32, q).clone(),
+                  bufs.idx_all.reshape(-1, ranked_cap)[:q].clone() if ranked_cap else None)
+        return ctx.shard_finish(bufs.rec_all, bufs.block, q), copies      # the path's host synchronisation
 
-    mean, (any_flag, bad_label, need_max) = exchange_and_merge(bufs)
+    (mean, (any_flag, bad_label, need_max)), copies = exchange_and_merge(bufs)
     if bad_label:
         raise _capi.DvlError(-1, f"a label is >= n_classes ({n_classes})")
     if need_max > length:
@@ -330,11 +337,9 @@ def evaluate_sharded(ctx, comm, gallery_local: torch.Tensor, queries: torch.Tens
         stats_all = bufs.stats_all
         bufs = _bufs_for(ctx, dev, q, world, length, ranked_cap)
         bufs.stats_all.copy_(stats_all)
-        mean, (any_flag, bad_label, need_max) = exchange_and_merge(bufs)
+        (mean, (any_flag, bad_label, need_max)), copies = exchange_and_merge(bufs)
     block = bufs.block
-    per_query = bufs.column(0, 32 * block, torch.float64, q).clone()
-    ranked_len = bufs.column(32 * block, 36 * block, torch.int32, q).clone()
-    ranked_idx = bufs.idx_all.reshape(-1, ranked_cap)[:q].clone() if ranked_cap else None
+    per_query, ranked_len, ranked_idx = copies
     n_flagged = 0
     # exact re-rank of flagged queries (tie run longer than a candidate list); rare
     if any_flag:

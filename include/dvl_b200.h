@@ -225,9 +225,10 @@ DVL_API int dvl_similarity(dvl_ctx* ctx,
 DVL_API int dvl_shard_topk(dvl_ctx* ctx, const void* gallery, int gallery_dtype, const void* queries, int query_dtype,
                            const uint8_t* labels, int64_t n_local, int64_t index_base, int32_t d, int32_t q,
                            int32_t n_classes, int64_t top_n, int precision, uint32_t flags,
-                           float* out_tau /* dev [q] */, uint32_t* out_flags /* dev [q] */,
-                           unsigned long long* out_class_counts /* dev [17] */, int32_t* out_list_cap /* host */,
-                           void* stream);
+                           float* out_tau /* dev [q] or NULL */, uint32_t* out_flags /* dev [q] or NULL */,
+                           unsigned long long* out_class_counts /* dev [17] or NULL */, int32_t* out_list_cap /* host */,
+                           void* stream);      /* the three device outputs are optional: dvl_shard_stats packs the same
+                                                  values from the context */
 /* dvl_shard_topk with HOST inputs (the shard as the embedding cache or the encoders' host copy holds it):
  * queries and labels are copied first, the gallery shard follows in row blocks on the context's copy
  * stream, and the operand split + similarity + threshold filter of a block start as soon as the block
@@ -237,9 +238,9 @@ DVL_API int dvl_shard_topk(dvl_ctx* ctx, const void* gallery, int gallery_dtype,
 DVL_API int dvl_shard_topk_host(dvl_ctx* ctx, const void* gallery_host, int gallery_dtype, const void* queries_host,
                                 int query_dtype, const uint8_t* labels_host, int64_t n_local, int64_t index_base,
                                 int32_t d, int32_t q, int32_t n_classes, int64_t top_n, int precision, uint32_t flags,
-                                float* out_tau /* dev [q] */, uint32_t* out_flags /* dev [q] */,
-                                unsigned long long* out_class_counts /* dev [17] */, int32_t* out_list_cap /* host */,
-                                const void** out_gallery_dev, const void** out_queries_dev,
+                                float* out_tau /* dev [q] or NULL */, uint32_t* out_flags /* dev [q] or NULL */,
+                                unsigned long long* out_class_counts /* dev [17] or NULL */,
+                                int32_t* out_list_cap /* host */, const void** out_gallery_dev, const void** out_queries_dev,
                                 const uint8_t** out_labels_dev, void* stream);
 DVL_API int dvl_shard_trim(dvl_ctx* ctx, const float* tau_bound /* dev [q] */, int32_t q, int32_t* out_cnt /* dev [q] */,
                            void* stream);

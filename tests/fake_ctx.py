@@ -35,7 +35,7 @@ class FakeCtx:
         self.list_cap = list_cap
         self.lists = None
 
-    def shard_topk(self, gallery, queries, labels_u8, index_base, n_classes, top_n, precision=0, flags=0):
+    def shard_topk(self, gallery, queries, labels_u8, index_base, n_classes, top_n, precision=0, flags=0, outputs=True):
         q = queries.shape[0]
         lab = labels_u8.numpy()
         tau = torch.full((q,), float("-inf"), dtype=torch.float32)
