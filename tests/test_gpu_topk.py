@@ -27,7 +27,11 @@ def _run(ctx, w, topn, flags, prec=_capi.PRECISION_FP32, cap=None):
 
 @pytest.mark.parametrize("n,d,q,c,topn,lim", [(6000, 64, 20, 2, 100, 127), (20000, 128, 40, 7, 1000, 15),
                                               (9000, 72, 130, 9, 37, 5), (40000, 256, 12, 2, 1000, 127),
-                                              (5000, 64, 3, 2, 1, 3)])
+                                              (5000, 64, 3, 2, 1, 3),
+                                              # coarse score grids: the kept list fits, its tie runs are ~200 rows (a
+                                              # crowded sub-bin: the select's counting sort hands over to the bitonic
+                                              # network) / ~35 rows (the in-bin ranking's loop beyond four candidates)
+                                              (30000, 32, 16, 2, 1000, 2), (60000, 64, 16, 2, 1000, 5)])
 def test_streaming_equals_full_sort_and_oracle(ctx, n, d, q, c, topn, lim):
     w = synthetic.dyadic_grid(n, d, q, c, seed=n + topn, lim=lim)
     stream = _run(ctx, w, topn, _capi.FLAG_STREAM_TOPK)
