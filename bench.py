@@ -266,6 +266,11 @@ def run_reference(args):
     if int(os.environ.get("RANK", "0")) != 0:
         return
     t_all = time.perf_counter()
+    # torchrun exports OMP_NUM_THREADS=1 to its workers; the reference arm is one process and takes every host core
+    try:
+        torch.set_num_threads(max(torch.get_num_threads(), len(os.sched_getaffinity(0))))
+    except (AttributeError, RuntimeError):
+        pass
     kind, run, what = cpu_arm()
     w, cut = cpu_workload(args.workload)
     cfg = config_of(args.workload)
