@@ -394,8 +394,8 @@ __device__ __forceinline__ uint32_t subbin_of(uint32_t k, float hi, float scale)
 }
 
 constexpr int kBinsPerThread = kSubBins / kSortThreads2;      // 8 consecutive sub-bins per thread
-// sub-bin sorted entries as two 32-bit arrays, sub-bins, arrival order (u16), ranked labels
-constexpr size_t kSortSmem = (size_t)kBucketCap * 8 + (size_t)kSubBins * 4 + (size_t)kBucketCap * 2 + kBucketCap;
+// sub-bin sorted entries as two 32-bit arrays, sub-bins (+ one sentinel word in front), ranked labels
+constexpr size_t kSortSmem = (size_t)kBucketCap * 8 + (size_t)(kSubBins + 4) * 4 + kBucketCap;
 
 // The kernel keeps nothing per entry in registers between its phases: every phase is a short strided loop over
 // the bucket that re-reads what it needs (the bucket's entries from L1/L2, the rest from shared memory).  An
@@ -528,14 +528,14 @@ __device__ __forceinline__ void fused_metrics(const BucketSortParams& p, int q, 
 }
 
 template <int W>
-__global__ void __launch_bounds__(kSortThreads2, 4) bucket_sort_kernel(const BucketSortParams p) {
+__global__ void __launch_bounds__(kSortThreads2, 5) bucket_sort_kernel(const BucketSortParams p) {
   extern __shared__ __align__(16) uint8_t smem_dyn[];
   // key | (index << 4 | label): the ranking compares keys and only looks at the index word of an equal key
   uint32_t* s_key = reinterpret_cast<uint32_t*>(smem_dyn);                           // [kBucketCap]
   uint32_t* s_val = s_key + kBucketCap;                                              // [kBucketCap]
-  uint32_t* bins = s_val + kBucketCap;                                               // [kSubBins]
-  uint16_t* s_arr = reinterpret_cast<uint16_t*>(bins + kSubBins);                    // [kBucketCap]
-  uint8_t* labs_s = reinterpret_cast<uint8_t*>(s_arr + kBucketCap);                  // [kBucketCap]
+  // bins[-1] = 0 is the end of "the sub-bin before the first"; the four words keep bins 16-byte aligned
+  uint32_t* bins = s_val + kBucketCap + 4;                                           // [kSubBins]
+  uint8_t* labs_s = reinterpret_cast<uint8_t*>(bins + kSubBins);                     // [kBucketCap]
   __shared__ uint32_t red_min[8], red_max[8];
   __shared__ uint32_t warp_tot[8];
   __shared__ uint32_t sh_big;
@@ -558,7 +558,7 @@ __global__ void __launch_bounds__(kSortThreads2, 4) bucket_sort_kernel(const Buc
   // 8 consecutive sub-bins per thread: zeroed and scanned by their owner
   reinterpret_cast<uint4*>(bins)[2 * tid] = make_uint4(0u, 0u, 0u, 0u);
   reinterpret_cast<uint4*>(bins)[2 * tid + 1] = make_uint4(0u, 0u, 0u, 0u);
-  if (tid == 0) sh_big = 0u;
+  if (tid == 0) { sh_big = 0u; bins[-1] = 0u; }
   const unsigned long long* src = p.store + ((int64_t)q * p.n_buckets + b) * kBucketCap;
 
   // ---- the bucket's score range: from the first-level cells it is made of; the two end buckets (which also
@@ -596,17 +596,18 @@ __global__ void __launch_bounds__(kSortThreads2, 4) bucket_sort_kernel(const Buc
   if (!(scale <= 3.4028234664e38f)) scale = 0.0f;
   __syncthreads();
 
-  // ---- counting sort over the sub-bins: the arrival order inside a sub-bin is arbitrary, resolved by the ranking
-  // (a planned bucket is 8 rounds of 256 entries: all its loads are in flight together -- the CTA's lifetime is
-  // a chain of memory round trips, and with two loads in flight this loop alone was four of them)
+  // ---- counting sort over the sub-bins: histogram (no value returned: reductions, not atomics), prefix, then
+  // every entry takes the next free slot of its sub-bin -- the order inside a sub-bin is arbitrary, the ranking
+  // resolves it.  (A planned bucket is 8 rounds of 256 entries: all its loads are in flight together -- the CTA's
+  // lifetime is a chain of memory round trips, and with two loads in flight this loop alone was four of them.)
 #pragma unroll 8
   for (int pos = tid; pos < count; pos += kSortThreads2) {
     const uint32_t k = (uint32_t)(__ldg(src + pos) >> 32);
-    s_arr[pos] = (uint16_t)atomicAdd(&bins[subbin_of(k, hi, scale)], 1u);
+    atomicAdd(&bins[subbin_of(k, hi, scale)], 1u);
   }
   __syncthreads();
   {
-    // exclusive prefix over the sub-bins; written back as start | size << 16 (both <= 4096)
+    // exclusive prefix over the sub-bins: bins[b] = first slot of sub-bin b (the scatter advances it to its end)
     const uint4 v0 = reinterpret_cast<const uint4*>(bins)[2 * tid];
     const uint4 v1 = reinterpret_cast<const uint4*>(bins)[2 * tid + 1];
     const uint32_t cnt8[kBinsPerThread] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
@@ -631,7 +632,7 @@ __global__ void __launch_bounds__(kSortThreads2, 4) bucket_sort_kernel(const Buc
 #pragma unroll
     for (int w = 0; w < 8; ++w) base += (w < warp) ? warp_tot[w] : 0u;
 #pragma unroll
-    for (int j = 0; j < kBinsPerThread; ++j) start[j] = (start[j] + base) | (cnt8[j] << 16);
+    for (int j = 0; j < kBinsPerThread; ++j) start[j] += base;
     reinterpret_cast<uint4*>(bins)[2 * tid] = make_uint4(start[0], start[1], start[2], start[3]);
     reinterpret_cast<uint4*>(bins)[2 * tid + 1] = make_uint4(start[4], start[5], start[6], start[7]);
   }
@@ -640,7 +641,7 @@ __global__ void __launch_bounds__(kSortThreads2, 4) bucket_sort_kernel(const Buc
   for (int pos = tid; pos < count; pos += kSortThreads2) {
     const unsigned long long e = __ldg(src + pos);     // second read: L1 / L2
     const uint32_t k = (uint32_t)(e >> 32);
-    const uint32_t dst = (bins[subbin_of(k, hi, scale)] & 0xFFFFu) + s_arr[pos];
+    const uint32_t dst = atomicAdd(&bins[subbin_of(k, hi, scale)], 1u);
     s_key[dst] = k;
     s_val[dst] = (uint32_t)e;
   }
@@ -653,8 +654,9 @@ __global__ void __launch_bounds__(kSortThreads2, 4) bucket_sort_kernel(const Buc
 #pragma unroll 2
     for (int d = tid; d < count; d += kSortThreads2) {
       const uint32_t k = s_key[d], v = s_val[d];
-      const uint32_t w = bins[subbin_of(k, hi, scale)];
-      const uint32_t s0 = w & 0xFFFFu, g = w >> 16, last = s0 + g - 1u;
+      const uint32_t sb = subbin_of(k, hi, scale);
+      const uint32_t s0 = bins[(int)sb - 1], end = bins[sb];     // after the scatter bins[b] is the END of sub-bin b
+      const uint32_t g = end - s0, last = end - 1u;
       uint32_t rank = s0;
 #pragma unroll
       for (uint32_t j = 0; j < 4u; ++j) {
