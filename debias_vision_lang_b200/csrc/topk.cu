@@ -48,7 +48,8 @@ struct SelectParams {
   int64_t trigger;          // skip (non-final) while the list is shorter than this
   int final_pass;
   int pilot_pass;
-  int rank_sort;            // final pass: the launch carries the shared memory of counting_rank_sort
+  int rank_sort;            // final pass: the launch carries the shared memory of counting_rank_sort (1), and
+                            // selection + ordering run fused (2)
   int64_t rows_total;
   // final outputs
   unsigned long long* sorted_out;   // [q][sort_cap] or null (defaults to in place for segs == 1)
@@ -152,14 +153,13 @@ __device__ __forceinline__ uint32_t sel_subbin(uint32_t k, float hi, float scale
 __device__ bool counting_rank_sort(unsigned long long* list, uint32_t kept, uint8_t* extra, int sort_cap, int tid) {
   uint32_t* s_key = reinterpret_cast<uint32_t*>(extra);           // [sort_cap]
   uint32_t* s_val = s_key + sort_cap;                             // [sort_cap]
-  uint32_t* bins = s_val + sort_cap;                              // [kSelBins]
-  uint16_t* arr = reinterpret_cast<uint16_t*>(bins + kSelBins);   // [sort_cap] arrival order inside the sub-bin
+  uint32_t* bins = s_val + sort_cap + 4;                          // [kSelBins]; bins[-1] = 0 (16-byte aligned)
   __shared__ uint32_t red_min[kSelThreads / 32], red_max[kSelThreads / 32], warp_tot[kSelThreads / 32];
   __shared__ uint32_t sh_big;
   const int lane = tid & 31, warp = tid >> 5;
   reinterpret_cast<uint4*>(bins)[2 * tid] = make_uint4(0u, 0u, 0u, 0u);
   reinterpret_cast<uint4*>(bins)[2 * tid + 1] = make_uint4(0u, 0u, 0u, 0u);
-  if (tid == 0) sh_big = 0u;
+  if (tid == 0) { sh_big = 0u; bins[-1] = 0u; }
   uint32_t kmin = 0xFFFFFFFFu, kmax = 0u;                         // over the keys of real scores
   for (uint32_t i = tid; i < kept; i += kSelThreads) {
     const uint32_t k = (uint32_t)(list[i] >> 32);
@@ -184,11 +184,11 @@ __device__ bool counting_rank_sort(unsigned long long* list, uint32_t kept, uint
   if (!(scale <= 3.4028234664e38f)) scale = 0.0f;
   for (uint32_t i = tid; i < kept; i += kSelThreads) {
     const uint32_t k = (uint32_t)(list[i] >> 32);
-    arr[i] = (uint16_t)atomicAdd(&bins[sel_subbin(k, hi, scale)], 1u);
+    atomicAdd(&bins[sel_subbin(k, hi, scale)], 1u);               // histogram: no value returned
   }
   __syncthreads();
   {
-    // exclusive prefix over the sub-bins, written back as start | size << 16 (both <= 4096)
+    // exclusive prefix over the sub-bins: bins[b] = first slot of sub-bin b (the scatter advances it to its end)
     const uint4 v0 = reinterpret_cast<const uint4*>(bins)[2 * tid];
     const uint4 v1 = reinterpret_cast<const uint4*>(bins)[2 * tid + 1];
     const uint32_t cnt8[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
@@ -214,7 +214,7 @@ __device__ bool counting_rank_sort(unsigned long long* list, uint32_t kept, uint
 #pragma unroll
     for (int w = 0; w < kSelThreads / 32; ++w) base += (w < warp) ? warp_tot[w] : 0u;
 #pragma unroll
-    for (int j = 0; j < 8; ++j) start[j] = (start[j] + base) | (cnt8[j] << 16);
+    for (int j = 0; j < 8; ++j) start[j] += base;
     reinterpret_cast<uint4*>(bins)[2 * tid] = make_uint4(start[0], start[1], start[2], start[3]);
     reinterpret_cast<uint4*>(bins)[2 * tid + 1] = make_uint4(start[4], start[5], start[6], start[7]);
   }
@@ -222,15 +222,16 @@ __device__ bool counting_rank_sort(unsigned long long* list, uint32_t kept, uint
   for (uint32_t i = tid; i < kept; i += kSelThreads) {
     const unsigned long long e = list[i];
     const uint32_t k = (uint32_t)(e >> 32);
-    const uint32_t dst = (bins[sel_subbin(k, hi, scale)] & 0xFFFFu) + arr[i];
+    const uint32_t dst = atomicAdd(&bins[sel_subbin(k, hi, scale)], 1u);   // next free slot of the sub-bin
     s_key[dst] = k;
     s_val[dst] = (uint32_t)e;
   }
   __syncthreads();
   for (uint32_t d = tid; d < kept; d += kSelThreads) {
     const uint32_t k = s_key[d], v = s_val[d];
-    const uint32_t w = bins[sel_subbin(k, hi, scale)];
-    const uint32_t s0 = w & 0xFFFFu, g = w >> 16, last = s0 + g - 1u;
+    const uint32_t sb = sel_subbin(k, hi, scale);
+    const uint32_t s0 = bins[(int)sb - 1], end = bins[sb];        // after the scatter bins[b] is the END of sub-bin b
+    const uint32_t g = end - s0, last = end - 1u;
     uint32_t rank = s0;
 #pragma unroll
     for (uint32_t j = 0; j < 4u; ++j) {                           // the first four candidates without a loop
@@ -250,7 +251,152 @@ __device__ bool counting_rank_sort(unsigned long long* list, uint32_t kept, uint
   return true;
 }
 
-__global__ void __launch_bounds__(kSelThreads) select_kernel(const SelectParams p) {
+// ---- final pass in one go: selection and ordering share the sub-bin histogram ----
+// The 4-pass radix select, the compaction and counting_rank_sort each walk the candidate list; on a list of
+// ~2 top_n candidates they were 30 % / 10 % / 25 % of the final select.  Here the score-linear histogram over ALL n
+// candidates does the selection as well: the sub-bin b* in which the cumulative count crosses top_n holds the
+// top_n-th entry, every candidate of a sub-bin <= b* is scattered and ranked (top_n + the few extra entries of b*),
+// the rest is never touched again; the top_n-th key is then simply the key at position top_n - 1 of the ordered
+// list, and the boundary tie run ends where the key changes.  Same exactness argument as counting_rank_sort.
+// Returns the number of kept entries, ordered at list[0..kept) (NaN keys and padding last), *kth_out = the top_n-th
+// key (0xFFFFFFFF if n <= top_n); or -1 (nothing written outside shared memory) when a sub-bin <= b* is crowded
+// or the kept entries do not fit -- the caller then takes the radix-select path.
+__device__ int fused_select_sort(const SelectParams& p, int q, int n, unsigned long long* list, uint8_t* extra, int tid,
+                                 uint32_t* kth_out) {
+  const int sort_cap = p.sort_cap;
+  uint32_t* sm_keys = reinterpret_cast<uint32_t*>(list);          // [n <= 2 sort_cap] the candidates' keys
+  uint32_t* s_key = reinterpret_cast<uint32_t*>(extra);           // [sort_cap]
+  uint32_t* s_val = s_key + sort_cap;                             // [sort_cap]
+  uint32_t* bins = s_val + sort_cap + 4;                          // [kSelBins]; bins[-1] = 0
+  __shared__ uint32_t red_min[kSelThreads / 32], red_max[kSelThreads / 32], warp_tot[kSelThreads / 32];
+  __shared__ uint32_t sh_big, sh_bstar, sh_kprime, sh_end;
+  const int lane = tid & 31, warp = tid >> 5;
+  *kth_out = 0xFFFFFFFFu;
+  if (n <= 0) return 0;
+  const uint32_t k = (uint32_t)(p.k < (int64_t)n ? p.k : (int64_t)n);   // >= 1
+  reinterpret_cast<uint4*>(bins)[2 * tid] = make_uint4(0u, 0u, 0u, 0u);
+  reinterpret_cast<uint4*>(bins)[2 * tid + 1] = make_uint4(0u, 0u, 0u, 0u);
+  if (tid == 0) { sh_big = 0u; bins[-1] = 0u; sh_bstar = (uint32_t)(kSelBins - 1); sh_kprime = (uint32_t)n; }
+  uint32_t kmin = 0xFFFFFFFFu, kmax = 0u;                         // over the keys of real scores
+  for (int i = tid; i < n; i += kSelThreads) {
+    const uint32_t key = (uint32_t)(load_entry(p, q, i) >> 32);
+    sm_keys[i] = key;
+    kmin = min(kmin, key);
+    kmax = max(kmax, key == kNanKey ? 0u : key);
+  }
+  kmin = __reduce_min_sync(0xffffffffu, kmin);
+  kmax = __reduce_max_sync(0xffffffffu, kmax);
+  if (lane == 0) { red_min[warp] = kmin; red_max[warp] = kmax; }
+  __syncthreads();
+#pragma unroll
+  for (int w = 0; w < kSelThreads / 32; ++w) {
+    kmin = min(kmin, red_min[w]);
+    kmax = max(kmax, red_max[w]);
+  }
+  float hi = 0.0f, scale = 0.0f;
+  if (kmax > kmin) {                                              // two distinct real scores; +-inf ends clamped
+    hi = fminf(sel_key_score(kmin), 3.4028234664e38f);
+    const float lo = fmaxf(sel_key_score(kmax), -3.4028234664e38f);
+    // real scores end in sub-bin kSelBins - 2: the last one is left to the NaN keys -- the padding of merged lists,
+    // hundreds of entries.  When the lists hold just top_n real entries the top_n-th is the worst real score, and
+    // sharing its sub-bin with the padding would make that sub-bin "crowded" for every query.
+    if (hi > lo) scale = (float)(kSelBins - 2) / (hi - lo);
+  }
+  if (!(scale <= 3.4028234664e38f)) scale = 0.0f;
+  for (int i = tid; i < n; i += kSelThreads) atomicAdd(&bins[sel_subbin(sm_keys[i], hi, scale)], 1u);
+  __syncthreads();
+  uint32_t cnt8[8], start[8];
+  {
+    const uint4 v0 = reinterpret_cast<const uint4*>(bins)[2 * tid];
+    const uint4 v1 = reinterpret_cast<const uint4*>(bins)[2 * tid + 1];
+    cnt8[0] = v0.x; cnt8[1] = v0.y; cnt8[2] = v0.z; cnt8[3] = v0.w;
+    cnt8[4] = v1.x; cnt8[5] = v1.y; cnt8[6] = v1.z; cnt8[7] = v1.w;
+    uint32_t sum = 0;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      start[j] = sum;
+      sum += cnt8[j];
+    }
+    uint32_t incl = sum;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+      const uint32_t o = __shfl_up_sync(0xffffffffu, incl, off);
+      if (lane >= off) incl += o;
+    }
+    if (lane == 31) warp_tot[warp] = incl;
+    __syncthreads();
+    uint32_t base = incl - sum;
+#pragma unroll
+    for (int w = 0; w < kSelThreads / 32; ++w) base += (w < warp) ? warp_tot[w] : 0u;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      start[j] += base;
+      // the sub-bin in which the cumulative count crosses k (exactly one: k >= 1 and k <= n)
+      if (start[j] < k && k <= start[j] + cnt8[j]) {
+        sh_bstar = (uint32_t)(8 * tid + j);
+        sh_kprime = start[j] + cnt8[j];
+      }
+    }
+    reinterpret_cast<uint4*>(bins)[2 * tid] = make_uint4(start[0], start[1], start[2], start[3]);
+    reinterpret_cast<uint4*>(bins)[2 * tid + 1] = make_uint4(start[4], start[5], start[6], start[7]);
+  }
+  __syncthreads();
+  const uint32_t bstar = sh_bstar, kprime = sh_kprime;            // kprime = entries of the sub-bins <= b*
+  {
+    uint32_t mx = 0;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) mx = max(mx, (uint32_t)(8 * tid + j) <= bstar ? cnt8[j] : 0u);
+    if (mx > (uint32_t)kSelGroupMax) sh_big = 1u;
+  }
+  __syncthreads();
+  if (sh_big != 0u || kprime > (uint32_t)sort_cap) return -1;     // uniform
+  // scatter: every candidate of a sub-bin <= b* takes the next free slot of its sub-bin
+  for (int i = tid; i < n; i += kSelThreads) {
+    const uint32_t key = sm_keys[i];
+    const uint32_t sb = sel_subbin(key, hi, scale);
+    if (sb <= bstar) {
+      const unsigned long long e = load_entry(p, q, i);           // second read: L1 / L2
+      const uint32_t dst = atomicAdd(&bins[sb], 1u);
+      s_key[dst] = key;
+      s_val[dst] = (uint32_t)e;
+    }
+  }
+  __syncthreads();                                                // sm_keys is dead: `list` takes the ordered entries
+  for (uint32_t d = tid; d < kprime; d += kSelThreads) {
+    const uint32_t key = s_key[d], v = s_val[d];
+    const uint32_t sb = sel_subbin(key, hi, scale);
+    const uint32_t s0 = bins[(int)sb - 1], end = bins[sb];        // after the scatter bins[b] is the END of sub-bin b
+    const uint32_t g = end - s0, last = end - 1u;
+    uint32_t rank = s0;
+#pragma unroll
+    for (uint32_t j = 0; j < 4u; ++j) {
+      const uint32_t at = min(s0 + j, last);
+      const uint32_t kk = s_key[at];
+      bool first = kk < key;
+      if (kk == key) first = s_val[at] < v;
+      rank += (j < g && first) ? 1u : 0u;
+    }
+    for (uint32_t j = 4u; j < g; ++j) {
+      const uint32_t kk = s_key[s0 + j];
+      rank += (kk < key || (kk == key && s_val[s0 + j] < v)) ? 1u : 0u;
+    }
+    list[rank] = ((unsigned long long)key << 32) | v;
+  }
+  if (tid == 0) sh_end = kprime;
+  __syncthreads();
+  uint32_t kth = 0xFFFFFFFFu;
+  if ((int64_t)n > p.k) {
+    // the top_n-th entry, and the end of its tie run: positions >= top_n all lie in sub-bin b*
+    kth = (uint32_t)(list[p.k - 1] >> 32);
+    for (uint32_t t = (uint32_t)p.k + tid; t < kprime; t += kSelThreads)
+      if ((uint32_t)(list[t] >> 32) > kth && (uint32_t)(list[t - 1] >> 32) <= kth) sh_end = t;
+  }
+  __syncthreads();
+  *kth_out = kth;
+  return (int)sh_end;
+}
+
+__global__ void __launch_bounds__(kSelThreads, 5) select_kernel(const SelectParams p) {
   extern __shared__ unsigned long long sm_list[];     // sort_cap entries
   __shared__ uint32_t hist[256];
   __shared__ uint32_t sh_prefix, sh_remaining, sh_kept;
@@ -283,7 +429,11 @@ __global__ void __launch_bounds__(kSelThreads) select_kernel(const SelectParams 
 
   // ---- the k-th smallest key ----
   uint32_t kth = 0xFFFFFFFFu;
-  if (n > p.k) {
+  int fast_kept = -1;
+  if (p.final_pass && p.rank_sort == 2 && n <= 2 * (int64_t)p.sort_cap)
+    fast_kept = fused_select_sort(p, q, (int)n, sm_list, reinterpret_cast<uint8_t*>(sm_list + p.sort_cap), tid, &kth);
+  if (fast_kept < 0) kth = 0xFFFFFFFFu;
+  if (fast_kept < 0 && n > p.k) {
     // short lists (the usual case) are cached once as 32-bit keys in the shared-memory list buffer,
     // so the four radix passes do not go back to L2
     uint32_t* sm_keys = reinterpret_cast<uint32_t*>(sm_list);
@@ -362,17 +512,19 @@ __global__ void __launch_bounds__(kSelThreads) select_kernel(const SelectParams 
   }
 
   // ---- keep everything that still can rank: key <= kth (ties at the boundary included) ----
-  if (tid == 0) sh_kept = 0u;
-  __syncthreads();
-  for (int64_t i = tid; i < n; i += kSelThreads) {
-    const unsigned long long e = load_entry(p, q, i);
-    if ((uint32_t)(e >> 32) <= kth && e != ~0ull) {
-      const uint32_t pos = atomicAdd(&sh_kept, 1u);
-      if (pos < (uint32_t)p.sort_cap) sm_list[pos] = e;
+  if (fast_kept < 0) {
+    if (tid == 0) sh_kept = 0u;
+    __syncthreads();
+    for (int64_t i = tid; i < n; i += kSelThreads) {
+      const unsigned long long e = load_entry(p, q, i);
+      if ((uint32_t)(e >> 32) <= kth && e != ~0ull) {
+        const uint32_t pos = atomicAdd(&sh_kept, 1u);
+        if (pos < (uint32_t)p.sort_cap) sm_list[pos] = e;
+      }
     }
+    __syncthreads();
   }
-  __syncthreads();
-  const uint32_t kept = sh_kept;
+  const uint32_t kept = fast_kept >= 0 ? (uint32_t)fast_kept : sh_kept;
   if (kept > (uint32_t)p.sort_cap) {
     if (tid == 0) {
       atomicOr(&p.flags[q], 1u);
@@ -401,7 +553,9 @@ __global__ void __launch_bounds__(kSelThreads) select_kernel(const SelectParams 
   uint32_t pow2 = 1;
   while (pow2 < kept) pow2 <<= 1;
   const uint32_t n_sort = pow2 <= 4u * kSelThreads ? 4u * kSelThreads : 8u * kSelThreads;
-  if (p.rank_sort && counting_rank_sort(sm_list, kept, reinterpret_cast<uint8_t*>(sm_list + p.sort_cap), p.sort_cap, tid)) {
+  if (fast_kept >= 0) {
+    // selected and ordered in one go
+  } else if (p.rank_sort && counting_rank_sort(sm_list, kept, reinterpret_cast<uint8_t*>(sm_list + p.sort_cap), p.sort_cap, tid)) {
     // ordered by sub-bin + in-bin rank
   } else if (pow2 <= n_sort && (uint32_t)p.sort_cap >= n_sort) {
     // up to 2048 entries (top_n <= ~1000 with its ties, the usual case): registers + warp shuffles
@@ -676,8 +830,13 @@ int launch_select(Ctx* c, const SelectArgs& a, cudaStream_t st) {
     const char* e = getenv("DVL_SELECT_BITONIC");
     return e != nullptr && e[0] == '1';
   }();
-  p.rank_sort = (a.final_pass && a.sort_cap <= 4096 && !bitonic_only) ? 1 : 0;
-  if (p.rank_sort) smem += (size_t)a.sort_cap * 8 + (size_t)kSelBins * 4 + (size_t)a.sort_cap * 2;
+  // DVL_SELECT_FUSED=0: radix select + compaction + counting sort (the path fused_select_sort falls back to)
+  static const bool fused_off = [] {
+    const char* e = getenv("DVL_SELECT_FUSED");
+    return e != nullptr && e[0] == '0';
+  }();
+  p.rank_sort = (a.final_pass && a.sort_cap <= 4096 && !bitonic_only) ? (fused_off ? 1 : 2) : 0;
+  if (p.rank_sort) smem += (size_t)a.sort_cap * 8 + (size_t)(kSelBins + 4) * 4;
   if (!c->select_attr_set) {
     DVL_CUDA(c, cudaFuncSetAttribute(select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 16384 * 8));
     c->select_attr_set = true;
