@@ -397,6 +397,11 @@ constexpr int kBinsPerThread = kSubBins / kSortThreads2;      // 8 consecutive s
 // sub-bin sorted entries as two 32-bit arrays, sub-bins (+ one sentinel word in front), ranked labels
 constexpr size_t kSortSmem = (size_t)kBucketCap * 8 + (size_t)(kSubBins + 4) * 4 + kBucketCap;
 
+// (Measured and not kept: a persistent form -- 5 CTAs per SM walking the (query, bucket) pairs, the next bucket's keys
+// requested into 8 registers per thread right after the current bucket's histogram pass so that they arrive during
+// its scan / scatter / ranking.  By ncu a third of this kernel's samples sit on the first use of the loaded key, yet
+// the persistent kernel ran 0.262 instead of 0.245 ms: five independent CTAs per SM in different phases already
+// overlap that wait, and the one-CTA-per-bucket grid balances the tail better.)
 // The kernel keeps nothing per entry in registers between its phases: every phase is a short strided loop over
 // the bucket that re-reads what it needs (the bucket's entries from L1/L2, the rest from shared memory).  An
 // earlier version held 16 entries per thread in registers across the phases; fully unrolled it executed 2.5x the
